@@ -1,0 +1,245 @@
+/*
+ * ub200.h -- C ABI of the B200-native uncertainty rendering-and-scoring hot path.
+ *
+ * Drop-in boundary for the hot path of AaltoML/uncertainty-nerf-gs (the "reference";
+ * citations are file:line under /root/reference/nerfuncertainty).  The reference is 100 %
+ * Python and has no FFI of its own: this path sits behind its Python plugin surface
+ * (model get_outputs dicts, nerfuncertainty.metrics.ause / auce).  Each entry point below
+ * replaces the torch / numpy arithmetic of the cited reference lines; the Python host layer
+ * (uncertainty_nerf_gs_b200/) binds them with ctypes and mirrors the reference interface.
+ * INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - the caller allocates all outputs and the workspace; *_workspace_bytes() is the query.
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising; no global mutable state, no internal threads; re-entrant across
+ *     streams and devices (uses the caller's current device).
+ *   - return value: UB_OK (0) or a negative ub_status; ub_last_error() returns a
+ *     thread-local message for the last failing call on this thread.
+ *   - built for sm_100a only; there is no CPU path.
+ */
+#ifndef UB200_H_
+#define UB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UB_ABI_VERSION 1
+
+typedef enum ub_status {
+  UB_OK = 0,
+  UB_ERR_BAD_ARG = -1,      /* null pointer, negative size, inconsistent arguments        */
+  UB_ERR_UNSUPPORTED = -2,  /* shape / alignment / option not supported by this build       */
+  UB_ERR_WORKSPACE = -3,    /* workspace null or smaller than *_workspace_bytes()           */
+  UB_ERR_LAUNCH = -4        /* CUDA reported an error while enqueuing                       */
+} ub_status;
+
+int ub_abi_version(void);
+const char* ub_last_error(void);
+/* SM count of the current device (grid sizing is a multiple of it). */
+int ub_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (A1) Per-ray front-to-back compositing with the variance term.
+ * Replaces, for one batch of rays downstream of the field:
+ *   RaySamples.get_weights          models/laplace/laplace_model.py:47-62 (in-repo restatement),
+ *                                   called models/activenerfacto/activenerfacto_model.py:94
+ *   renderer_rgb/depth/expected/acc models/activenerfacto/activenerfacto_model.py:98-102
+ *   beta NaN guard + Sum w^2 beta    models/activenerfacto/activenerfacto_model.py:105-107,
+ *                                   models/laplace/laplace_model.py:478-480
+ *   depth variance                  models/activenerfacto/activenerfacto_model.py:111-112
+ * Inputs are [num_rays, num_samples] row-major float32 (rgb: [num_rays, num_samples, 3]).
+ * Outputs are [num_rays] float32 (rgb: [num_rays, 3]); any output pointer may be NULL.
+ * ---------------------------------------------------------------------------------------- */
+enum {
+  UB_BG_LAST_SAMPLE = 0,  /* nerfacto default: background = colour of the last sample        */
+  UB_BG_NONE = 1,         /* "random" at eval: return the unblended sum                       */
+  UB_BG_FIXED = 2         /* fixed colour in background_rgb                                   */
+};
+enum {
+  UB_BETA_RAW = 0,        /* nerfacto-laplace: beta used as is                                */
+  UB_BETA_NAN_GUARD = 1   /* active-nerfacto: if any NaN in the chunk, beta = nan_to_num(beta) */
+};
+
+typedef struct ub_composite_rays_args {
+  const float* density;      /* [R,S]                                                        */
+  const float* deltas;       /* [R,S]                                                        */
+  const float* starts;       /* [R,S]                                                        */
+  const float* ends;         /* [R,S]                                                        */
+  const float* rgb;          /* [R,S,3]                                                      */
+  const float* beta;         /* [R,S] per-sample variance (field "rgb_var"); may be NULL      */
+  int64_t num_rays;          /* R >= 0                                                       */
+  int32_t num_samples;       /* S >= 1                                                       */
+  int32_t background_mode;   /* UB_BG_*                                                      */
+  float background_rgb[3];   /* used when background_mode == UB_BG_FIXED                     */
+  int32_t beta_mode;         /* UB_BETA_*                                                    */
+  int64_t rays_per_chunk;    /* eval chunk (reference: 1 << 15); <= 0 means one chunk.       *
+                              * Chunk-wide reductions (clip bounds of the expected depth,    *
+                              * the beta NaN guard) are evaluated per chunk, as the          *
+                              * reference's chunk loop does.                                 */
+  int32_t eval_mode;         /* 1: nan_to_num(rgb) in, clamp [0,1] out (not self.training)   */
+  float* out_rgb;            /* [R,3]                                                        */
+  float* out_accumulation;   /* [R]                                                          */
+  float* out_depth;          /* [R] median depth                                             */
+  float* out_expected_depth; /* [R]                                                          */
+  float* out_rgb_var;        /* [R]                                                          */
+  float* out_rgb_std;        /* [R]                                                          */
+  float* out_depth_var;      /* [R]                                                          */
+  float* out_depth_std;      /* [R]                                                          */
+  float* out_weights;        /* [R,S] optional: the volume-rendering weights                 */
+} ub_composite_rays_args;
+
+size_t ub_composite_rays_workspace_bytes(int64_t num_rays, int64_t rays_per_chunk);
+int ub_composite_rays(const ub_composite_rays_args* args, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* Same renderers driven by given weights instead of densities:
+ *   prop_depth_i   models/activenerfacto/activenerfacto_model.py:150-151
+ *   depth / depth_var / expected_depth / accumulation from the averaged sampled weights,
+ *                  models/laplace/laplace_model.py:509-521
+ * Any output may be NULL. */
+typedef struct ub_render_weights_args {
+  const float* weights;      /* [R,S] */
+  const float* starts;       /* [R,S] */
+  const float* ends;         /* [R,S] */
+  int64_t num_rays;
+  int32_t num_samples;
+  int64_t rays_per_chunk;
+  float* out_accumulation;
+  float* out_depth;
+  float* out_expected_depth;
+  float* out_depth_var;
+  float* out_depth_std;
+} ub_render_weights_args;
+
+size_t ub_render_weights_workspace_bytes(int64_t num_rays, int64_t rays_per_chunk);
+int ub_render_weights(const ub_render_weights_args* args, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (B) Fused per-pixel mean / variance across K ensemble members or MC-dropout passes.
+ * Replaces torch.stack(...).mean(0) / .std(0).mean(-1) / .var(0).mean(-1):
+ *   models/mcdropout/mcdropout_models.py:121-126
+ *   models/ensemble/ensemble_pipeline.py:159-190
+ * members_host: HOST array of num_members DEVICE pointers, each [num_pixels, channels] float32
+ * (no stacked copy is made).  out_mean [num_pixels, channels]; out_spread [num_pixels]:
+ * unbiased std (spread_mode 1) or unbiased variance (spread_mode 2) over members, averaged
+ * over channels; spread_mode 0 / out_spread NULL skips it.
+ * ---------------------------------------------------------------------------------------- */
+enum { UB_SPREAD_NONE = 0, UB_SPREAD_STD = 1, UB_SPREAD_VAR = 2 };
+#define UB_MAX_MEMBERS 64
+
+int ub_reduce_members(const float* const* members_host, int32_t num_members, int64_t num_pixels,
+                      int32_t channels, int32_t spread_mode, float* out_mean, float* out_spread,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (C1) Metric prologue, NLL and AUCE interval histogram for a batch of images (segments).
+ * Replaces scripts/eval_uncertainty.py:323-333 (se / ae / var), :404-412 (NLL), and the 99
+ * interval-coverage passes of metrics/auce.py:18-28.
+ * pred, target: [total_pixels, channels]; std: [total_pixels] (one sigma per pixel, shared by
+ * the channels, as eval_uncertainty.py:371-374 repeats it).  seg_offsets_host: HOST array of
+ * num_segments+1 pixel offsets (segment s = [off[s], off[s+1])).
+ * z_values: DEVICE [num_z] float64, strictly decreasing (norm.ppf(1 - alpha/2)).
+ * Outputs: out_sq_err / out_abs_err / out_var [total_pixels] (may be NULL);
+ * out_sums [num_segments, UB_PROLOGUE_NSUMS] float64:
+ *     0 sum(se) 1 sum(ae) 2 sum(var) 3 sum(nll over pixels and channels) 4 sum(interval sigma)
+ * out_hist [num_segments, num_z + 1] int64: hist[c] = number of (pixel, channel) elements
+ *     whose interval predicate  t >= m - z_k s  &&  t <= m + z_k s  (float64, NumPy >= 2
+ *     promotion) holds for exactly the first c thresholds; coverage count at k = sum_{c>k} hist[c].
+ * ---------------------------------------------------------------------------------------- */
+#define UB_PROLOGUE_NSUMS 5
+
+typedef struct ub_score_prologue_args {
+  const float* pred;
+  const float* target;
+  const float* std;
+  int32_t channels;               /* 1 or 3 */
+  int32_t num_segments;
+  const int64_t* seg_offsets_host;
+  float nll_min_std;              /* eps of negative_gaussian_loglikelihood */
+  int32_t sigma_from_var;         /* 1: interval sigma = sqrt(std*std) as eval_uncertainty.py:371 (rgb); *
+                                   * 0: sigma = std (depth, eval_uncertainty.py:612-614)                */
+  const double* z_values;
+  int32_t num_z;                  /* <= 127 */
+  float* out_sq_err;
+  float* out_abs_err;
+  float* out_var;
+  double* out_sums;
+  int64_t* out_hist;
+} ub_score_prologue_args;
+
+/* max_segment_len: length of the longest segment (workspace scales with it, not with the total). */
+size_t ub_score_prologue_workspace_bytes(int32_t num_segments, int64_t max_segment_len, int32_t num_z);
+int ub_score_prologue(const ub_score_prologue_args* args, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (C2) Per-image segmented stable radix sort and cumulative-error scans for AUSE.
+ * Replaces torch.sort + the 2 x 100 slice means of metrics/ause.py:10-34.
+ * Ordering contract == torch.sort(stable=True) on float32: ascending, ties keep ascending
+ * original index, -0.0 == +0.0, every NaN after +inf.
+ * keys [total] float32 segmented by seg_offsets_host (num_segments+1, HOST).
+ * out_sorted_keys [total] (may be NULL); out_perm [total] int32: index *within its segment* of
+ * the element at each sorted position (NULL for a keys-only sort).
+ * ---------------------------------------------------------------------------------------- */
+size_t ub_segmented_sort_workspace_bytes(int32_t num_segments, int64_t total, int64_t max_segment_len,
+                                         int32_t with_perm);
+int ub_segmented_sort(const float* keys, int32_t num_segments, const int64_t* seg_offsets_host,
+                      float* out_sorted_keys, int32_t* out_perm, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* Prefix sums at cut points, float64 accumulation:
+ *   out_sums[s, v, c] = sum_{i < cuts[s, c]} values_v[off[s] + (perm ? perm[off[s] + i] : i)]
+ * values_host: HOST array of num_values DEVICE pointers [total] float32; perm (DEVICE, may be
+ * NULL) as produced by ub_segmented_sort; cuts_host: HOST [num_segments, num_cuts] int64, each
+ * in [0, segment length]; out_sums: DEVICE [num_segments, num_values, num_cuts] float64. */
+size_t ub_cut_prefix_sums_workspace_bytes(int32_t num_segments, int64_t max_segment_len,
+                                          int32_t num_values, int32_t num_cuts);
+int ub_cut_prefix_sums(const float* const* values_host, int32_t num_values, const int32_t* perm,
+                       int32_t num_segments, const int64_t* seg_offsets_host,
+                       const int64_t* cuts_host, int32_t num_cuts, double* out_sums,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (A3) Last-layer diagonal-Laplace MC moments.
+ * Replaces NerfactoLaplaceField.sample_laplace, models/laplace/laplace_field.py:528-568, for a
+ * linear head out = act(x W^T + b): for each of n_samples parameter draws theta_s (rows of
+ * sampled_params [n_samples, out_dim*hidden + out_dim], weight row-major then bias -- the
+ * order of torch parameters_to_vector) accumulate E[y] and E[y^2]; sigma2 = E[y^2] - E[y]^2.
+ * activation: 0 identity, 1 sigmoid (rgb head, :468-476), 2 trunc_exp == exp (density head,
+ * :331-339).  out_mean / out_sigma2 [num_points, out_dim]; out_mean2 optional.
+ * ---------------------------------------------------------------------------------------- */
+enum { UB_ACT_IDENTITY = 0, UB_ACT_SIGMOID = 1, UB_ACT_EXP = 2 };
+
+int ub_laplace_ll_moments(const float* x, int64_t num_points, int32_t hidden, int32_t out_dim,
+                          const float* sampled_params, int32_t n_samples, int32_t activation,
+                          float* out_mean, float* out_mean2, float* out_sigma2, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (A2) Alpha compositing over pre-binned per-tile splat lists (16x16 tiles).
+ * Replaces the four gsplat.rasterize_gaussians passes of
+ * models/activesplatfacto/activesplatfacto_model.py:260-356 by one fused pass over
+ * rgb[3] + beta[1] + depth[1] and a second pass for the depth variance.
+ * xys [G,2], conics [G,3], opacities [G], colors [G, channels] float32;
+ * gaussian_ids [num_intersects] int32 sorted by (tile, depth); tile_bins [tiles, 2] int32.
+ * out [H, W, channels] = sum_i c_i alpha_i T_i + T_final * background; out_alpha [H, W] = 1 - T_final.
+ * ---------------------------------------------------------------------------------------- */
+#define UB_TILE 16
+#define UB_MAX_SPLAT_CHANNELS 8
+
+int ub_composite_tiles(const float* xys, const float* conics, const float* opacities,
+                       const float* colors, int32_t channels, const int32_t* gaussian_ids,
+                       const int32_t* tile_bins, int32_t img_height, int32_t img_width,
+                       const float* background_host, float* out, float* out_alpha, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UB200_H_ */

@@ -1,0 +1,112 @@
+"""CPU: host-side logic of the product package (no kernels): cut counts, z table, the numpy tails of
+ause / auce fed with exact intermediate results, argument validation, binning, and the failure mode when
+no CUDA device / library is present (the product path must fail loudly, never fall back)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics as om
+from uncertainty_nerf_gs_b200 import binning, metrics, ops, synthetic
+
+
+def test_cut_counts_follow_reference_float64_truncation():
+    n = 640000
+    cuts = metrics.ause_cut_counts(n)
+    assert cuts.tolist() == om.ause_cut_counts(n)
+    naive = np.array([n * (100 - i) // 100 for i in range(100)])
+    assert (cuts != naive).sum() > 0          # SURVEY hard part 2: integer arithmetic would be wrong
+    assert cuts[31] == 441599
+    assert cuts[0] == n and (np.diff(cuts) <= 0).all()
+
+
+def test_z_table_matches_reference_expression():
+    z = metrics.z_values_host()
+    assert z.shape == (99,) and (np.diff(z) < 0).all()
+    assert np.array_equal(z, om.auce_z_values())
+    assert z[0] == pytest.approx(2.5758293035489004) and z[-1] == pytest.approx(0.012533469508069276)
+
+
+@pytest.mark.parametrize("err_type", ["mae", "mse", "rmse"])
+@pytest.mark.parametrize("n", [10007, 57])
+def test_ause_host_tail_reproduces_oracle_bit_for_bit(err_type, n):
+    """Feed the numpy tail with float64 prefix sums computed on CPU: everything the device returns is a
+    float64 sum, so this pins the host half of the drop-in exactly."""
+    g = torch.Generator().manual_seed(n)
+    unc = torch.clamp(0.1 * torch.rand(n, generator=g), min=0.03) ** 2
+    err = torch.rand(n, generator=g)
+    cuts = metrics.ause_cut_counts(n)
+    es = torch.sort(err, stable=True).values
+    eb = err[torch.sort(unc, stable=True).indices]
+
+    def sums(v):
+        c = torch.cat([torch.zeros(1, dtype=torch.float64), v.double().cumsum(0)])
+        return c[cuts].numpy()
+
+    r, e, v, a = metrics._ause_tail(metrics._prefix_means(sums(es), cuts, err_type),
+                                    metrics._prefix_means(sums(eb), cuts, err_type))
+    r0, e0, v0, a0 = om.ause(unc, err, err_type)
+    assert np.array_equal(r, r0)
+    np.testing.assert_allclose(e, e0, rtol=3e-7, equal_nan=True)   # torch's fp32 mean vs fp64 sum / n
+    np.testing.assert_allclose(v, v0, rtol=3e-7, equal_nan=True)
+    np.testing.assert_allclose(a, a0, rtol=1e-5, atol=1e-9, equal_nan=True)
+    assert e.dtype == np.asarray(e0).dtype and v.dtype == v0.dtype and type(a) is type(a0)
+
+
+def test_auce_host_tail_from_exact_histogram():
+    g = torch.Generator().manual_seed(0)
+    m = torch.rand(5000, 3, generator=g).numpy()
+    s = np.clip(0.1 * torch.rand(5000, 3, generator=g).numpy(), 0.03, None).astype(np.float32)
+    t = (m + s * torch.randn(5000, 3, generator=g).numpy()).astype(np.float32)
+    ref = om.auce(m, s, t)
+    z = metrics.z_values_host()
+    inside = np.stack([(t >= m - zk * s) & (t <= m + zk * s) for zk in z])     # float64 promotion
+    counts = inside.sum(axis=0).ravel()                                        # leading thresholds satisfied
+    assert (np.diff(inside.astype(np.int8), axis=0) <= 0).all()                # monotone in k
+    hist = np.bincount(counts, minlength=100)
+    out = metrics._auce_from_hist(hist, float(s.astype(np.float64).sum()), float(m.size), z)
+    assert list(out.keys()) == list(ref.keys())
+    assert np.array_equal(out["coverage_values"], ref["coverage_values"])
+    np.testing.assert_allclose(out["avg_length_values"], ref["avg_length_values"], rtol=1e-6)
+    for k in ("auc_abs_error_values", "auc_length_values", "auc_neg_error_values"):
+        np.testing.assert_allclose(out[k], ref[k], rtol=1e-6, atol=1e-12)
+
+
+def test_ops_refuse_cpu_tensors_and_bad_shapes():
+    z = torch.zeros(4, 48)
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        ops.composite_rays(z, z, z, z, torch.zeros(4, 48, 3))
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        ops.reduce_members([torch.zeros(4, 3)], "std")
+    with pytest.raises(ValueError):
+        metrics.ause(torch.zeros(4), torch.zeros(5))
+    with pytest.raises(ValueError):
+        metrics.ause(torch.zeros(4), torch.zeros(4), "l1")
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from uncertainty_nerf_gs_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libub200.so")
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_binning_ranges_and_order():
+    sc = synthetic.splat_scene(300, 50, 70, seed=1)
+    ids, bins = binning.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], 50, 70)
+    tx, ty = binning.tile_grid(50, 70)
+    assert bins.shape == (tx * ty, 2) and ids.dtype == torch.int32
+    assert int(bins[0, 0]) == 0 and int(bins[-1, 1]) == ids.numel()
+    assert bool((bins[1:, 0] == bins[:-1, 1]).all())
+    # a Gaussian is listed in a tile iff its +-radius box overlaps the tile rectangle rule of gsplat
+    g0 = int(ids[0])
+    assert sc["radii"][g0] > 0
+
+
+def test_synthetic_shapes():
+    inp = synthetic.ray_samples(100, 48, seed=0)
+    assert inp["rgb"].shape == (100, 48, 3) and inp["beta"].shape == (100, 48, 1)
+    assert bool((inp["ends"] > inp["starts"]).all())
+    p, s, g = synthetic.scoring_image(8, 9)
+    assert p.shape == (8, 9, 3) and s.shape == (8, 9, 1) and float(s.min()) == pytest.approx(0.03)

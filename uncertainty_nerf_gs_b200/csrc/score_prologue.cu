@@ -1,0 +1,313 @@
+// (C1) Metric prologue + NLL + AUCE interval histogram, one pass over (pred, target, std).
+//
+// Reference arithmetic (file:line under /root/reference/nerfuncertainty):
+//   scripts/eval_uncertainty.py:323-333   se = sum_c (p-t)^2, ae = sum_c |p-t|, var = std^2
+//   scripts/eval_uncertainty.py:404-412   -Normal(p, max(std, eps)).log_prob(t)
+//   scripts/eval_uncertainty.py:371-378   sigma = sqrt(var) repeated over channels -> auce()
+//   metrics/auce.py:18-28                 99 x count(t >= m - z s  and  t <= m + z s)
+//
+// The 99 coverage passes collapse into one histogram: the interval predicate is monotone in z
+// (z decreasing in k), so every element is characterised by the number c of leading thresholds
+// it satisfies; coverage_k = #{c > k}.  c is located with a float32 estimate and then *verified*
+// with the exact float64 predicate (NumPy >= 2 promotion: np.float64 z * float32 sigma ->
+// float64, no fused multiply-add); if the verification fails the element falls back to an exact
+// float64 binary search, so the counts are bit-exact regardless of the estimate.
+// Sums are accumulated in float64 per block and combined in a fixed order (deterministic).
+#include "ub_common.cuh"
+
+namespace ub {
+
+constexpr int kPrologueThreads = 256;
+constexpr int kPixPerThread = 4;
+constexpr int kPixPerBlock = kPrologueThreads * kPixPerThread;
+constexpr int kMaxZ = 127;
+
+struct PrologueParams {
+  const float* pred;
+  const float* target;
+  const float* std;
+  int channels;
+  int num_segments;
+  const long long* seg_offsets;  // device copy
+  float nll_min_std;
+  int sigma_from_var;
+  const double* z;
+  int num_z;
+  float* o_se;
+  float* o_ae;
+  float* o_var;
+  double* partial;  // [num_segments][blocks_per_seg][NSUMS]
+  int blocks_per_seg;
+  unsigned long long* hist;  // [num_segments][num_z + 1]
+  int vec_ok;
+};
+
+__device__ __forceinline__ bool interval_holds(double z, float m, float s, float t) {
+  const double zs = __dmul_rn(z, (double)s);
+  const double lo = __dsub_rn((double)m, zs);
+  const double hi = __dadd_rn((double)m, zs);
+  const double td = (double)t;
+  return td >= lo && td <= hi;
+}
+
+// number of leading thresholds (z strictly decreasing) whose interval contains t
+__device__ __forceinline__ int coverage_count(const double* __restrict__ zs_d,
+                                              const float* __restrict__ zs_f, int nz, float m,
+                                              float s, float t) {
+  // float32 estimate: count of z_k >= |t - m| / s
+  const float r = fabsf(t - m) / s;
+  int lo = 0, hi = nz;  // invariant: z[lo-1] >= r (or lo == 0), z[hi] < r (or hi == nz)
+  if (r == r) {
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (zs_f[mid] >= r) lo = mid + 1; else hi = mid;
+    }
+  } else {
+    lo = 0;  // NaN ratio (0/0, NaN inputs): let the exact check decide
+  }
+  int c = lo;
+  const bool left_ok = c == 0 || interval_holds(zs_d[c - 1], m, s, t);
+  const bool right_ok = c == nz || !interval_holds(zs_d[c], m, s, t);
+  if (left_ok && right_ok) return c;
+  // exact float64 binary search (predicate true on a prefix of k)
+  lo = 0;
+  hi = nz;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (interval_holds(zs_d[mid], m, s, t)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const PrologueParams p) {
+  __shared__ double z_d[kMaxZ + 1];
+  __shared__ float z_f[kMaxZ + 1];
+  __shared__ unsigned int hist_s[kPrologueThreads / 32][kMaxZ + 1];
+  __shared__ double red[kPrologueThreads / 32][UB_PROLOGUE_NSUMS];
+
+  const int seg = blockIdx.y;
+  const long long seg_lo = p.seg_offsets[seg], seg_hi = p.seg_offsets[seg + 1];
+  const long long blk_lo = seg_lo + (long long)blockIdx.x * kPixPerBlock;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < p.num_z; i += blockDim.x) {
+    z_d[i] = p.z[i];
+    z_f[i] = (float)p.z[i];
+  }
+  for (int i = threadIdx.x; i < (kPrologueThreads / 32) * (kMaxZ + 1); i += blockDim.x)
+    (&hist_s[0][0])[i] = 0u;
+  __syncthreads();
+
+  double sums[UB_PROLOGUE_NSUMS] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (blk_lo < seg_hi) {
+    const long long pix0 = blk_lo + (long long)threadIdx.x * kPixPerThread;
+    const int npix = (int)max(0LL, min((long long)kPixPerThread, seg_hi - pix0));
+    if (npix > 0) {
+      float pr[kPixPerThread * C], tg[kPixPerThread * C], sd[kPixPerThread];
+      const bool vec = p.vec_ok && npix == kPixPerThread && (pix0 & 3) == 0;
+      if (vec) {
+        const float4* a = reinterpret_cast<const float4*>(p.pred + pix0 * C);
+        const float4* b = reinterpret_cast<const float4*>(p.target + pix0 * C);
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          const float4 x = a[j], y = b[j];
+          pr[4 * j] = x.x; pr[4 * j + 1] = x.y; pr[4 * j + 2] = x.z; pr[4 * j + 3] = x.w;
+          tg[4 * j] = y.x; tg[4 * j + 1] = y.y; tg[4 * j + 2] = y.z; tg[4 * j + 3] = y.w;
+        }
+        const float4 s4 = *reinterpret_cast<const float4*>(p.std + pix0);
+        sd[0] = s4.x; sd[1] = s4.y; sd[2] = s4.z; sd[3] = s4.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < kPixPerThread * C; ++i) {
+          const bool ok = i < npix * C;
+          pr[i] = ok ? p.pred[pix0 * C + i] : 0.f;
+          tg[i] = ok ? p.target[pix0 * C + i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < kPixPerThread; ++i) sd[i] = i < npix ? p.std[pix0 + i] : 1.f;
+      }
+      float se[kPixPerThread], ae[kPixPerThread], vr[kPixPerThread];
+#pragma unroll
+      for (int px = 0; px < kPixPerThread; ++px) {
+        const float sdv = sd[px];
+        const float var = __fmul_rn(sdv, sdv);
+        const float sigma = p.sigma_from_var ? sqrtf(var) : sdv;
+        const float nll_s = fmaxf(sdv, p.nll_min_std);  // torch.maximum propagates NaN:
+        const float s_nll = sdv != sdv ? sdv : nll_s;
+        const float two_var = 2.0f * __fmul_rn(s_nll, s_nll);
+        const float log_s = logf(s_nll);
+        float se_px = 0.f, ae_px = 0.f;
+        double nll_px = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float m = pr[px * C + c], t = tg[px * C + c];
+          const float d = m - t;
+          const float d2 = __fmul_rn(d, d);
+          se_px = c == 0 ? d2 : __fadd_rn(se_px, d2);
+          ae_px = c == 0 ? fabsf(d) : __fadd_rn(ae_px, fabsf(d));
+          if (px < npix) {
+            const float dt = t - m;
+            const float nll = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(dt, dt), two_var), log_s),
+                                        0.91893853320467274178f);
+            nll_px += (double)nll;
+            const int cnt = coverage_count(z_d, z_f, p.num_z, m, sigma, t);
+            atomicAdd(&hist_s[warp][cnt], 1u);
+          }
+        }
+        se[px] = se_px;
+        ae[px] = ae_px;
+        vr[px] = var;
+        if (px < npix) {
+          sums[0] += (double)se_px;
+          sums[1] += (double)ae_px;
+          sums[2] += (double)var;
+          sums[3] += nll_px;
+          sums[4] += (double)sigma;
+        }
+      }
+      if (vec) {
+        if (p.o_se) *reinterpret_cast<float4*>(p.o_se + pix0) = make_float4(se[0], se[1], se[2], se[3]);
+        if (p.o_ae) *reinterpret_cast<float4*>(p.o_ae + pix0) = make_float4(ae[0], ae[1], ae[2], ae[3]);
+        if (p.o_var) *reinterpret_cast<float4*>(p.o_var + pix0) = make_float4(vr[0], vr[1], vr[2], vr[3]);
+      } else {
+#pragma unroll
+        for (int px = 0; px < kPixPerThread; ++px)
+          if (px < npix) {
+            if (p.o_se) p.o_se[pix0 + px] = se[px];
+            if (p.o_ae) p.o_ae[pix0 + px] = ae[px];
+            if (p.o_var) p.o_var[pix0 + px] = vr[px];
+          }
+      }
+    }
+  }
+
+  // block reduction of the float64 sums in a fixed order
+#pragma unroll
+  for (int j = 0; j < UB_PROLOGUE_NSUMS; ++j) {
+    double v = sums[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += shfl_xor_double(FULL_MASK, v, o);
+    if (lane == 0) red[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < UB_PROLOGUE_NSUMS) {
+    double v = 0.0;
+    for (int w = 0; w < kPrologueThreads / 32; ++w) v += red[w][threadIdx.x];
+    p.partial[((size_t)seg * p.blocks_per_seg + blockIdx.x) * UB_PROLOGUE_NSUMS + threadIdx.x] = v;
+  }
+  for (int c = threadIdx.x; c <= p.num_z; c += blockDim.x) {
+    unsigned int v = 0;
+    for (int w = 0; w < kPrologueThreads / 32; ++w) v += hist_s[w][c];
+    if (v) atomicAdd(&p.hist[(size_t)seg * (p.num_z + 1) + c], (unsigned long long)v);
+  }
+}
+
+// out_sums[seg][j] = sum over the segment's blocks in block order (deterministic)
+__global__ void prologue_finalize_kernel(const double* partial, int blocks_per_seg, double* out_sums) {
+  const int seg = blockIdx.x;
+  const int j = threadIdx.x;
+  if (j >= UB_PROLOGUE_NSUMS) return;
+  double v = 0.0;
+  for (int b = 0; b < blocks_per_seg; ++b)
+    v += partial[((size_t)seg * blocks_per_seg + b) * UB_PROLOGUE_NSUMS + j];
+  out_sums[(size_t)seg * UB_PROLOGUE_NSUMS + j] = v;
+}
+
+static long long max_seg_len(const int64_t* off, int n) {
+  long long m = 0;
+  for (int i = 0; i < n; ++i) m = off[i + 1] - off[i] > m ? off[i + 1] - off[i] : m;
+  return m;
+}
+
+struct PrologueLayout {
+  size_t off_offsets, off_partial, total;
+  int blocks_per_seg;
+};
+static PrologueLayout prologue_layout(int num_segments, long long max_len) {
+  PrologueLayout l{};
+  l.blocks_per_seg = (int)((max_len + kPixPerBlock - 1) / kPixPerBlock);
+  if (l.blocks_per_seg < 1) l.blocks_per_seg = 1;
+  l.off_offsets = 0;
+  l.off_partial = align_up((size_t)(num_segments + 1) * sizeof(long long), 256);
+  l.total = l.off_partial + (size_t)num_segments * l.blocks_per_seg * UB_PROLOGUE_NSUMS * sizeof(double);
+  return l;
+}
+
+}  // namespace ub
+
+extern "C" {
+
+size_t ub_score_prologue_workspace_bytes(int32_t num_segments, int64_t max_segment_len, int32_t num_z) {
+  (void)num_z;
+  if (num_segments < 1 || max_segment_len < 0) return 256;
+  return ub::prologue_layout(num_segments, max_segment_len).total;
+}
+
+int ub_score_prologue(const ub_score_prologue_args* a, void* workspace, size_t workspace_bytes,
+                      void* stream_v) {
+  using namespace ub;
+  UB_REQUIRE(a != nullptr, UB_ERR_BAD_ARG, "score_prologue: args is NULL");
+  UB_REQUIRE(a->channels == 1 || a->channels == 3, UB_ERR_UNSUPPORTED,
+             "score_prologue: channels must be 1 or 3 (got %d)", a->channels);
+  UB_REQUIRE(a->num_segments >= 1 && a->num_segments <= 65535 && a->seg_offsets_host != nullptr,
+             UB_ERR_BAD_ARG, "score_prologue: bad segments");
+  UB_REQUIRE(a->num_z >= 1 && a->num_z <= kMaxZ && a->z_values != nullptr, UB_ERR_BAD_ARG,
+             "score_prologue: num_z must be in [1, %d]", kMaxZ);
+  UB_REQUIRE(a->out_sums != nullptr && a->out_hist != nullptr, UB_ERR_BAD_ARG,
+             "score_prologue: out_sums / out_hist must be non-NULL");
+  const int64_t* off = a->seg_offsets_host;
+  for (int s = 0; s < a->num_segments; ++s)
+    UB_REQUIRE(off[s + 1] >= off[s] && off[s] >= 0, UB_ERR_BAD_ARG,
+               "score_prologue: segment offsets must be non-decreasing");
+  const long long total = off[a->num_segments];
+  UB_REQUIRE(total == 0 || (a->pred && a->target && a->std), UB_ERR_BAD_ARG,
+             "score_prologue: pred/target/std must be non-NULL");
+  const PrologueLayout lay = prologue_layout(a->num_segments, max_seg_len(off, a->num_segments));
+  UB_REQUIRE(workspace != nullptr && workspace_bytes >= lay.total, UB_ERR_WORKSPACE,
+             "score_prologue: workspace %zu B < required %zu B", workspace_bytes, lay.total);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  char* ws = static_cast<char*>(workspace);
+
+  if (cudaMemcpyAsync(ws + lay.off_offsets, off, (size_t)(a->num_segments + 1) * sizeof(int64_t),
+                      cudaMemcpyHostToDevice, stream) != cudaSuccess)
+    return check_launch("score_prologue offsets copy");
+  if (cudaMemsetAsync(a->out_hist, 0, (size_t)a->num_segments * (a->num_z + 1) * sizeof(int64_t),
+                      stream) != cudaSuccess)
+    return check_launch("score_prologue hist memset");
+
+  PrologueParams p{};
+  p.pred = a->pred;
+  p.target = a->target;
+  p.std = a->std;
+  p.channels = a->channels;
+  p.num_segments = a->num_segments;
+  p.seg_offsets = reinterpret_cast<const long long*>(ws + lay.off_offsets);
+  p.nll_min_std = a->nll_min_std;
+  p.sigma_from_var = a->sigma_from_var;
+  p.z = a->z_values;
+  p.num_z = a->num_z;
+  p.o_se = a->out_sq_err;
+  p.o_ae = a->out_abs_err;
+  p.o_var = a->out_var;
+  p.partial = reinterpret_cast<double*>(ws + lay.off_partial);
+  p.blocks_per_seg = lay.blocks_per_seg;
+  p.hist = reinterpret_cast<unsigned long long*>(a->out_hist);
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  bool vec_ok = al16(a->pred) && al16(a->target) && al16(a->std) && al16(a->out_sq_err) &&
+                al16(a->out_abs_err) && al16(a->out_var);
+  for (int s = 0; s < a->num_segments; ++s) vec_ok = vec_ok && (off[s] % 4 == 0);
+  p.vec_ok = vec_ok ? 1 : 0;
+
+  dim3 grid((unsigned)lay.blocks_per_seg, (unsigned)a->num_segments);
+  if (a->channels == 3)
+    score_prologue_kernel<3><<<grid, kPrologueThreads, 0, stream>>>(p);
+  else
+    score_prologue_kernel<1><<<grid, kPrologueThreads, 0, stream>>>(p);
+  int rc = check_launch("score_prologue");
+  if (rc != UB_OK) return rc;
+  prologue_finalize_kernel<<<a->num_segments, 32, 0, stream>>>(p.partial, lay.blocks_per_seg, a->out_sums);
+  return check_launch("score_prologue finalize");
+}
+
+}  // extern "C"

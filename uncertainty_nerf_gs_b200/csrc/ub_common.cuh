@@ -1,0 +1,117 @@
+// Shared device / host helpers for the ub200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <float.h>
+
+#include "../../include/ub200.h"
+
+namespace ub {
+
+// ---- host side: thread-local error record -------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);  // cudaPeekAtLastError -> UB_ERR_LAUNCH
+int sm_count();
+
+#define UB_REQUIRE(cond, code, ...)      \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::ub::set_error(__VA_ARGS__);      \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- device side ---------------------------------------------------------------------------
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// torch.nan_to_num with default arguments on float32: NaN -> 0, +-inf -> +-FLT_MAX.
+__device__ __forceinline__ float nan_to_num(float x) {
+  if (x != x) return 0.0f;
+  if (x == INFINITY) return FLT_MAX;
+  if (x == -INFINITY) return -FLT_MAX;
+  return x;
+}
+
+// Order-preserving float32 -> uint32 key matching torch.sort on float32:
+// -0.0 == +0.0, every NaN is the single largest key (ties broken by index => stable).
+__device__ __forceinline__ uint32_t sort_key_from_float(float f) {
+  if (f != f) return 0xFFFFFFFEu;
+  if (f == 0.0f) f = 0.0f;  // canonicalise -0.0
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ uint32_t order_key(float f) {  // monotone, no canonicalisation
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float order_key_inv(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+  return __uint_as_float(b);
+}
+
+__device__ __forceinline__ double shfl_double(unsigned mask, double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(mask, lo, src);
+  hi = __shfl_sync(mask, hi, src);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_xor_double(unsigned mask, double v, int lane_mask) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(mask, lo, lane_mask);
+  hi = __shfl_xor_sync(mask, hi, lane_mask);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_up_double(unsigned mask, double v, int delta) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(mask, lo, delta);
+  hi = __shfl_up_sync(mask, hi, delta);
+  return __hiloint2double(hi, lo);
+}
+
+// ---- mbarrier / bulk-copy (TMA) PTX wrappers -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk asynchronous copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst / src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+}  // namespace ub

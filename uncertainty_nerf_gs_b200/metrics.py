@@ -1,0 +1,215 @@
+"""Drop-in ``ause`` / ``auce`` (same signatures and return values as ``nerfuncertainty.metrics``) and the
+batched per-image scorer, running on the ub200 CUDA kernels.
+
+Mirrors reference ``nerfuncertainty/metrics/ause.py:7-44``, ``auce.py:10-57`` and
+``scripts/eval_uncertainty.py:306-402`` (``get_unc_metrics_rgb``).  The device does the O(N) work
+(stable segmented radix sort, float64 cut-point prefix sums, metric prologue, NLL, interval
+histogram); the O(100) tail (normalisation, trapezoid areas, dict assembly) stays on the host in
+numpy exactly as the reference computes it, so dtypes and rounding of the returned objects match.
+
+Ranking contract: ``torch.sort(stable=True)`` order (the reference's default unstable CPU sort is not
+reproducible under ties).  AUCE contract: NumPy >= 2 promotion (float64 interval arithmetic).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import scipy.stats
+import torch
+
+from . import ops
+
+Tensor = torch.Tensor
+
+if not hasattr(np, "trapz"):  # newer NumPy dropped the alias the reference calls
+    np.trapz = np.trapezoid  # type: ignore[attr-defined]
+
+_Z_CACHE: Dict[str, Tensor] = {}
+
+
+def _ratios() -> np.ndarray:
+    return np.linspace(0, 1, 100, endpoint=False)  # ause.py:8
+
+
+def ause_cut_counts(n: int) -> np.ndarray:
+    """``int((1 - r) * n)`` for the 100 removal ratios, evaluated in float64 with truncation exactly as
+    ause.py:16,30 does (NOT ``n * (100 - i) // 100``: the two differ at ~25 of 100 indices)."""
+    return np.array([int((1 - r) * n) for r in _ratios()], dtype=np.int64)
+
+
+def _alphas() -> List[np.float64]:
+    return list(np.arange(start=0.01, stop=1.0, step=0.01))  # auce.py:17
+
+
+def z_values_host() -> np.ndarray:
+    return np.array([scipy.stats.norm.ppf(1.0 - a / 2) for a in _alphas()], dtype=np.float64)  # auce.py:21-22
+
+
+def _z_table(device) -> Tensor:
+    key = str(device)
+    if key not in _Z_CACHE:
+        _Z_CACHE[key] = torch.from_numpy(z_values_host()).to(device)
+    return _Z_CACHE[key]
+
+
+def _prefix_means(sums: np.ndarray, cuts: np.ndarray, err_type: str) -> List[np.ndarray]:
+    """float32 value of ``err_sorted[:c].mean()`` (and ``torch.sqrt`` of it for rmse) from the float64
+    prefix sums; an empty slice gives NaN like torch."""
+    pts = []
+    for s, c in zip(sums, cuts):
+        m = np.float32(s / c) if c > 0 else np.float32(np.nan)
+        if err_type == "rmse":
+            m = np.sqrt(m)
+        pts.append(np.asarray(m, dtype=np.float32))
+    return pts
+
+
+def _ause_tail(oracle_pts: List[np.ndarray], by_unc_pts: List[np.ndarray]):
+    """ause.py:27-44 downstream of the slice means: normalise both curves by the common maximum and
+    integrate the gap.  Object types follow the reference (list of 0-d float32 arrays vs float64 array)."""
+    ratios = _ratios()
+    by_unc = np.zeros(len(ratios))
+    for i, v in enumerate(by_unc_pts):
+        by_unc[i] = v
+    max_val = max(max(oracle_pts), max(by_unc))
+    oracle_curve = np.array(oracle_pts / max_val)
+    by_unc = np.array(by_unc / max_val)
+    return ratios, oracle_curve, by_unc, np.trapz(by_unc - oracle_curve, ratios)
+
+
+def _check_err_type(err_type: str) -> None:
+    if err_type not in ("rmse", "mse", "mae"):
+        raise ValueError(f"err_type must be 'rmse', 'mse' or 'mae', got {err_type!r}")
+
+
+def ause(unc_vec: Tensor, err_vec: Tensor, err_type: str = "rmse"
+         ) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.float64]:
+    """Drop-in for ``nerfuncertainty.metrics.ause`` (ause.py:7-44): ``(ratio_removed, ause_err,
+    ause_err_by_var, ause)``.  ``unc_vec`` / ``err_vec`` are 1-D CUDA float32 tensors."""
+    _check_err_type(err_type)
+    if unc_vec.dim() != 1 or unc_vec.shape != err_vec.shape:
+        raise ValueError("unc_vec and err_vec must be 1-D tensors of equal length")
+    n = len(err_vec)
+    cuts = ause_cut_counts(n)[None, :]
+    err_sorted, _ = ops.segmented_sort(err_vec, [n], want_perm=False, want_keys=True)
+    _, perm = ops.segmented_sort(unc_vec, [n], want_perm=True, want_keys=False)
+    s_oracle = ops.cut_prefix_sums([err_sorted], None, [n], cuts)
+    s_by_unc = ops.cut_prefix_sums([err_vec], perm, [n], cuts)
+    both = torch.stack([s_oracle[0, 0], s_by_unc[0, 0]]).cpu().numpy()
+    return _ause_tail(_prefix_means(both[0], cuts[0], err_type), _prefix_means(both[1], cuts[0], err_type))
+
+
+def _auce_from_hist(hist: np.ndarray, sigma_sum: float, n: float, z: np.ndarray) -> Dict[str, object]:
+    """auce.py:24-54 from the interval histogram: coverage_k = #{elements satisfying > k thresholds} / n;
+    mean interval length = 2 z_k mean(sigma) (equal to the reference's float64 ``mean(upper - lower)`` to
+    ~2e-16 relative)."""
+    alphas = _alphas()
+    inside = (np.cumsum(hist[::-1])[::-1])[1:]  # count with c > k, k = 0..nz-1
+    coverage_values = [int(c) / n for c in inside]
+    avg_length_values = [np.float64(2.0 * zk * (sigma_sum / n)) for zk in z]
+    auc_length = np.trapz(y=avg_length_values, x=alphas)
+    err = np.array(coverage_values) - (1.0 - np.array(alphas))
+    abs_err = np.abs(err)
+    neg_err = (np.abs(err) - err) / 2.0
+    return {
+        "coverage_values": np.array(coverage_values),
+        "avg_length_values": np.array(avg_length_values),
+        "coverage_error_values": np.array(err),
+        "abs_coverage_error_values": abs_err,
+        "neg_coverage_error_values": neg_err,
+        "auc_abs_error_values": np.trapz(y=abs_err, x=alphas),
+        "auc_length_values": auc_length,
+        "auc_neg_error_values": np.trapz(y=neg_err, x=alphas),
+    }
+
+
+ArrayLike = Union[np.ndarray, Tensor]
+
+
+def _to_cuda_f32(a: ArrayLike, device) -> Tensor:
+    if isinstance(a, np.ndarray):
+        a = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return a.to(device=device, dtype=torch.float32, non_blocking=True)
+
+
+def auce(mean_values: ArrayLike, sigma_values: ArrayLike, target_values: ArrayLike, device=None) -> Dict[str, object]:
+    """Drop-in for ``nerfuncertainty.metrics.auce`` (auce.py:10-57).  Accepts the reference's host numpy
+    arrays (copied to ``device``, default the current CUDA device) or CUDA tensors; all three must share
+    one shape (sigma per element)."""
+    if device is None:
+        device = mean_values.device if isinstance(mean_values, torch.Tensor) and mean_values.is_cuda \
+            else torch.device("cuda", torch.cuda.current_device())
+    m = _to_cuda_f32(mean_values, device).reshape(-1, 1)
+    s = _to_cuda_f32(sigma_values, device).reshape(-1)
+    t = _to_cuda_f32(target_values, device).reshape(-1, 1)
+    if not (m.shape[0] == s.shape[0] == t.shape[0]):
+        raise ValueError("mean_values, sigma_values and target_values must have the same shape")
+    n = m.shape[0]
+    z = _z_table(device)
+    out = ops.score_prologue(m, t, s, [n], z, nll_min_std=0.0, sigma_from_var=False, want_vectors=False)
+    hist = out["hist"][0].cpu().numpy()
+    sigma_sum = float(out["sums"][0, 4].item())
+    return _auce_from_hist(hist, sigma_sum, float(n), z_values_host())
+
+
+def score_rgb_batch(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb_std_for_nll: float = 3e-2
+                    ) -> List[Dict[str, object]]:
+    """``get_unc_metrics_rgb`` (eval_uncertainty.py:306-402) for a batch of images in one set of
+    segmented launches.  ``rgb_pred, rgb_gt [B, H, W, 3]``, ``rgb_std [B, H, W, 1]`` (CUDA float32; the
+    ground truth already composited with the background for splat models).  Returns one dict per image
+    with the reference's scalar / curve entries (``nll_rgb``, ``ause_*``, ``err_*``, ``err_var_*``,
+    ``avg_var``, ``mse_mean`` and the 8 AUCE entries)."""
+    if rgb_pred.dim() == 3:
+        rgb_pred, rgb_gt, rgb_std = rgb_pred[None], rgb_gt[None], rgb_std[None]
+    b, h, w, c = rgb_pred.shape
+    n = h * w
+    lens = [n] * b
+    dev = rgb_pred.device
+    z = _z_table(dev)
+    pro = ops.score_prologue(rgb_pred.reshape(-1, c), rgb_gt.reshape(-1, c), rgb_std.reshape(-1), lens, z,
+                             nll_min_std=min_rgb_std_for_nll, sigma_from_var=True, want_vectors=True)
+    se, ae, var = pro["squared_error"], pro["absolute_error"], pro["var"]
+    cuts = np.tile(ause_cut_counts(n)[None, :], (b, 1))
+    _, perm = ops.segmented_sort(var, lens, want_perm=True, want_keys=False)
+    by_unc = ops.cut_prefix_sums([ae, se], perm, lens, cuts)            # [B, 2, 100]
+    ae_sorted, _ = ops.segmented_sort(ae, lens, want_perm=False, want_keys=True)
+    se_sorted, _ = ops.segmented_sort(se, lens, want_perm=False, want_keys=True)
+    oracle_ae = ops.cut_prefix_sums([ae_sorted], None, lens, cuts)      # [B, 1, 100]
+    oracle_se = ops.cut_prefix_sums([se_sorted], None, lens, cuts)
+    # one device->host transfer for everything the host tail needs
+    packed = torch.cat([by_unc.reshape(b, -1), oracle_ae.reshape(b, -1), oracle_se.reshape(b, -1),
+                        pro["sums"], pro["hist"].to(torch.float64)], dim=1).cpu().numpy()
+    zh = z_values_host()
+    results = []
+    for i in range(b):
+        row = packed[i]
+        bu_ae, bu_se, or_ae, or_se = row[0:100], row[100:200], row[200:300], row[300:400]
+        sums = row[400:405]
+        hist = np.rint(row[405:405 + len(zh) + 1]).astype(np.int64)
+        ci = cuts[i]
+        d: Dict[str, object] = {}
+        _, d["err_mae"], d["err_var_mae"], d["ause_mae"] = _ause_tail(
+            _prefix_means(or_ae, ci, "mae"), _prefix_means(bu_ae, ci, "mae"))
+        _, d["err_mse"], d["err_var_mse"], d["ause_mse"] = _ause_tail(
+            _prefix_means(or_se, ci, "mse"), _prefix_means(bu_se, ci, "mse"))
+        _, d["err_rmse"], d["err_var_rmse"], d["ause_rmse"] = _ause_tail(
+            _prefix_means(or_se, ci, "rmse"), _prefix_means(bu_se, ci, "rmse"))
+        d["nll_rgb"] = float(np.float32(sums[3] / (n * c)))
+        d["avg_var"] = float(np.float32(sums[2] / n))
+        d["mse_mean"] = float(np.float32(sums[0] / n))
+        d.update(_auce_from_hist(hist, float(sums[4]) * c, float(n * c), zh))
+        results.append(d)
+    return results
+
+
+def per_image_rgb_scalars(d: Dict[str, object]) -> Dict[str, float]:
+    """The per-image scalar entries of ``metrics_dict`` (eval_uncertainty.py:765-776)."""
+    mse = float(d["mse_mean"])
+    return {
+        "rgb_ause_mse": float(d["ause_mse"]), "rgb_ause_mae": float(d["ause_mae"]),
+        "rgb_ause_rmse": float(d["ause_rmse"]), "rgb_mse": mse, "rgb_rmse": float(np.sqrt(mse)),
+        "rgb_nll": float(d["nll_rgb"]), "rgb_avg_var": float(d["avg_var"]),
+        "rgb_auc_abs_error": d["auc_abs_error_values"], "rgb_auc_length": d["auc_length_values"],
+        "rgb_auc_neg_error": d["auc_neg_error_values"],
+    }

@@ -1,0 +1,152 @@
+"""Output-dict assembly of the reference's models on top of the fused CUDA ops.
+
+These functions are the part of each model's ``get_outputs*`` that lies downstream of the field /
+projection (the hot path); they return dicts with the reference's keys *in the reference's insertion
+order* (which matters for the ensemble overwrite quirk).  They work on plain tensors so that they can
+be tested without nerfstudio; ``nerfstudio_plugin.py`` wraps them into nerfstudio ``Model`` subclasses.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from .. import ops
+
+Tensor = torch.Tensor
+Level = Tuple[Tensor, Tensor, Tensor]  # (weights, starts, ends) of one proposal level
+
+STD_KEYS = ("rgb", "depth", "expected_depth")
+
+
+def active_nerfacto_outputs(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor, rgb: Tensor,
+                            beta: Tensor, *, background="last_sample", rays_per_chunk: Optional[int] = None,
+                            eval_mode: bool = True, proposal_levels: Sequence[Level] = (),
+                            return_weights: bool = False) -> Dict[str, Tensor]:
+    """``ActiveNerfactoModel.get_outputs`` downstream of ``field.forward``
+    (reference activenerfacto_model.py:94-127, 150-151).  Inputs ``[R, S, C]``; outputs ``[R, C]``."""
+    o = ops.composite_rays(density, deltas, starts, ends, rgb, beta, background=background,
+                           beta_mode="nan_guard", rays_per_chunk=rays_per_chunk, eval_mode=eval_mode,
+                           return_weights=return_weights)
+    out = {
+        "rgb": o["rgb"],
+        "accumulation": o["accumulation"],
+        "depth": o["depth"],
+        "expected_depth": o["expected_depth"],
+        "density": density,
+        "rgb_var": o["rgb_var"],
+        "rgb_std": o["rgb_std"],
+        "depth_var": o["depth_var"],
+        "depth_std": o["depth_std"],
+    }
+    if return_weights:
+        out["weights"] = o["weights"]
+    for i, (w, s, e) in enumerate(proposal_levels):
+        out[f"prop_depth_{i}"] = ops.render_weights(w, s, e, want=("depth",))["depth"]
+    return out
+
+
+def laplace_outputs_unc(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor, rgb: Tensor,
+                        rgb_var: Tensor, *, averaged_weights: Optional[Tensor] = None, background="last_sample",
+                        rays_per_chunk: Optional[int] = None, proposal_levels: Sequence[Level] = ()
+                        ) -> Dict[str, Tensor]:
+    """``NerfactoLaplaceModel.get_outputs_unc`` downstream of ``field.forward_unc``
+    (reference laplace_model.py:471-530).  ``rgb`` / ``rgb_var`` are the last-layer Laplace moments
+    (``laplace_ll_moments``).  With ``averaged_weights`` (mean weights of the sampled densities,
+    :486-507) depth / depth_std / expected_depth / accumulation come from those, else from the
+    deterministic weights (``use_deterministic_density``)."""
+    o = ops.composite_rays(density, deltas, starts, ends, rgb, rgb_var, background=background, beta_mode="raw",
+                           rays_per_chunk=rays_per_chunk, eval_mode=True)
+    if averaged_weights is not None:
+        g = ops.render_weights(averaged_weights, starts, ends, rays_per_chunk=rays_per_chunk,
+                               want=("accumulation", "depth", "expected_depth", "depth_std"))
+    else:
+        g = o
+    out = {
+        "rgb": o["rgb"],
+        "rgb_std": o["rgb_std"],
+        "accumulation": g["accumulation"],
+        "depth": g["depth"],
+        "depth_std": g["depth_std"],
+        "expected_depth": g["expected_depth"],
+    }
+    for i, (w, s, e) in enumerate(proposal_levels):
+        out[f"prop_depth_{i}"] = ops.render_weights(w, s, e, want=("depth",))["depth"]
+    return out
+
+
+def _mean_only(members: List[Tensor]) -> Tensor:
+    flat = [m.reshape(-1, 1) for m in members]
+    mean, _ = ops.reduce_members(flat, None)
+    return mean.reshape(members[0].shape)
+
+
+def mcdropout_reduce(outputs_list: Sequence[Dict[str, Tensor]]) -> Dict[str, Tensor]:
+    """``NerfactoMCDropoutModel.get_outputs_for_camera_ray_bundle`` after the K stochastic renders
+    (reference mcdropout_models.py:121-126)."""
+    out: Dict[str, Tensor] = {}
+    for k in outputs_list[0].keys():
+        members = [o[k] for o in outputs_list]
+        if k in STD_KEYS:
+            out[k], out[k + "_std"] = ops.reduce_members(members, "std")
+        else:
+            out[k] = _mean_only(members)
+    return out
+
+
+def ensemble_reduce(outputs_list: Sequence[Dict[str, Tensor]]) -> Dict[str, Tensor]:
+    """``EnsemblePipeline.get_ensemble_outputs_for_camera_ray_bundle`` after the M member renders
+    (reference ensemble_pipeline.py:159-190), including the reference's overwrite order."""
+    first = outputs_list[0]
+    has_pred_std = "rgb_std" in first.keys() and "depth_std" in first.keys()
+    out: Dict[str, Tensor] = {}
+    for k in first.keys():
+        members = [o[k] for o in outputs_list]
+        if has_pred_std and k in ("rgb", "depth"):
+            out[k], epi = ops.reduce_members(members, "var")
+            alea, _ = ops.reduce_members([o[k + "_var"] for o in outputs_list], None)
+            out[k + "_var_alea"] = alea.mean(dim=-1).unsqueeze(-1)
+            out[k + "_var_epi"] = epi
+            out[k + "_var"] = out[k + "_var_epi"] + out[k + "_var_alea"]
+            out[k + "_std"] = out[k + "_var"].sqrt()
+        elif not has_pred_std and k in STD_KEYS:
+            out[k], out[k + "_std"] = ops.reduce_members(members, "std")
+        else:
+            out[k] = _mean_only(members)
+    return out
+
+
+def active_splatfacto_outputs(xys: Tensor, depths: Tensor, conics: Tensor, opacities: Tensor, rgbs: Tensor,
+                              betas: Tensor, gaussian_ids: Tensor, tile_bins: Tensor, height: int, width: int,
+                              background: Tensor) -> Dict[str, Tensor]:
+    """``ActiveSplatfactoModel.get_outputs`` downstream of projection and binning
+    (reference activesplatfacto_model.py:260-367): one fused pass for rgb + beta + depth, the
+    per-Gaussian squared depth residual, and a second pass for the depth variance."""
+    g = xys.shape[0]
+    colors = torch.cat([rgbs.reshape(g, 3), betas.reshape(g, 1), depths.reshape(g, 1)], dim=1)
+    bg = [float(v) for v in background.tolist()] + [0.0, 0.0]
+    img, alpha = ops.composite_tiles(xys, conics, opacities, colors, gaussian_ids, tile_bins, height, width, bg)
+    rgb = torch.clamp(img[..., 0:3], max=1.0)
+    uncertainty = img[..., 3:4]
+    depth_raw = img[..., 4:5]
+    depth_im = torch.where(alpha > 0, depth_raw / alpha, depth_raw.detach().max())
+    # squared residual of every Gaussian's depth against the rendered depth at its centre pixel (:325-341)
+    pix = torch.floor(xys).long()
+    valid = (pix[:, 0] > 0) & (pix[:, 0] < width) & (pix[:, 1] > 0) & (pix[:, 1] < height)
+    resid = depths.reshape(g).clone()
+    pv = pix[valid]
+    resid[valid] -= depth_im[pv[:, 1], pv[:, 0], 0]
+    dvar_raw, _ = ops.composite_tiles(xys, conics, opacities, (resid ** 2).reshape(g, 1), gaussian_ids, tile_bins,
+                                      height, width, [0.0])
+    depth_var = torch.where(alpha > 0, dvar_raw / alpha, dvar_raw.detach().max())
+    return {
+        "rgb": rgb,
+        "depth": depth_im,
+        "accumulation": alpha,
+        "background": background,
+        "uncertainty": uncertainty,
+        "rgb_var": uncertainty ** 2,
+        "rgb_std": uncertainty,
+        "depth_var": depth_var,
+        "depth_std": depth_var.sqrt(),
+    }

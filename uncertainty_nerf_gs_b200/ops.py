@@ -1,0 +1,348 @@
+"""Torch-tensor front end of the C ABI: shape checks, output / workspace allocation, stream passing.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic happens in ``libub200.so``.
+Every function requires CUDA float32 tensors and raises otherwise -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import UBError  # noqa: F401  (re-exported)
+
+Tensor = torch.Tensor
+
+# kernels launched by this process through the C ABI (bench.py reports it as `gpu_launches`)
+LAUNCH_COUNT = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += n
+
+
+def _dev_f32(t: Tensor, name: str) -> Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device: the ub200 path has no CPU implementation")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _workspace(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _squeeze_last(t: Tensor, name: str, ndim: int) -> Tensor:
+    if t.dim() == ndim + 1 and t.shape[-1] == 1:
+        t = t[..., 0]
+    if t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dims (or a trailing singleton), got shape {tuple(t.shape)}")
+    return t
+
+
+_BG_MODES = {"last_sample": _lib.UB_BG_LAST_SAMPLE, "random": _lib.UB_BG_NONE, "none": _lib.UB_BG_NONE}
+_BETA_MODES = {"raw": _lib.UB_BETA_RAW, "nan_guard": _lib.UB_BETA_NAN_GUARD}
+
+
+def composite_rays(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor, rgb: Tensor,
+                   beta: Optional[Tensor] = None, *, background: Union[str, Sequence[float], Tensor] = "last_sample",
+                   beta_mode: str = "nan_guard", rays_per_chunk: Optional[int] = None,
+                   eval_mode: bool = True, return_weights: bool = False) -> Dict[str, Tensor]:
+    """One fused pass over ``[R, S]`` ray samples -> rgb, accumulation, median depth, expected depth,
+    ``rgb_var = sum w^2 beta``, depth variance (+ std of both).  Outputs are ``[R, C]`` like the
+    reference's per-chunk ``get_outputs`` (activenerfacto_model.py:94-127)."""
+    lib = _lib.load()
+    density = _dev_f32(_squeeze_last(density, "density", 2), "density")
+    R, S = density.shape
+    tensors = {"deltas": deltas, "starts": starts, "ends": ends}
+    flat = {}
+    for name, t in tensors.items():
+        t = _dev_f32(_squeeze_last(t, name, 2), name)
+        if t.shape != (R, S):
+            raise ValueError(f"{name}: shape {tuple(t.shape)} != {(R, S)}")
+        flat[name] = t
+    rgb = _dev_f32(rgb, "rgb")
+    if rgb.shape != (R, S, 3):
+        raise ValueError(f"rgb: shape {tuple(rgb.shape)} != {(R, S, 3)}")
+    if beta is not None:
+        beta = _dev_f32(_squeeze_last(beta, "beta", 2), "beta")
+        if beta.shape != (R, S):
+            raise ValueError(f"beta: shape {tuple(beta.shape)} != {(R, S)}")
+    dev = density.device
+    args = _lib.CompositeRaysArgs()
+    args.density, args.deltas = density.data_ptr(), flat["deltas"].data_ptr()
+    args.starts, args.ends = flat["starts"].data_ptr(), flat["ends"].data_ptr()
+    args.rgb, args.beta = rgb.data_ptr(), _ptr(beta)
+    args.num_rays, args.num_samples = R, S
+    if isinstance(background, str):
+        if background not in _BG_MODES:
+            raise ValueError(f"unsupported background {background!r}")
+        args.background_mode = _BG_MODES[background]
+    else:
+        bg = [float(v) for v in (background.tolist() if isinstance(background, torch.Tensor) else background)]
+        if len(bg) != 3:
+            raise ValueError("fixed background must have 3 components")
+        args.background_mode = _lib.UB_BG_FIXED
+        args.background_rgb = (C.c_float * 3)(*bg)
+    args.beta_mode = _BETA_MODES[beta_mode]
+    args.rays_per_chunk = int(rays_per_chunk) if rays_per_chunk else 0
+    args.eval_mode = 1 if eval_mode else 0
+    out = {
+        "rgb": torch.empty(R, 3, device=dev), "accumulation": torch.empty(R, 1, device=dev),
+        "depth": torch.empty(R, 1, device=dev), "expected_depth": torch.empty(R, 1, device=dev),
+        "depth_var": torch.empty(R, 1, device=dev), "depth_std": torch.empty(R, 1, device=dev),
+    }
+    args.out_rgb, args.out_accumulation = out["rgb"].data_ptr(), out["accumulation"].data_ptr()
+    args.out_depth, args.out_expected_depth = out["depth"].data_ptr(), out["expected_depth"].data_ptr()
+    args.out_depth_var, args.out_depth_std = out["depth_var"].data_ptr(), out["depth_std"].data_ptr()
+    if beta is not None:
+        out["rgb_var"] = torch.empty(R, 1, device=dev)
+        out["rgb_std"] = torch.empty(R, 1, device=dev)
+        args.out_rgb_var, args.out_rgb_std = out["rgb_var"].data_ptr(), out["rgb_std"].data_ptr()
+    if return_weights:
+        out["weights"] = torch.empty(R, S, 1, device=dev)
+        args.out_weights = out["weights"].data_ptr()
+    ws_bytes = lib.ub_composite_rays_workspace_bytes(R, args.rays_per_chunk)
+    ws = _workspace(ws_bytes, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ub_composite_rays(C.byref(args), ws.data_ptr(), ws.numel(), _stream()))
+    _count(2 if R > 0 else 0)
+    return out
+
+
+def render_weights(weights: Tensor, starts: Tensor, ends: Tensor, *, rays_per_chunk: Optional[int] = None,
+                   want: Sequence[str] = ("depth",)) -> Dict[str, Tensor]:
+    """Median depth / expected depth / accumulation / depth variance from given weights
+    (``prop_depth_i``, activenerfacto_model.py:150-151; averaged sampled weights, laplace_model.py:509-521)."""
+    lib = _lib.load()
+    weights = _dev_f32(_squeeze_last(weights, "weights", 2), "weights")
+    R, S = weights.shape
+    starts = _dev_f32(_squeeze_last(starts, "starts", 2), "starts")
+    ends = _dev_f32(_squeeze_last(ends, "ends", 2), "ends")
+    if starts.shape != (R, S) or ends.shape != (R, S):
+        raise ValueError("starts / ends must match weights")
+    dev = weights.device
+    args = _lib.RenderWeightsArgs()
+    args.weights, args.starts, args.ends = weights.data_ptr(), starts.data_ptr(), ends.data_ptr()
+    args.num_rays, args.num_samples = R, S
+    args.rays_per_chunk = int(rays_per_chunk) if rays_per_chunk else 0
+    fields = {"accumulation": "out_accumulation", "depth": "out_depth", "expected_depth": "out_expected_depth",
+              "depth_var": "out_depth_var", "depth_std": "out_depth_std"}
+    out: Dict[str, Tensor] = {}
+    for k in want:
+        if k not in fields:
+            raise ValueError(f"unknown output {k!r}")
+        out[k] = torch.empty(R, 1, device=dev)
+        setattr(args, fields[k], out[k].data_ptr())
+    ws = _workspace(lib.ub_render_weights_workspace_bytes(R, args.rays_per_chunk), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ub_render_weights(C.byref(args), ws.data_ptr(), ws.numel(), _stream()))
+    _count((2 if "expected_depth" in out else 1) if R > 0 else 0)
+    return out
+
+
+_SPREAD = {None: _lib.UB_SPREAD_NONE, "std": _lib.UB_SPREAD_STD, "var": _lib.UB_SPREAD_VAR}
+
+
+def reduce_members(members: Sequence[Tensor], spread: Optional[str] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """Mean over K same-shaped ``[..., C]`` member tensors (read in place, no stack) and, optionally,
+    the unbiased std / var over members averaged over the channel axis -> ``[..., 1]``."""
+    lib = _lib.load()
+    if len(members) < 1:
+        raise ValueError("need at least one member")
+    ms = [_dev_f32(m, f"members[{i}]") for i, m in enumerate(members)]
+    shape = ms[0].shape
+    if any(m.shape != shape for m in ms):
+        raise ValueError("all members must share one shape")
+    if spread not in _SPREAD:
+        raise ValueError(f"spread must be None, 'std' or 'var', got {spread!r}")
+    c = int(shape[-1]) if len(shape) else 1
+    n = ms[0].numel() // max(c, 1)
+    dev = ms[0].device
+    mean = torch.empty(shape, device=dev)
+    spr = torch.empty((*shape[:-1], 1), device=dev) if spread else None
+    ptrs = (C.c_void_p * len(ms))(*[m.data_ptr() for m in ms])
+    with torch.cuda.device(dev):
+        _lib.check(lib.ub_reduce_members(ptrs, len(ms), n, c, _SPREAD[spread], mean.data_ptr(), _ptr(spr), _stream()))
+    _count(1 if n > 0 else 0)
+    return mean, spr
+
+
+def _offsets(seg_lengths: Sequence[int]) -> np.ndarray:
+    off = np.zeros(len(seg_lengths) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(seg_lengths, dtype=np.int64), out=off[1:])
+    return off
+
+
+def _i64p(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def score_prologue(pred: Tensor, target: Tensor, std: Tensor, seg_lengths: Sequence[int], z_values: Tensor,
+                   nll_min_std: float, sigma_from_var: bool = True, want_vectors: bool = True
+                   ) -> Dict[str, Tensor]:
+    """se / ae / var vectors, float64 sums and the AUCE interval histogram for a batch of images.
+    ``pred, target [N, C]``, ``std [N]``; images are consecutive segments of ``seg_lengths`` pixels."""
+    lib = _lib.load()
+    pred = _dev_f32(pred, "pred")
+    target = _dev_f32(target, "target")
+    if pred.dim() != 2 or pred.shape != target.shape or pred.shape[1] not in (1, 3):
+        raise ValueError("pred / target must be [N, 1] or [N, 3] and match")
+    n, c = pred.shape
+    std = _dev_f32(std.reshape(-1), "std")
+    if std.numel() != n:
+        raise ValueError("std must hold one value per pixel")
+    off = _offsets(seg_lengths)
+    if off[-1] != n:
+        raise ValueError("segment lengths do not sum to the number of pixels")
+    if z_values.dtype != torch.float64 or not z_values.is_cuda:
+        raise TypeError("z_values must be a CUDA float64 tensor")
+    dev = pred.device
+    nseg, nz = len(seg_lengths), z_values.numel()
+    out: Dict[str, Tensor] = {
+        "sums": torch.empty(nseg, _lib.UB_PROLOGUE_NSUMS, dtype=torch.float64, device=dev),
+        "hist": torch.empty(nseg, nz + 1, dtype=torch.int64, device=dev),
+    }
+    if want_vectors:
+        out["squared_error"] = torch.empty(n, device=dev)
+        out["absolute_error"] = torch.empty(n, device=dev)
+        out["var"] = torch.empty(n, device=dev)
+    args = _lib.ScorePrologueArgs()
+    args.pred, args.target, args.std = pred.data_ptr(), target.data_ptr(), std.data_ptr()
+    args.channels, args.num_segments, args.seg_offsets_host = c, nseg, _i64p(off)
+    args.nll_min_std, args.sigma_from_var = float(nll_min_std), 1 if sigma_from_var else 0
+    args.z_values, args.num_z = z_values.data_ptr(), nz
+    args.out_sq_err, args.out_abs_err = _ptr(out.get("squared_error")), _ptr(out.get("absolute_error"))
+    args.out_var = _ptr(out.get("var"))
+    args.out_sums, args.out_hist = out["sums"].data_ptr(), out["hist"].data_ptr()
+    ws = _workspace(lib.ub_score_prologue_workspace_bytes(nseg, int(max(seg_lengths) if nseg else 0), nz), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ub_score_prologue(C.byref(args), ws.data_ptr(), ws.numel(), _stream()))
+    _count(2)
+    return out
+
+
+def segmented_sort(keys: Tensor, seg_lengths: Sequence[int], want_perm: bool = True, want_keys: bool = True
+                   ) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """Stable ascending sort of each segment (``torch.sort(stable=True)`` order).  Returns
+    ``(sorted_keys, perm)`` with ``perm`` int32 indices *within the segment*."""
+    lib = _lib.load()
+    keys = _dev_f32(keys.reshape(-1), "keys")
+    off = _offsets(seg_lengths)
+    if off[-1] != keys.numel():
+        raise ValueError("segment lengths do not sum to the number of keys")
+    dev = keys.device
+    total = keys.numel()
+    sorted_keys = torch.empty(total, device=dev) if want_keys else None
+    perm = torch.empty(total, dtype=torch.int32, device=dev) if want_perm else None
+    nseg = len(seg_lengths)
+    max_len = int(max(seg_lengths)) if nseg else 0
+    ws = _workspace(lib.ub_segmented_sort_workspace_bytes(nseg, total, max_len, 1 if want_perm else 0), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ub_segmented_sort(keys.data_ptr(), nseg, _i64p(off), _ptr(sorted_keys), _ptr(perm),
+                                         ws.data_ptr(), ws.numel(), _stream()))
+    _count(12 if total > 0 else 0)
+    return sorted_keys, perm
+
+
+def cut_prefix_sums(values: Sequence[Tensor], perm: Optional[Tensor], seg_lengths: Sequence[int],
+                    cuts: np.ndarray) -> Tensor:
+    """float64 ``sum_{i < cut} values_v[perm[i]]`` per segment, value array and cut -> ``[nseg, V, ncuts]``."""
+    lib = _lib.load()
+    vals = [_dev_f32(v.reshape(-1), f"values[{i}]") for i, v in enumerate(values)]
+    off = _offsets(seg_lengths)
+    total = int(off[-1])
+    if any(v.numel() != total for v in vals):
+        raise ValueError("every value array must hold one entry per element")
+    if perm is not None and (perm.dtype != torch.int32 or not perm.is_cuda or perm.numel() != total):
+        raise TypeError("perm must be a CUDA int32 tensor with one entry per element")
+    cuts = np.ascontiguousarray(cuts, dtype=np.int64)
+    nseg = len(seg_lengths)
+    if cuts.ndim != 2 or cuts.shape[0] != nseg:
+        raise ValueError("cuts must be [num_segments, num_cuts]")
+    ncuts = cuts.shape[1]
+    dev = vals[0].device
+    out = torch.empty(nseg, len(vals), ncuts, dtype=torch.float64, device=dev)
+    ptrs = (C.c_void_p * len(vals))(*[v.data_ptr() for v in vals])
+    max_len = int(max(seg_lengths)) if nseg else 0
+    ws = _workspace(lib.ub_cut_prefix_sums_workspace_bytes(nseg, max_len, len(vals), ncuts), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ub_cut_prefix_sums(ptrs, len(vals), _ptr(perm), nseg, _i64p(off), _i64p(cuts), ncuts,
+                                          out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    _count(2)
+    return out
+
+
+_ACTS = {"identity": _lib.UB_ACT_IDENTITY, "sigmoid": _lib.UB_ACT_SIGMOID, "exp": _lib.UB_ACT_EXP,
+         "trunc_exp": _lib.UB_ACT_EXP}
+
+
+def laplace_ll_moments(x: Tensor, sampled_params: Tensor, out_dim: int, activation: str,
+                       want_mean2: bool = False) -> Dict[str, Tensor]:
+    """E[y], E[y^2]-E[y]^2 of ``y = act(x W_s^T + b_s)`` over the rows of ``sampled_params``
+    (``[n_samples, out_dim*hidden + out_dim]``, torch ``parameters_to_vector`` order)."""
+    lib = _lib.load()
+    x = _dev_f32(x, "x")
+    if x.dim() != 2:
+        x = x.reshape(-1, x.shape[-1])
+    p, h = x.shape
+    sampled_params = _dev_f32(sampled_params, "sampled_params")
+    if sampled_params.dim() != 2 or sampled_params.shape[1] != out_dim * h + out_dim:
+        raise ValueError("sampled_params must be [n_samples, out_dim*hidden + out_dim]")
+    if activation not in _ACTS:
+        raise ValueError(f"unknown activation {activation!r}")
+    dev = x.device
+    out = {"mean": torch.empty(p, out_dim, device=dev), "sigma2": torch.empty(p, out_dim, device=dev)}
+    if want_mean2:
+        out["mean2"] = torch.empty(p, out_dim, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ub_laplace_ll_moments(x.data_ptr(), p, h, out_dim, sampled_params.data_ptr(),
+                                             sampled_params.shape[0], _ACTS[activation], out["mean"].data_ptr(),
+                                             _ptr(out.get("mean2")), out["sigma2"].data_ptr(), _stream()))
+    _count(1 if p > 0 else 0)
+    return out
+
+
+def composite_tiles(xys: Tensor, conics: Tensor, opacities: Tensor, colors: Tensor, gaussian_ids: Tensor,
+                    tile_bins: Tensor, height: int, width: int, background: Optional[Sequence[float]] = None
+                    ) -> Tuple[Tensor, Tensor]:
+    """Alpha-composite ``colors [G, CH]`` over pre-binned 16x16 tile lists -> ``([H, W, CH], alpha [H, W, 1])``."""
+    lib = _lib.load()
+    xys, conics = _dev_f32(xys, "xys"), _dev_f32(conics, "conics")
+    opacities = _dev_f32(opacities.reshape(-1), "opacities")
+    colors = _dev_f32(colors, "colors")
+    g, ch = colors.shape
+    if xys.shape != (g, 2) or conics.shape != (g, 3) or opacities.numel() != g:
+        raise ValueError("xys [G,2], conics [G,3], opacities [G] must match colors [G,CH]")
+    for name, t in (("gaussian_ids", gaussian_ids), ("tile_bins", tile_bins)):
+        if t.dtype != torch.int32 or not t.is_cuda:
+            raise TypeError(f"{name} must be a CUDA int32 tensor")
+    gaussian_ids, tile_bins = gaussian_ids.contiguous(), tile_bins.contiguous()
+    tiles = ((width + _lib.UB_TILE - 1) // _lib.UB_TILE) * ((height + _lib.UB_TILE - 1) // _lib.UB_TILE)
+    if tile_bins.shape != (tiles, 2):
+        raise ValueError(f"tile_bins must be [{tiles}, 2]")
+    dev = colors.device
+    out = torch.empty(height, width, ch, device=dev)
+    alpha = torch.empty(height, width, 1, device=dev)
+    bg = (C.c_float * ch)(*([0.0] * ch if background is None else [float(v) for v in background]))
+    with torch.cuda.device(dev):
+        _lib.check(lib.ub_composite_tiles(xys.data_ptr(), conics.data_ptr(), opacities.data_ptr(), colors.data_ptr(),
+                                          ch, gaussian_ids.data_ptr(), tile_bins.data_ptr(), height, width, bg,
+                                          out.data_ptr(), alpha.data_ptr(), _stream()))
+    _count(1)
+    return out, alpha
