@@ -104,7 +104,8 @@ extern "C" int ub_composite_tiles(const float* xys, const float* conics, const f
   UB_REQUIRE(channels >= 1 && channels <= UB_MAX_SPLAT_CHANNELS, UB_ERR_UNSUPPORTED,
              "composite_tiles: channels must be in [1, %d]", UB_MAX_SPLAT_CHANNELS);
   UB_REQUIRE(img_height >= 1 && img_width >= 1, UB_ERR_BAD_ARG, "composite_tiles: bad image size");
-  UB_REQUIRE(xys && conics && opacities && colors && gaussian_ids && tile_bins && out, UB_ERR_BAD_ARG,
+  // gaussian_ids may be NULL when there is no intersection at all (every tile range empty)
+  UB_REQUIRE(xys && conics && opacities && colors && tile_bins && out, UB_ERR_BAD_ARG,
              "composite_tiles: NULL input / output pointer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   TileParams p{};
