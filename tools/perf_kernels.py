@@ -1,0 +1,99 @@
+"""Per-kernel device timings (CUDA events, rotating input sets larger than L2) -- development aid.
+Usage: python tools/perf_kernels.py [composite|reduce|score|sort|laplace|splat ...]"""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from uncertainty_nerf_gs_b200 import ops, synthetic, metrics
+from uncertainty_nerf_gs_b200.build import build_library
+
+build_library()
+dev = torch.device("cuda:0")
+H, W, S = 840, 1297, 48
+R = H * W
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn(0)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def composite():
+    sets = [synthetic.ray_samples(R, S, seed=i, device=dev) for i in range(3)]
+    def run(i):
+        m = sets[i % 3]
+        ops.composite_rays(m["density"], m["deltas"], m["starts"], m["ends"], m["rgb"], m["beta"], rays_per_chunk=1 << 15)
+    ms = timeit(run)
+    print(json.dumps({"kernel": "composite_rays", "ms": ms, "GBs": 1576 * R / ms / 1e6, "Grays_s": R / ms / 1e6}))
+    for r in (4096, 32768):
+        small = [{k: v[:r].contiguous() for k, v in s.items()} for s in sets]
+        def run2(i):
+            m = small[i % 3]
+            ops.composite_rays(m["density"], m["deltas"], m["starts"], m["ends"], m["rgb"], m["beta"], rays_per_chunk=1 << 15)
+        ms = timeit(run2, iters=50)
+        print(json.dumps({"kernel": f"composite_rays[{r}]", "ms": ms, "GBs": 1576 * r / ms / 1e6}))
+
+
+def reduce():
+    for K in (5, 10):
+        ms_ = [torch.rand(R, 3, device=dev) for _ in range(K)]
+        ds = [torch.rand(R, 1, device=dev) for _ in range(K)]
+        t3 = timeit(lambda i: ops.reduce_members(ms_, "std"))
+        t1 = timeit(lambda i: ops.reduce_members(ds, "std"))
+        t0 = timeit(lambda i: ops.reduce_members(ds, None))
+        print(json.dumps({"kernel": f"reduce K={K}", "ms_c3_std": t3, "GBs_c3": (K * 12 + 16) * R / t3 / 1e6,
+                          "ms_c1_std": t1, "GBs_c1": (K * 4 + 8) * R / t1 / 1e6, "ms_c1_mean": t0,
+                          "GBs_c1_mean": (K * 4 + 4) * R / t0 / 1e6}))
+
+
+def score():
+    for (h, w, b) in ((840, 1297, 1), (800, 800, 1), (800, 800, 16)):
+        imgs = [synthetic.scoring_image(h, w, seed=i, device=dev) for i in range(b)]
+        pred = torch.stack([i[0] for i in imgs]); std = torch.stack([i[1] for i in imgs]); gt = torch.stack([i[2] for i in imgs])
+        ms = timeit(lambda i: metrics.score_rgb_batch(pred, gt, std), iters=10)
+        n = h * w
+        z = metrics._z_table(dev)
+        tp = timeit(lambda i: ops.score_prologue(pred.reshape(-1, 3), gt.reshape(-1, 3), std.reshape(-1), [n] * b, z, 0.03))
+        var = (std ** 2).reshape(-1)
+        ts = timeit(lambda i: ops.segmented_sort(var, [n] * b, want_perm=True, want_keys=False))
+        tk = timeit(lambda i: ops.segmented_sort(var, [n] * b, want_perm=False, want_keys=True))
+        print(json.dumps({"kernel": f"score {w}x{h} x{b}", "ms_total": ms, "images_s": b / ms * 1e3, "ms_prologue": tp,
+                          "prologue_GBs": 40 * n * b / tp / 1e6, "ms_sort_pairs": ts, "ms_sort_keys": tk,
+                          "sort_pairs_Mkeys_s": n * b / ts / 1e3}))
+
+
+def laplace():
+    P = 1 << 20
+    lap = synthetic.laplace_head(P, 64, 3, 100, seed=0, device=dev)
+    theta = lap["mu_q"][None] + lap["eps_draws"] / torch.sqrt(lap["ggn"] + 1.0)[None]
+    ms = timeit(lambda i: ops.laplace_ll_moments(lap["x"], theta, 3, "sigmoid"), iters=5, warm=1)
+    print(json.dumps({"kernel": "laplace rgb head", "ms": ms, "Mpoints_s": P / ms / 1e3, "TFLOPs": 2 * 64 * 3 * 100 * P / ms / 1e9}))
+    th1 = theta[:, :65].contiguous()
+    ms = timeit(lambda i: ops.laplace_ll_moments(lap["x"], th1, 1, "exp"), iters=5, warm=1)
+    print(json.dumps({"kernel": "laplace density head", "ms": ms, "Mpoints_s": P / ms / 1e3, "TFLOPs": 2 * 64 * 1 * 100 * P / ms / 1e9}))
+
+
+def splat():
+    from uncertainty_nerf_gs_b200 import binning
+    G = 1_000_000
+    sc = synthetic.splat_scene(G, H, W, seed=0, device=dev)
+    ids, bins = binning.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], H, W)
+    colors = torch.cat([sc["rgbs"], sc["betas"], sc["depths"][:, None]], 1).contiguous()
+    I = ids.numel()
+    ms5 = timeit(lambda i: ops.composite_tiles(sc["xys"], sc["conics"], sc["opacities"], colors, ids, bins, H, W), iters=10)
+    ms3 = timeit(lambda i: ops.composite_tiles(sc["xys"], sc["conics"], sc["opacities"], sc["rgbs"], ids, bins, H, W), iters=10)
+    print(json.dumps({"kernel": "composite_tiles", "intersections": I, "ms_5ch": ms5, "ms_3ch": ms3,
+                      "GBs_5ch": (48 * I + 24 * R) / ms5 / 1e6, "Mpix_s": R / ms5 / 1e3}))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["composite", "reduce", "score", "laplace", "splat"]
+    for name in which:
+        globals()[name]()

@@ -6,20 +6,27 @@
 //   Sum w^2 beta   models/activenerfacto/activenerfacto_model.py:105-107, laplace_model.py:478-480
 //
 // Data layout in HBM: six streams of [R,S] float32 rows (rgb: [R,S,3]); a tile of 8 consecutive
-// rays is contiguous in every stream.  Fast path (composite_rays_tma<S>):
-//   * persistent CTAs, one per SM: warp 0 = producer, warps 1..8 = consumers;
-//   * the producer's elected lane stages 8-ray tiles into shared memory with 1-D bulk async
-//     copies (cp.async.bulk -> UBLKCP), two 12 KB stages per consumer warp, full/empty mbarriers;
-//   * a consumer warp owns a tile: 4 lanes per ray, 12 consecutive samples per lane (S = 48),
-//     conflict-free LDS.128 reads, then everything from registers;
-//   * the two prefix scans (optical depth, cumulative weight) run in float64 *sequentially* along
-//     the ray (lane after lane inside the 4-lane group), rounding every prefix to float32 -- the
-//     exact semantics of torch.cumsum on CPU float32, which decides the median-depth index.
+// rays is contiguous in every stream.  Fast path (composite_rays_tma<S, NCW, NST>):
+//   * persistent CTAs, one per SM: warps 0..NCW-1 = consumers, warp NCW = producer;
+//   * the producer's elected lane stages 8-ray tiles (12 KB at S = 48) into a ring of NST
+//     shared-memory stages with 1-D bulk async copies (cp.async.bulk -> UBLKCP) signalled on
+//     full/empty mbarriers; tiles are dealt to consumer warps round-robin;
+//   * a consumer warp owns a tile: 4 lanes per ray, S/4 consecutive samples per lane,
+//     conflict-free LDS.128 reads, arithmetic from registers, 2-step shuffles inside the ray;
+//   * the two prefix scans (optical depth, cumulative weight) run in float64 and every prefix is
+//     rounded to float32 -- the semantics of torch.cumsum on CPU float32, which decides the
+//     median-depth index.  (float64 sums of float32 terms are exact unless the terms span more
+//     than 2^29, so the lane-parallel association equals the sequential one.)
+//   * nan_to_num of weights / colours and the beta NaN guard are applied on a rare slow path that
+//     is entered only when a per-ray sum comes out non-finite (a non-finite term always makes the
+//     sum non-finite), so the common path carries no per-sample NaN tests.
 // Generic path (composite_rays_generic): warp per ray, any S / alignment, same outputs.
 //
 // Chunk-wide reductions of the reference (clip bounds of expected depth = min/max of steps over
 // the eval chunk; the `isnan(beta).any()` guard) are accumulated per chunk in the workspace and
 // applied by a small finalize kernel.
+#include <stdlib.h>
+
 #include "ub_common.cuh"
 
 namespace ub {
@@ -38,6 +45,7 @@ struct CompositeParams {
   float bg[3];
   int beta_mode;
   long long rays_per_chunk;
+  int tiles_per_chunk;  // rays_per_chunk / 8 on the fast path (0: one chunk)
   int eval_mode;
   float* o_rgb;
   float* o_acc;
@@ -51,9 +59,6 @@ struct CompositeParams {
   unsigned* chunk_ws;  // [num_chunks][4]: max key(steps), max ~key(steps), beta-has-NaN, pad
 };
 
-constexpr int kStagesPerWarp = 2;
-// consumer warps per CTA: as many as fit two 8-ray stages each in 227 KB of shared memory
-constexpr int consumer_warps_for(int S) { return S <= 48 ? 8 : (S <= 64 ? 6 : 4); }
 constexpr int kLanesPerRay = 4;
 constexpr int kRaysPerTile = 32 / kLanesPerRay;  // 8
 
@@ -65,31 +70,34 @@ __device__ __forceinline__ float reduce4(float v) {
   v += __shfl_xor_sync(FULL_MASK, v, 2);
   return v;
 }
+__device__ __forceinline__ bool non_finite(float v) { return !(fabsf(v) <= FLT_MAX); }
 
 // Per-warp running min/max of `steps` for the current chunk, flushed with two atomics when the
 // chunk changes (identity of both atomicMax targets is 0, so the workspace is memset to 0).
 struct ChunkBounds {
   long long chunk = -1;
-  unsigned kmax = 0u, kmin_inv = 0u;
+  float lo = INFINITY, hi = -INFINITY;
   bool has_nan = false;
   __device__ __forceinline__ void flush(unsigned* ws) {
     if (chunk >= 0) {
-      unsigned a = kmax, b = kmin_inv;
+      float a = lo, b = hi;
       int n = has_nan ? 1 : 0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        a = max(a, __shfl_xor_sync(FULL_MASK, a, o));
-        b = max(b, __shfl_xor_sync(FULL_MASK, b, o));
+        a = fminf(a, __shfl_xor_sync(FULL_MASK, a, o));
+        b = fmaxf(b, __shfl_xor_sync(FULL_MASK, b, o));
         n |= __shfl_xor_sync(FULL_MASK, n, o);
       }
       if ((threadIdx.x & 31) == 0) {
-        atomicMax(ws + chunk * 4 + 0, a);
-        atomicMax(ws + chunk * 4 + 1, b);
+        if (a <= b) {
+          atomicMax(ws + chunk * 4 + 0, order_key(b));
+          atomicMax(ws + chunk * 4 + 1, ~order_key(a));
+        }
         if (n) ws[chunk * 4 + 2] = 1u;
       }
     }
-    kmax = 0u;
-    kmin_inv = 0u;
+    lo = INFINITY;
+    hi = -INFINITY;
     has_nan = false;
   }
   __device__ __forceinline__ void enter(long long c, unsigned* ws) {
@@ -99,36 +107,50 @@ struct ChunkBounds {
     }
   }
   __device__ __forceinline__ void add_step(float s) {
-    unsigned k = order_key(s);
-    kmax = max(kmax, k);
-    kmin_inv = max(kmin_inv, ~k);
+    lo = fminf(lo, s);
+    hi = fmaxf(hi, s);
   }
 };
 
-template <int S>
-__global__ void __launch_bounds__(32 * (1 + consumer_warps_for(S)), 1)
-composite_rays_tma(const CompositeParams p) {
-  constexpr int kConsumerWarps = consumer_warps_for(S);
+// exclusive prefix over the 4 lanes of a ray of the lanes' float64 totals, in lane order
+__device__ __forceinline__ double ray_exclusive_offset(double total, int q, int group_base) {
+  const double t0 = shfl_double(FULL_MASK, total, group_base | 0);
+  const double t1 = shfl_double(FULL_MASK, total, group_base | 1);
+  const double t2 = shfl_double(FULL_MASK, total, group_base | 2);
+  const double s01 = t0 + t1;
+  const double s012 = s01 + t2;
+  return q == 0 ? 0.0 : (q == 1 ? t0 : (q == 2 ? s01 : s012));
+}
+
+template <int S, int NCW, int NST>
+__global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const CompositeParams p) {
   constexpr int P = S / kLanesPerRay;  // samples per lane
   constexpr int V = P / 4;             // float4 per lane per scalar stream
   static_assert(S % 16 == 0, "fast path needs S % 16 == 0");
-  constexpr int kTileFloats = kRaysPerTile * S;      // one scalar stream of one tile
-  constexpr int kStageFloats = kTileFloats * 8;      // 5 scalar streams + rgb (3x)
+  // Tiles are dealt round-robin to the NCW consumer warps and to the NST ring stages.  NST must be a
+  // multiple of NCW so that every stage is always consumed by the same warp: bulk copies of different
+  // stages complete out of order, and a *different* warp waiting for tile t+NST on a stage whose
+  // tile t is still in flight would see the opposite phase parity as "complete" and read early.
+  static_assert(NST % NCW == 0, "ring stages must be a multiple of the consumer warps");
+  constexpr int kTileFloats = kRaysPerTile * S;  // one scalar stream of one tile
+  constexpr int kStageFloats = kTileFloats * 8;  // 5 scalar streams + rgb (3x)
   constexpr uint32_t kStageBytes = kStageFloats * 4;
+  // (float)x >= 0.5f  <=>  x >= 0.5 - 2^-26 for a double x under round-to-nearest-even
+  const double kHalf = 0.5 - 1.4901161193847656e-08;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stages = reinterpret_cast<float*>(smem_raw);
-  uint64_t* full_bar =
-      reinterpret_cast<uint64_t*>(smem_raw + (size_t)kConsumerWarps * kStagesPerWarp * kStageBytes);
-  uint64_t* empty_bar = full_bar + kConsumerWarps * kStagesPerWarp;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NST * kStageBytes);
+  uint64_t* empty_bar = full_bar + NST;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long num_tiles = (p.num_rays + kRaysPerTile - 1) / kRaysPerTile;
+  const int num_tiles = (int)((p.num_rays + kRaysPerTile - 1) / kRaysPerTile);
+  const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool has_beta = p.beta != nullptr;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kConsumerWarps * kStagesPerWarp; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -136,206 +158,211 @@ composite_rays_tma(const CompositeParams p) {
   }
   __syncthreads();
 
-  if (warp == 0) {
-    // ===== producer: one elected lane issues all bulk copies =====
+  if (warp == NCW) {
+    // ===== producer (the highest warp id: the issue arbiter favours it over the consumers, so the
+    // copy stream never starves): one elected lane issues all bulk copies =====
     if (lane == 0) {
-      for (long long k = 0;; ++k) {
-        const long long base_tile = (k * gridDim.x + blockIdx.x) * kConsumerWarps;
-        if (base_tile >= num_tiles) break;
-        const int s = (int)(k % kStagesPerWarp);
-        const uint32_t ph = (uint32_t)((k / kStagesPerWarp) & 1);
-        for (int w = 0; w < kConsumerWarps; ++w) {
-          const long long tile = base_tile + w;
-          if (tile >= num_tiles) break;
-          const int slot = w * kStagesPerWarp + s;
-          mbar_wait(&empty_bar[slot], ph ^ 1u);
-          const long long ray0 = tile * kRaysPerTile;
-          const int n = (int)min((long long)kRaysPerTile, p.num_rays - ray0);
-          const uint32_t sb = (uint32_t)n * S * 4u;  // bytes of one scalar stream
-          float* dst = stages + (size_t)slot * kStageFloats;
-          const size_t off = (size_t)ray0 * S;
-          mbar_arrive_expect_tx(&full_bar[slot], sb * (has_beta ? 8u : 7u));
-          bulk_g2s(dst + 0 * kTileFloats, p.density + off, sb, &full_bar[slot]);
-          bulk_g2s(dst + 1 * kTileFloats, p.deltas + off, sb, &full_bar[slot]);
-          bulk_g2s(dst + 2 * kTileFloats, p.starts + off, sb, &full_bar[slot]);
-          bulk_g2s(dst + 3 * kTileFloats, p.ends + off, sb, &full_bar[slot]);
-          if (has_beta) bulk_g2s(dst + 4 * kTileFloats, p.beta + off, sb, &full_bar[slot]);
-          bulk_g2s(dst + 5 * kTileFloats, p.rgb + off * 3, sb * 3u, &full_bar[slot]);
-        }
+      for (int j = 0; j < my_tiles; ++j) {
+        const int st = j % NST;
+        const uint32_t ph = (uint32_t)((j / NST) & 1);
+        mbar_wait(&empty_bar[st], ph ^ 1u, 1000000 + j);
+        const long long ray0 = ((long long)j * gridDim.x + blockIdx.x) * kRaysPerTile;
+        const int n = (int)min((long long)kRaysPerTile, p.num_rays - ray0);
+        const uint32_t sb = (uint32_t)n * S * 4u;  // bytes of one scalar stream
+        float* dst = stages + (size_t)st * kStageFloats;
+        const size_t off = (size_t)ray0 * S;
+        mbar_arrive_expect_tx(&full_bar[st], sb * (has_beta ? 8u : 7u));
+        bulk_g2s(dst + 0 * kTileFloats, p.density + off, sb, &full_bar[st]);
+        bulk_g2s(dst + 1 * kTileFloats, p.deltas + off, sb, &full_bar[st]);
+        bulk_g2s(dst + 2 * kTileFloats, p.starts + off, sb, &full_bar[st]);
+        bulk_g2s(dst + 3 * kTileFloats, p.ends + off, sb, &full_bar[st]);
+        if (has_beta) bulk_g2s(dst + 4 * kTileFloats, p.beta + off, sb, &full_bar[st]);
+        bulk_g2s(dst + 5 * kTileFloats, p.rgb + off * 3, sb * 3u, &full_bar[st]);
       }
     }
     return;
   }
 
   // ===== consumers =====
-  const int w = warp - 1;
+  const int w = warp;
   const int r = lane >> 2;  // ray within the tile
   const int q = lane & 3;   // quarter of the ray this lane owns
   const int group_base = lane & ~3;
+  const int lane_off = r * S + q * P;
   ChunkBounds bounds;
 
-  for (long long k = 0;; ++k) {
-    const long long tile = (k * gridDim.x + blockIdx.x) * kConsumerWarps + w;
-    if (tile >= num_tiles) break;
-    const int s = (int)(k % kStagesPerWarp);
-    const uint32_t ph = (uint32_t)((k / kStagesPerWarp) & 1);
-    const int slot = w * kStagesPerWarp + s;
-    const long long ray0 = tile * kRaysPerTile;
-    const int n = (int)min((long long)kRaysPerTile, p.num_rays - ray0);
-    const bool active = r < n;
-    const long long ray = ray0 + r;
+  for (int j = w; j < my_tiles; j += NCW) {
+    const int st = j % NST;
+    const uint32_t ph = (uint32_t)((j / NST) & 1);
+    const int tile = j * (int)gridDim.x + (int)blockIdx.x;
+    const int ray0 = tile * kRaysPerTile;
+    const bool active = (long long)ray0 + r < p.num_rays;
+    const int ray = ray0 + r;
 
-    mbar_wait(&full_bar[slot], ph);
-    const float* st = stages + (size_t)slot * kStageFloats;
-    const int lane_off = r * S + q * P;
+    mbar_wait(&full_bar[st], ph, j);
+    const float* sb = stages + (size_t)st * kStageFloats;
 
-    float dd[P], step[P], beta[P], col[3 * P];
+    // ---- optical depth: dd = delta * sigma, float64 exclusive prefix along the ray ----
+    float dd[P];
     {
-      const float4* a = reinterpret_cast<const float4*>(st + 0 * kTileFloats + lane_off);
-      const float4* b = reinterpret_cast<const float4*>(st + 1 * kTileFloats + lane_off);
+      const float4* a = reinterpret_cast<const float4*>(sb + 0 * kTileFloats + lane_off);
+      const float4* b = reinterpret_cast<const float4*>(sb + 1 * kTileFloats + lane_off);
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        float4 x = a[j], y = b[j];
-        dd[4 * j + 0] = y.x * x.x;
-        dd[4 * j + 1] = y.y * x.y;
-        dd[4 * j + 2] = y.z * x.z;
-        dd[4 * j + 3] = y.w * x.w;
-      }
-      const float4* c = reinterpret_cast<const float4*>(st + 2 * kTileFloats + lane_off);
-      const float4* d = reinterpret_cast<const float4*>(st + 3 * kTileFloats + lane_off);
-#pragma unroll
-      for (int j = 0; j < V; ++j) {
-        float4 x = c[j], y = d[j];
-        step[4 * j + 0] = (x.x + y.x) / 2;
-        step[4 * j + 1] = (x.y + y.y) / 2;
-        step[4 * j + 2] = (x.z + y.z) / 2;
-        step[4 * j + 3] = (x.w + y.w) / 2;
-      }
-      if (has_beta) {
-        const float4* e = reinterpret_cast<const float4*>(st + 4 * kTileFloats + lane_off);
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-          float4 x = e[j];
-          beta[4 * j + 0] = x.x;
-          beta[4 * j + 1] = x.y;
-          beta[4 * j + 2] = x.z;
-          beta[4 * j + 3] = x.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < P; ++i) beta[i] = 0.0f;
-      }
-      const float4* f = reinterpret_cast<const float4*>(st + 5 * kTileFloats + 3 * lane_off);
-#pragma unroll
-      for (int j = 0; j < 3 * V; ++j) {
-        float4 x = f[j];
-        col[4 * j + 0] = x.x;
-        col[4 * j + 1] = x.y;
-        col[4 * j + 2] = x.z;
-        col[4 * j + 3] = x.w;
+      for (int v = 0; v < V; ++v) {
+        const float4 x = a[v], y = b[v];
+        dd[4 * v + 0] = __fmul_rn(y.x, x.x);
+        dd[4 * v + 1] = __fmul_rn(y.y, x.y);
+        dd[4 * v + 2] = __fmul_rn(y.z, x.z);
+        dd[4 * v + 3] = __fmul_rn(y.w, x.w);
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[slot]);  // stage can be refilled while we compute
-
-    // ---- scan 1: exclusive prefix of dd in float64, sequential along the ray ----
-    double dd64[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) dd64[i] = (double)dd[i];
     double pre[P];
-    double carry = 0.0;
-#pragma unroll 1
-    for (int qq = 0; qq < kLanesPerRay; ++qq) {
-      if (q == qq) {
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-          pre[i] = carry;
-          carry += dd64[i];
-        }
-      }
-      carry = shfl_double(FULL_MASK, carry, group_base | qq);
-    }
-
-    float wgt[P];
-    float acc = 0.f, e_num = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, var = 0.f;
-    bool nan_beta = false;
+    double run = 0.0;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      const float trans = expf(-(float)pre[i]);
+      pre[i] = run;
+      run += (double)dd[i];
+    }
+    double off = ray_exclusive_offset(run, q, group_base);
+
+    // ---- weights ----
+    float wgt[P];
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const float trans = expf(-(float)(off + pre[i]));
       const float alpha = 1.0f - expf(-dd[i]);
-      const float wi = nan_to_num(alpha * trans);
-      wgt[i] = wi;
-      acc += wi;
-      e_num += wi * step[i];
-      float c0 = col[3 * i + 0], c1 = col[3 * i + 1], c2 = col[3 * i + 2];
-      if (p.eval_mode) {
-        c0 = nan_to_num(c0);
-        c1 = nan_to_num(c1);
-        c2 = nan_to_num(c2);
-        col[3 * i + 0] = c0;
-        col[3 * i + 1] = c1;
-        col[3 * i + 2] = c2;
+      wgt[i] = __fmul_rn(alpha, trans);
+      acc += wgt[i];
+    }
+    acc = reduce4(acc);
+    if (__any_sync(FULL_MASK, non_finite(acc))) {  // rare: some weight is NaN / inf -> torch.nan_to_num
+      acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        wgt[i] = nan_to_num(wgt[i]);
+        acc += wgt[i];
       }
-      cr += wi * c0;
-      cg += wi * c1;
-      cb += wi * c2;
-      float bi = beta[i];
-      if (p.beta_mode == UB_BETA_NAN_GUARD && bi != bi) {
-        bi = 0.0f;
-        nan_beta = true;
-      }
-      var += (wi * wi) * bi;
+      acc = reduce4(acc);
     }
 
-    // ---- scan 2: inclusive prefix of the weights in float64, sequential; median index ----
-    double w64[P];
+    // ---- sample midpoints, chunk bounds ----
+    float step[P];
+    {
+      const float4* c = reinterpret_cast<const float4*>(sb + 2 * kTileFloats + lane_off);
+      const float4* d = reinterpret_cast<const float4*>(sb + 3 * kTileFloats + lane_off);
 #pragma unroll
-    for (int i = 0; i < P; ++i) w64[i] = (double)wgt[i];
-    double cw[P];
-    carry = 0.0;
-#pragma unroll 1
-    for (int qq = 0; qq < kLanesPerRay; ++qq) {
-      if (q == qq) {
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-          carry += w64[i];
-          cw[i] = carry;
-        }
+      for (int v = 0; v < V; ++v) {
+        const float4 x = c[v], y = d[v];
+        step[4 * v + 0] = __fadd_rn(x.x, y.x) * 0.5f;
+        step[4 * v + 1] = __fadd_rn(x.y, y.y) * 0.5f;
+        step[4 * v + 2] = __fadd_rn(x.z, y.z) * 0.5f;
+        step[4 * v + 3] = __fadd_rn(x.w, y.w) * 0.5f;
       }
-      carry = shfl_double(FULL_MASK, carry, group_base | qq);
     }
-    int first = S;  // first sample index with cumulative weight >= 0.5 (searchsorted side=left)
+    bounds.enter(p.tiles_per_chunk > 0 ? tile / p.tiles_per_chunk : 0, p.chunk_ws);
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < P; ++i) bounds.add_step(step[i]);
+    }
+
+    // ---- cumulative weight in float64, first sample with (float)cw >= 0.5 ----
+    run = 0.0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      run += (double)wgt[i];
+      pre[i] = run;
+    }
+    off = ray_exclusive_offset(run, q, group_base);
+    int first = S;
 #pragma unroll
     for (int i = P - 1; i >= 0; --i)
-      if ((float)cw[i] >= 0.5f) first = q * P + i;
+      if (off + pre[i] >= kHalf) first = q * P + i;
     first = min(first, __shfl_xor_sync(FULL_MASK, first, 1));
     first = min(first, __shfl_xor_sync(FULL_MASK, first, 2));
     first = min(first, S - 1);  // clamp(idx, 0, S-1)
+    const int floc = first - q * P;
     float depth = step[0];
 #pragma unroll
-    for (int i = 1; i < P; ++i)
-      if (i == first % P) depth = step[i];
+    for (int i = 1; i < P; ++i) depth = (i == floc) ? step[i] : depth;
     depth = __shfl_sync(FULL_MASK, depth, group_base | (first / P));
 
-    float dvar = 0.f;
+    // ---- expected depth numerator, depth variance ----
+    float e_num = 0.f, dvar = 0.f;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
+      e_num = fmaf(wgt[i], step[i], e_num);
       const float t = step[i] - depth;
-      dvar += wgt[i] * (t * t);
+      dvar = fmaf(wgt[i], t * t, dvar);
     }
 
-    acc = reduce4(acc);
-    e_num = reduce4(e_num);
-    cr = reduce4(cr);
-    cg = reduce4(cg);
-    cb = reduce4(cb);
-    var = reduce4(var);
-    dvar = reduce4(dvar) + 1e-5f;
+    // ---- sum w^2 beta ----
+    float var = 0.f;
+    if (has_beta) {
+      const float4* e = reinterpret_cast<const float4*>(sb + 4 * kTileFloats + lane_off);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float4 x = e[v];
+        var = fmaf(wgt[4 * v + 0] * wgt[4 * v + 0], x.x, var);
+        var = fmaf(wgt[4 * v + 1] * wgt[4 * v + 1], x.y, var);
+        var = fmaf(wgt[4 * v + 2] * wgt[4 * v + 2], x.z, var);
+        var = fmaf(wgt[4 * v + 3] * wgt[4 * v + 3], x.w, var);
+      }
+      var = reduce4(var);
+      if (p.beta_mode == UB_BETA_NAN_GUARD && __any_sync(FULL_MASK, var != var)) {
+        // rare: a NaN sum -- redo with NaN betas zeroed and remember that this chunk had a NaN
+        const float* bs = sb + 4 * kTileFloats + lane_off;
+        bool saw_nan = false;
+        var = 0.f;
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          float bi = bs[i];
+          if (bi != bi) {
+            bi = 0.f;
+            saw_nan = true;
+          }
+          var = fmaf(wgt[i] * wgt[i], bi, var);
+        }
+        var = reduce4(var);
+        if (active && saw_nan) bounds.has_nan = true;
+      }
+    }
 
-    // background: colour of the last sample lives in lane q == 3, local index P-1
-    float b0 = __shfl_sync(FULL_MASK, col[3 * P - 3], group_base | 3);
-    float b1 = __shfl_sync(FULL_MASK, col[3 * P - 2], group_base | 3);
-    float b2 = __shfl_sync(FULL_MASK, col[3 * P - 1], group_base | 3);
+    // ---- colours (read straight from the stage) ----
+    float col[3] = {0.f, 0.f, 0.f};
+    const float* cs = sb + 5 * kTileFloats + 3 * lane_off;
+    {
+      const float4* f = reinterpret_cast<const float4*>(cs);
+#pragma unroll
+      for (int v = 0; v < 3 * V; ++v) {
+        const float4 x = f[v];
+        col[(4 * v + 0) % 3] = fmaf(wgt[(4 * v + 0) / 3], x.x, col[(4 * v + 0) % 3]);
+        col[(4 * v + 1) % 3] = fmaf(wgt[(4 * v + 1) / 3], x.y, col[(4 * v + 1) % 3]);
+        col[(4 * v + 2) % 3] = fmaf(wgt[(4 * v + 2) / 3], x.z, col[(4 * v + 2) % 3]);
+        col[(4 * v + 3) % 3] = fmaf(wgt[(4 * v + 3) / 3], x.w, col[(4 * v + 3) % 3]);
+      }
+    }
+    float cr = reduce4(col[0]), cg = reduce4(col[1]), cb = reduce4(col[2]);
+    const float* last = sb + 5 * kTileFloats + 3 * (r * S + S - 1);  // colour of the ray's last sample
+    float b0 = last[0], b1 = last[1], b2 = last[2];
+    if (p.eval_mode &&
+        __any_sync(FULL_MASK, non_finite(cr) || non_finite(cg) || non_finite(cb))) {
+      // rare: a non-finite colour -> eval-mode nan_to_num(rgb) before the weighted sum
+      col[0] = col[1] = col[2] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3 * P; ++k) col[k % 3] = fmaf(wgt[k / 3], nan_to_num(cs[k]), col[k % 3]);
+      cr = reduce4(col[0]);
+      cg = reduce4(col[1]);
+      cb = reduce4(col[2]);
+      b0 = nan_to_num(b0);
+      b1 = nan_to_num(b1);
+      b2 = nan_to_num(b2);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[st]);  // the stage can be refilled
+
+    e_num = reduce4(e_num);
+    dvar = reduce4(dvar) + 1e-5f;
     if (p.bg_mode == UB_BG_FIXED) {
       b0 = p.bg[0];
       b1 = p.bg[1];
@@ -352,29 +379,19 @@ composite_rays_tma(const CompositeParams p) {
       cg = clamp01_keep_nan(cg);
       cb = clamp01_keep_nan(cb);
     }
-    const float expected = e_num / (acc + 1e-10f);
-
-    // ---- chunk-wide bookkeeping (clip bounds of expected depth, beta NaN flag) ----
-    const long long chunk = p.rays_per_chunk > 0 ? ray0 / p.rays_per_chunk : 0;
-    bounds.enter(chunk, p.chunk_ws);
-    if (active) {
-#pragma unroll
-      for (int i = 0; i < P; ++i) bounds.add_step(step[i]);
-      bounds.has_nan |= nan_beta;
-    }
 
     // ---- outputs: the 4 lanes of a ray split the stores ----
     if (active) {
       if (q == 0) {
         if (p.o_rgb) {
-          p.o_rgb[ray * 3 + 0] = cr;
-          p.o_rgb[ray * 3 + 1] = cg;
-          p.o_rgb[ray * 3 + 2] = cb;
+          p.o_rgb[(size_t)ray * 3 + 0] = cr;
+          p.o_rgb[(size_t)ray * 3 + 1] = cg;
+          p.o_rgb[(size_t)ray * 3 + 2] = cb;
         }
       } else if (q == 1) {
         if (p.o_acc) p.o_acc[ray] = acc;
         if (p.o_depth) p.o_depth[ray] = depth;
-        if (p.o_exp) p.o_exp[ray] = expected;
+        if (p.o_exp) p.o_exp[ray] = e_num / (acc + 1e-10f);
       } else if (q == 2) {
         if (p.o_rgb_var) p.o_rgb_var[ray] = var;
         if (p.o_rgb_std) p.o_rgb_std[ray] = sqrtf(var);
@@ -385,8 +402,8 @@ composite_rays_tma(const CompositeParams p) {
       if (p.o_w) {
         float4* ow = reinterpret_cast<float4*>(p.o_w + (size_t)ray * S + q * P);
 #pragma unroll
-        for (int j = 0; j < V; ++j)
-          ow[j] = make_float4(wgt[4 * j], wgt[4 * j + 1], wgt[4 * j + 2], wgt[4 * j + 3]);
+        for (int v = 0; v < V; ++v)
+          ow[v] = make_float4(wgt[4 * v], wgt[4 * v + 1], wgt[4 * v + 2], wgt[4 * v + 3]);
       }
     }
   }
@@ -608,25 +625,22 @@ static size_t chunk_ws_bytes(long long num_rays, long long rays_per_chunk) {
   return (size_t)chunks * 4 * sizeof(unsigned);
 }
 
-template <int S>
+template <int S, int NCW, int NST>
 static int launch_tma(const CompositeParams& p, cudaStream_t stream) {
-  constexpr int kConsumerWarps = consumer_warps_for(S);
   constexpr size_t stage_bytes = (size_t)kRaysPerTile * S * 8 * 4;
-  constexpr size_t smem = kConsumerWarps * kStagesPerWarp * stage_bytes +
-                          2 * kConsumerWarps * kStagesPerWarp * sizeof(uint64_t);
+  constexpr size_t smem = NST * stage_bytes + 2 * NST * sizeof(uint64_t);
   static_assert(smem <= 227 * 1024, "stage ring exceeds shared memory");
-  cudaError_t e = cudaFuncSetAttribute(composite_rays_tma<S>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = composite_rays_tma<S, NCW, NST>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("composite_rays: cannot reserve %zu B shared memory (%s)", smem, cudaGetErrorString(e));
     return UB_ERR_LAUNCH;
   }
   const long long tiles = (p.num_rays + kRaysPerTile - 1) / kRaysPerTile;
-  const long long want = (tiles + kConsumerWarps - 1) / kConsumerWarps;
   int grid = sm_count();
   if (grid <= 0) grid = 148;
-  if (want < grid) grid = (int)want;
-  composite_rays_tma<S><<<grid, 32 * (1 + kConsumerWarps), smem, stream>>>(p);
+  if (tiles < grid) grid = (int)tiles;
+  kern<<<grid, 32 * (1 + NCW), smem, stream>>>(p);
   return check_launch("composite_rays_tma");
 }
 
@@ -693,7 +707,9 @@ int ub_composite_rays(const ub_composite_rays_args* a, void* workspace, size_t w
 
   if (cudaMemsetAsync(workspace, 0, need, stream) != cudaSuccess) return check_launch("composite_rays memset");
 
-  const bool chunk_ok = a->rays_per_chunk <= 0 || a->rays_per_chunk % kRaysPerTile == 0;
+  const bool chunk_ok = (a->rays_per_chunk <= 0 || a->rays_per_chunk % kRaysPerTile == 0) &&
+                        a->num_rays < (1LL << 31) - 64;
+  p.tiles_per_chunk = a->rays_per_chunk > 0 ? (int)(a->rays_per_chunk / kRaysPerTile) : 0;
   const bool align_ok = aligned16(a->density) && aligned16(a->deltas) && aligned16(a->starts) &&
                         aligned16(a->ends) && aligned16(a->rgb) &&
                         (a->beta == nullptr || aligned16(a->beta)) &&
@@ -702,10 +718,20 @@ int ub_composite_rays(const ub_composite_rays_args* a, void* workspace, size_t w
   bool fast = chunk_ok && align_ok;
   if (fast) {
     switch (a->num_samples) {
-      case 32: rc = launch_tma<32>(p, stream); break;
-      case 48: rc = launch_tma<48>(p, stream); break;
-      case 64: rc = launch_tma<64>(p, stream); break;
-      case 96: rc = launch_tma<96>(p, stream); break;
+      case 32: rc = launch_tma<32, 8, 16>(p, stream); break;
+      case 48: {
+        // tuning hook: consumer warps per CTA / ring stages (default 7 / 14, the fastest measured on B200)
+        static const int ncw = [] { const char* e = getenv("UB_COMPOSITE_NCW"); return e ? atoi(e) : 7; }();
+        static const int nst = [] { const char* e = getenv("UB_COMPOSITE_NST"); return e ? atoi(e) : 14; }();
+#define UB_TRY(N, T) if (ncw == N && nst == T) { rc = launch_tma<48, N, T>(p, stream); break; }
+        UB_TRY(4, 16) UB_TRY(8, 16) UB_TRY(16, 16) UB_TRY(6, 18) UB_TRY(9, 18) UB_TRY(6, 12) UB_TRY(12, 12)
+        UB_TRY(14, 14) UB_TRY(10, 10) UB_TRY(7, 14) UB_TRY(5, 15) UB_TRY(8, 8)
+#undef UB_TRY
+        rc = launch_tma<48, 7, 14>(p, stream);
+        break;
+      }
+      case 64: rc = launch_tma<64, 8, 8>(p, stream); break;
+      case 96: rc = launch_tma<96, 4, 8>(p, stream); break;
       default: fast = false;
     }
   }

@@ -90,18 +90,43 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+#ifdef UB_DEBUG_WAIT
+__device__ unsigned long long g_ub_wait_debug[8];
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+#ifdef UB_DEBUG_WAIT
+  for (long long spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > (1LL << 22)) {
+      if (atomicAdd(&g_ub_wait_debug[0], 1ULL) == 0) {
+        g_ub_wait_debug[1] = blockIdx.x;
+        g_ub_wait_debug[2] = threadIdx.x;
+        g_ub_wait_debug[3] = (unsigned long long)tag;
+        g_ub_wait_debug[4] = parity;
+        g_ub_wait_debug[5] = smem_u32(bar);
+        printf("ub wait timeout: block %d thread %d tag %d parity %u bar %u\n", blockIdx.x, threadIdx.x,
+               tag, parity, smem_u32(bar));
+      }
+      __trap();
+    }
+  }
+#else
+  (void)tag;
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#endif
 }
 // 1-D bulk asynchronous copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 // dst / src 16-byte aligned, bytes a multiple of 16.

@@ -1,0 +1,173 @@
+"""Per-view evaluation pipeline: M member renders -> ensemble reduce -> AUSE / AUCE / NLL record.
+
+This is the data-parallel unit of the hot path: one view = M x R ray-sample
+batches composited, reduced per pixel and scored; views are independent, so ranks take disjoint
+blocks of views and only the fixed-size per-view records are all-gathered (``gather_records``), after
+which the reference's *ordered* host-side aggregation (eval_uncertainty.py:920-946, 1070-1077) makes the
+multi-GPU result identical to the single-GPU one.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import metrics
+from .models import outputs as mo
+
+Tensor = torch.Tensor
+
+RAY_KEYS = ("density", "deltas", "starts", "ends", "rgb", "beta")
+
+# layout of the per-view float64 record that crosses GPUs
+CURVE_KEYS_100 = ("err_mae", "err_mse", "err_rmse", "err_var_mae", "err_var_mse", "err_var_rmse")
+CURVE_KEYS_99 = ("coverage_values", "avg_length_values", "coverage_error_values", "abs_coverage_error_values",
+                 "neg_coverage_error_values")
+SCALAR_KEYS = ("rgb_ause_mse", "rgb_ause_mae", "rgb_ause_rmse", "rgb_mse", "rgb_rmse", "rgb_nll", "rgb_avg_var",
+               "rgb_auc_abs_error", "rgb_auc_length", "rgb_auc_neg_error")
+RECORD_LEN = 100 * len(CURVE_KEYS_100) + 99 * len(CURVE_KEYS_99) + len(SCALAR_KEYS) + 1  # + view id
+
+
+def render_members(members: Sequence[Dict[str, Tensor]], height: int, width: int, rays_per_chunk: int,
+                   timers: Optional[List[Tuple[torch.cuda.Event, torch.cuda.Event]]] = None
+                   ) -> List[Dict[str, Tensor]]:
+    """Composite every member's ray samples (active-nerfacto ``get_outputs`` per eval chunk) and view the
+    per-ray outputs as ``[H, W, C]`` like ``get_outputs_for_camera`` does."""
+    outs = []
+    for m in members:
+        if timers is not None:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+        o = mo.active_nerfacto_outputs(m["density"], m["deltas"], m["starts"], m["ends"], m["rgb"], m["beta"],
+                                       rays_per_chunk=rays_per_chunk)
+        if timers is not None:
+            t1.record()
+            timers.append((t0, t1))
+        outs.append({k: v.view(height, width, -1) for k, v in o.items()})
+    return outs
+
+
+def evaluate_view(members: Sequence[Dict[str, Tensor]], rgb_gt: Tensor, height: int, width: int,
+                  rays_per_chunk: int = 1 << 15, min_rgb_std_for_nll: float = 3e-2,
+                  timers: Optional[list] = None) -> Dict[str, object]:
+    """One view, inputs resident on the device: render M members, reduce, score.  Returns the
+    reference's per-image entries (``get_unc_metrics_rgb`` dict + ``metrics_dict`` scalars)."""
+    outs = render_members(members, height, width, rays_per_chunk, timers)
+    red = mo.ensemble_reduce(outs) if len(outs) > 1 else outs[0]
+    d = metrics.score_rgb_batch(red["rgb"], rgb_gt, red["rgb_std"], min_rgb_std_for_nll)[0]
+    d.update(metrics.per_image_rgb_scalars(d))
+    return d
+
+
+class HostViewEvaluator:
+    """End-to-end entry: the caller holds one view's member ray samples and ground truth in *pinned host*
+    memory; every call copies them to the device on a copy stream (member m+1 uploads while member m
+    composites), runs the pipeline and reads the metric record back."""
+
+    def __init__(self, num_members: int, num_rays: int, num_samples: int, height: int, width: int, device):
+        self.m, self.r, self.s, self.h, self.w = num_members, num_rays, num_samples, height, width
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        shapes = {"density": (num_rays, num_samples, 1), "deltas": (num_rays, num_samples, 1),
+                  "starts": (num_rays, num_samples, 1), "ends": (num_rays, num_samples, 1),
+                  "rgb": (num_rays, num_samples, 3), "beta": (num_rays, num_samples, 1)}
+        self.slots = [{k: torch.empty(s, device=self.device) for k, s in shapes.items()}
+                      for _ in range(num_members)]
+        self.gt_dev = torch.empty(height, width, 3, device=self.device)
+        self.h2d_bytes = num_members * sum(int(np.prod(s)) * 4 for s in shapes.values()) + height * width * 3 * 4
+        self.d2h_bytes = (400 + 5 + 100) * 8  # the packed curve sums / scalar sums / histogram row
+
+    def __call__(self, members_host: Sequence[Dict[str, Tensor]], gt_host: Tensor,
+                 rays_per_chunk: int = 1 << 15) -> Dict[str, object]:
+        main = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_stream(main)  # the previous call has finished reading the device slots
+        events = []
+        with torch.cuda.stream(self.copy_stream):
+            for mh, slot in zip(members_host, self.slots):
+                for k in RAY_KEYS:
+                    slot[k].copy_(mh[k], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                events.append(ev)
+            self.gt_dev.copy_(gt_host, non_blocking=True)
+        outs = []
+        for slot, ev in zip(self.slots, events):
+            main.wait_event(ev)
+            o = mo.active_nerfacto_outputs(slot["density"], slot["deltas"], slot["starts"], slot["ends"], slot["rgb"],
+                                           slot["beta"], rays_per_chunk=rays_per_chunk)
+            outs.append({k: v.view(self.h, self.w, -1) for k, v in o.items()})
+        red = mo.ensemble_reduce(outs) if len(outs) > 1 else outs[0]
+        main.wait_stream(self.copy_stream)
+        d = metrics.score_rgb_batch(red["rgb"], self.gt_dev, red["rgb_std"])[0]
+        d.update(metrics.per_image_rgb_scalars(d))
+        return d
+
+
+def pack_record(view_id: int, d: Dict[str, object]) -> np.ndarray:
+    """Fixed-size float64 record of one view: 6 AUSE curves, 5 AUCE curves, 10 scalars, view id."""
+    parts = [np.asarray(d[k], dtype=np.float64).reshape(100) for k in CURVE_KEYS_100]
+    parts += [np.asarray(d[k], dtype=np.float64).reshape(99) for k in CURVE_KEYS_99]
+    parts.append(np.array([float(d[k]) for k in SCALAR_KEYS] + [float(view_id)], dtype=np.float64))
+    rec = np.concatenate(parts)
+    assert rec.shape == (RECORD_LEN,)
+    return rec
+
+
+def unpack_record(rec: np.ndarray) -> Tuple[int, Dict[str, object]]:
+    d: Dict[str, object] = {}
+    o = 0
+    for k in CURVE_KEYS_100:
+        d[k] = rec[o:o + 100]
+        o += 100
+    for k in CURVE_KEYS_99:
+        d[k] = rec[o:o + 99]
+        o += 99
+    for k in SCALAR_KEYS:
+        d[k] = float(rec[o])
+        o += 1
+    return int(rec[o]), d
+
+
+def gather_records(local: np.ndarray, device=None) -> np.ndarray:
+    """All-gather the ``[views_per_rank, RECORD_LEN]`` float64 records of every rank (the only collective on
+    the path; NCCL all_gather_into_tensor over NVLink when ``device`` is CUDA, gloo on CPU) and return them
+    ordered by view id."""
+    import torch.distributed as dist
+
+    t = torch.from_numpy(np.ascontiguousarray(local))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        allrec = t
+    else:
+        if device is not None:
+            t = t.to(device)
+        out = torch.empty((dist.get_world_size() * t.shape[0], t.shape[1]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        allrec = out.cpu()
+    allrec = allrec.numpy()
+    order = np.argsort(allrec[:, -1], kind="stable")
+    return allrec[order]
+
+
+def aggregate_records(records: np.ndarray) -> Dict[str, object]:
+    """The reference's test-set aggregation (eval_uncertainty.py:920-946, 957-1067, 1070-1077) in view
+    order: float64 running sums of the curves / num_images, float32 ``torch.mean`` of the scalars."""
+    n = records.shape[0]
+    curves: Dict[str, np.ndarray] = {}
+    scal: Dict[str, list] = {k: [] for k in SCALAR_KEYS}
+    for rec in records:
+        _, d = unpack_record(rec)
+        for k in CURVE_KEYS_100 + CURVE_KEYS_99:
+            curves[k] = curves.get(k, np.zeros(len(d[k]))) + d[k]
+        for k in SCALAR_KEYS:
+            scal[k].append(d[k])
+    out: Dict[str, object] = {k: v / n for k, v in curves.items()}
+    for k in SCALAR_KEYS:
+        out[k] = float(torch.mean(torch.tensor(scal[k])))
+    return out
+
+
+def shard_views(num_views: int, rank: int, world_size: int) -> range:
+    """Block distribution of views over ranks."""
+    per = (num_views + world_size - 1) // world_size
+    return range(min(num_views, rank * per), min(num_views, (rank + 1) * per))
