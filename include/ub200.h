@@ -133,19 +133,37 @@ int ub_render_weights(const ub_render_weights_args* args, void* workspace, size_
  * over channels; spread_mode 0 / out_spread NULL skips it.
  * ---------------------------------------------------------------------------------------- */
 enum { UB_SPREAD_NONE = 0, UB_SPREAD_STD = 1, UB_SPREAD_VAR = 2 };
-#define UB_MAX_MEMBERS 64
+#define UB_MAX_MEMBERS 32
+#define UB_MAX_REDUCE_JOBS 16
+#define UB_MAX_REDUCE_BATCH_MEMBERS UB_MAX_MEMBERS
 
 int ub_reduce_members(const float* const* members_host, int32_t num_members, int64_t num_pixels,
                       int32_t channels, int32_t spread_mode, float* out_mean, float* out_spread,
                       void* stream);
+
+/* All output keys of one view in ONE launch: job j reduces its own set of num_members member
+ * tensors (the loop over keys of mcdropout_models.py:121-126 / ensemble_pipeline.py:159-190). */
+typedef struct ub_reduce_job {
+  const float* const* members_host; /* HOST array of num_members DEVICE pointers [num_pixels, channels] */
+  int64_t num_pixels;
+  int32_t channels;
+  int32_t spread_mode;              /* UB_SPREAD_* */
+  float* out_mean;                  /* [num_pixels, channels] or NULL */
+  float* out_spread;                /* [num_pixels] or NULL */
+} ub_reduce_job;
+
+int ub_reduce_members_batched(const ub_reduce_job* jobs_host, int32_t num_jobs, int32_t num_members,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (C1) Metric prologue, NLL and AUCE interval histogram for a batch of images (segments).
  * Replaces scripts/eval_uncertainty.py:323-333 (se / ae / var), :404-412 (NLL), and the 99
  * interval-coverage passes of metrics/auce.py:18-28.
  * pred, target: [total_pixels, channels]; std: [total_pixels] (one sigma per pixel, shared by
- * the channels, as eval_uncertainty.py:371-374 repeats it).  seg_offsets_host: HOST array of
- * num_segments+1 pixel offsets (segment s = [off[s], off[s+1])).
+ * the channels, as eval_uncertainty.py:371-374 repeats it).  seg_offsets: DEVICE array of
+ * num_segments+1 int64 pixel offsets (segment s = [off[s], off[s+1])); segment tables live on the
+ * device so that no call on this path performs a host->device copy (a pageable copy would
+ * synchronise the stream).
  * z_values: DEVICE [num_z] float64, strictly decreasing (norm.ppf(1 - alpha/2)).
  * Outputs: out_sq_err / out_abs_err / out_var [total_pixels] (may be NULL);
  * out_sums [num_segments, UB_PROLOGUE_NSUMS] float64:
@@ -162,7 +180,8 @@ typedef struct ub_score_prologue_args {
   const float* std;
   int32_t channels;               /* 1 or 3 */
   int32_t num_segments;
-  const int64_t* seg_offsets_host;
+  const int64_t* seg_offsets;     /* DEVICE [num_segments + 1] */
+  int64_t max_segment_len;        /* length of the longest segment */
   float nll_min_std;              /* eps of negative_gaussian_loglikelihood */
   int32_t sigma_from_var;         /* 1: interval sigma = sqrt(std*std) as eval_uncertainty.py:371 (rgb); *
                                    * 0: sigma = std (depth, eval_uncertainty.py:612-614)                */
@@ -185,26 +204,28 @@ int ub_score_prologue(const ub_score_prologue_args* args, void* workspace, size_
  * Replaces torch.sort + the 2 x 100 slice means of metrics/ause.py:10-34.
  * Ordering contract == torch.sort(stable=True) on float32: ascending, ties keep ascending
  * original index, -0.0 == +0.0, every NaN after +inf.
- * keys [total] float32 segmented by seg_offsets_host (num_segments+1, HOST).
+ * keys [total] float32 segmented by seg_offsets (DEVICE int64 [num_segments+1]); total and
+ * max_segment_len are the host-side copies of off[num_segments] and the longest segment.
  * out_sorted_keys [total] (may be NULL); out_perm [total] int32: index *within its segment* of
  * the element at each sorted position (NULL for a keys-only sort).
  * ---------------------------------------------------------------------------------------- */
 size_t ub_segmented_sort_workspace_bytes(int32_t num_segments, int64_t total, int64_t max_segment_len,
                                          int32_t with_perm);
-int ub_segmented_sort(const float* keys, int32_t num_segments, const int64_t* seg_offsets_host,
-                      float* out_sorted_keys, int32_t* out_perm, void* workspace,
+int ub_segmented_sort(const float* keys, int32_t num_segments, const int64_t* seg_offsets,
+                      int64_t total, int64_t max_segment_len, float* out_sorted_keys, int32_t* out_perm, void* workspace,
                       size_t workspace_bytes, void* stream);
 
 /* Prefix sums at cut points, float64 accumulation:
- *   out_sums[s, v, c] = sum_{i < cuts[s, c]} values_v[off[s] + (perm ? perm[off[s] + i] : i)]
- * values_host: HOST array of num_values DEVICE pointers [total] float32; perm (DEVICE, may be
- * NULL) as produced by ub_segmented_sort; cuts_host: HOST [num_segments, num_cuts] int64, each
- * in [0, segment length]; out_sums: DEVICE [num_segments, num_values, num_cuts] float64. */
+ *   out_sums[s, v, c] = sum_{i < cuts[s, c]} values_v[off[s] + (perm_v ? perm_v[off[s] + i] : i)]
+ * values_host: HOST array of num_values (<= 8) DEVICE pointers [total] float32; perms_host: HOST
+ * array of num_values DEVICE int32 pointers as produced by ub_segmented_sort (entries, or the whole
+ * array, may be NULL = identity); cuts: DEVICE [num_segments, num_cuts] int64, each in
+ * [0, segment length] (caller's contract); out_sums: DEVICE [num_segments, num_values, num_cuts] float64. */
 size_t ub_cut_prefix_sums_workspace_bytes(int32_t num_segments, int64_t max_segment_len,
                                           int32_t num_values, int32_t num_cuts);
-int ub_cut_prefix_sums(const float* const* values_host, int32_t num_values, const int32_t* perm,
-                       int32_t num_segments, const int64_t* seg_offsets_host,
-                       const int64_t* cuts_host, int32_t num_cuts, double* out_sums,
+int ub_cut_prefix_sums(const float* const* values_host, const int32_t* const* perms_host,
+                       int32_t num_values, int32_t num_segments, const int64_t* seg_offsets,
+                       int64_t max_segment_len, const int64_t* cuts, int32_t num_cuts, double* out_sums,
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -19,7 +19,8 @@ UB_BETA_RAW, UB_BETA_NAN_GUARD = 0, 1
 UB_SPREAD_NONE, UB_SPREAD_STD, UB_SPREAD_VAR = 0, 1, 2
 UB_ACT_IDENTITY, UB_ACT_SIGMOID, UB_ACT_EXP = 0, 1, 2
 UB_PROLOGUE_NSUMS = 5
-UB_MAX_MEMBERS = 64
+UB_MAX_MEMBERS = 32
+UB_MAX_REDUCE_JOBS = 16
 UB_TILE = 16
 
 fp = C.c_void_p  # device pointers travel as void*
@@ -46,10 +47,17 @@ class RenderWeightsArgs(C.Structure):
     ]
 
 
+class ReduceJob(C.Structure):
+    _fields_ = [
+        ("members_host", C.POINTER(fp)), ("num_pixels", C.c_int64), ("channels", C.c_int32),
+        ("spread_mode", C.c_int32), ("out_mean", fp), ("out_spread", fp),
+    ]
+
+
 class ScorePrologueArgs(C.Structure):
     _fields_ = [
         ("pred", fp), ("target", fp), ("std", fp),
-        ("channels", C.c_int32), ("num_segments", C.c_int32), ("seg_offsets_host", C.POINTER(C.c_int64)),
+        ("channels", C.c_int32), ("num_segments", C.c_int32), ("seg_offsets", fp), ("max_segment_len", C.c_int64),
         ("nll_min_std", C.c_float), ("sigma_from_var", C.c_int32),
         ("z_values", fp), ("num_z", C.c_int32),
         ("out_sq_err", fp), ("out_abs_err", fp), ("out_var", fp), ("out_sums", fp), ("out_hist", fp),
@@ -66,13 +74,14 @@ SIGNATURES = {
     "ub_render_weights_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "ub_render_weights": (C.c_int, [C.POINTER(RenderWeightsArgs), fp, C.c_size_t, fp]),
     "ub_reduce_members": (C.c_int, [C.POINTER(fp), C.c_int32, C.c_int64, C.c_int32, C.c_int32, fp, fp, fp]),
+    "ub_reduce_members_batched": (C.c_int, [C.POINTER(ReduceJob), C.c_int32, C.c_int32, fp]),
     "ub_score_prologue_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int32]),
     "ub_score_prologue": (C.c_int, [C.POINTER(ScorePrologueArgs), fp, C.c_size_t, fp]),
     "ub_segmented_sort_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int64, C.c_int32]),
-    "ub_segmented_sort": (C.c_int, [fp, C.c_int32, C.POINTER(C.c_int64), fp, fp, fp, C.c_size_t, fp]),
+    "ub_segmented_sort": (C.c_int, [fp, C.c_int32, fp, C.c_int64, C.c_int64, fp, fp, fp, C.c_size_t, fp]),
     "ub_cut_prefix_sums_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int32, C.c_int32]),
-    "ub_cut_prefix_sums": (C.c_int, [C.POINTER(fp), C.c_int32, fp, C.c_int32, C.POINTER(C.c_int64),
-                                     C.POINTER(C.c_int64), C.c_int32, fp, fp, C.c_size_t, fp]),
+    "ub_cut_prefix_sums": (C.c_int, [C.POINTER(fp), C.POINTER(fp), C.c_int32, C.c_int32, fp, C.c_int64,
+                                     fp, C.c_int32, fp, fp, C.c_size_t, fp]),
     "ub_laplace_ll_moments": (C.c_int, [fp, C.c_int64, C.c_int32, C.c_int32, fp, C.c_int32, C.c_int32,
                                         fp, fp, fp, fp]),
     "ub_composite_tiles": (C.c_int, [fp, fp, fp, fp, C.c_int32, fp, fp, C.c_int32, C.c_int32,

@@ -9,8 +9,9 @@
 // ties keep ascending original index, -0.0 == +0.0, every NaN after +inf.
 //
 // Layout: a batch of images is one flat key array split into segments.  Four 8-bit passes, each
-//   upsweep   : per-tile digit histogram                      -> counts[seg][digit][tile]
-//   scan      : exclusive scan over (digit, tile) per segment -> global offsets inside the segment
+//   upsweep   : per-tile digit histogram                       -> counts[seg][digit][tile]
+//   scan      : one block per (digit, segment) scans its row of tile counts and records the digit
+//               total; the downsweep turns the 256 totals into digit bases itself
 //   downsweep : stable rank inside the tile (warp match-any multi-split, warp-private counters),
 //               local reorder through shared memory, run-coalesced scatter.
 // Pass 0 reads the float keys and synthesises the payload (index within the segment); pass 3
@@ -35,6 +36,7 @@ struct SortPass {
   int32_t* out_vals;         // NULL for keys-only
   const long long* seg_offsets;
   uint32_t* counts;          // [num_segments][kRadix][max_tiles]
+  uint32_t* totals;          // [num_segments][kRadix]
   int max_tiles;
   int shift;
   int first_pass;
@@ -43,6 +45,31 @@ struct SortPass {
 
 __device__ __forceinline__ uint32_t load_key(const SortPass& p, long long gidx) {
   return p.first_pass ? sort_key_from_float(p.in_float[gidx]) : p.in_keys[gidx];
+}
+
+// block-wide exclusive scan of one value per thread (256 threads); returns the exclusive prefix and
+// leaves the block total in *total_out (shared)
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* warp_tmp,
+                                                             uint32_t* total_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(FULL_MASK, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) warp_tmp[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) {
+    const uint32_t t = warp_tmp[w];
+    if (w < warp) base += t;
+    tot += t;
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = tot;
+  __syncthreads();
+  return base + incl - v;
 }
 
 __global__ void __launch_bounds__(kSortThreads) sort_upsweep(const SortPass p) {
@@ -67,46 +94,24 @@ __global__ void __launch_bounds__(kSortThreads) sort_upsweep(const SortPass p) {
   p.counts[((size_t)seg * kRadix + threadIdx.x) * p.max_tiles + tile] = v;
 }
 
-// One block per segment: exclusive scan of counts in (digit, tile) order, in place.
-__global__ void __launch_bounds__(1024) sort_scan(uint32_t* counts, const long long* seg_offsets,
-                                                  int max_tiles) {
-  __shared__ uint32_t warp_tot[32];
-  const int seg = blockIdx.x;
-  const long long len = seg_offsets[seg + 1] - seg_offsets[seg];
+// One block per (digit, segment): exclusive scan of that digit's tile counts in place + digit total.
+__global__ void __launch_bounds__(kSortThreads) sort_scan_rows(const SortPass p) {
+  __shared__ uint32_t warp_tmp[kSortWarps];
+  __shared__ uint32_t chunk_total;
+  const int d = blockIdx.x, seg = blockIdx.y;
+  const long long len = p.seg_offsets[seg + 1] - p.seg_offsets[seg];
   const int tiles = (int)((len + kTile - 1) / kTile);
-  if (tiles == 0) return;
-  uint32_t* c = counts + (size_t)seg * kRadix * max_tiles;
-  const int total = kRadix * tiles;
-  const int per = (total + 1023) / 1024;
-  const int lo = threadIdx.x * per, hi = min(total, lo + per);
-  uint32_t sum = 0;
-  for (int i = lo; i < hi; ++i) sum += c[(size_t)(i / tiles) * max_tiles + (i % tiles)];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t u = __shfl_up_sync(FULL_MASK, incl, o);
-    if (lane >= o) incl += u;
+  uint32_t* row = p.counts + ((size_t)seg * kRadix + d) * p.max_tiles;
+  uint32_t carry = 0;
+  for (int base = 0; base < tiles; base += kSortThreads) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = i < tiles ? row[i] : 0u;
+    const uint32_t ex = block_exclusive_scan_256(v, warp_tmp, &chunk_total);
+    if (i < tiles) row[i] = carry + ex;
+    carry += chunk_total;
+    __syncthreads();
   }
-  if (lane == 31) warp_tot[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t t = warp_tot[lane], ti = t;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t u = __shfl_up_sync(FULL_MASK, ti, o);
-      if (lane >= o) ti += u;
-    }
-    warp_tot[lane] = ti - t;
-  }
-  __syncthreads();
-  uint32_t run = warp_tot[warp] + incl - sum;
-  for (int i = lo; i < hi; ++i) {
-    uint32_t* q = &c[(size_t)(i / tiles) * max_tiles + (i % tiles)];
-    const uint32_t v = *q;
-    *q = run;
-    run += v;
-  }
+  if (threadIdx.x == 0) p.totals[(size_t)seg * kRadix + d] = carry;
 }
 
 template <bool WITH_VALS>
@@ -145,7 +150,13 @@ __global__ void __launch_bounds__(kSortThreads) sort_downsweep(const SortPass p)
       if (WITH_VALS) val[i] = 0;
     }
   }
-  __syncthreads();  // counters zeroed
+  // global base of every digit for this tile: exclusive scan of the 256 digit totals + row prefix
+  {
+    const int d = threadIdx.x;
+    const uint32_t tot = p.totals[(size_t)seg * kRadix + d];
+    const uint32_t base = block_exclusive_scan_256(tot, scan_tmp, nullptr);  // also syncs: counters zeroed
+    gofs[d] = base + p.counts[((size_t)seg * kRadix + d) * p.max_tiles + tile];
+  }
 
   // stable rank within the warp, digit by digit group (match-any multi-split)
 #pragma unroll
@@ -166,29 +177,16 @@ __global__ void __launch_bounds__(kSortThreads) sort_downsweep(const SortPass p)
   __syncthreads();
 
   // per digit: exclusive scan over warps (thread d owns digit d), then over digits
-  uint32_t total = 0;
   {
     const int d = threadIdx.x;
+    uint32_t total = 0;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
       const uint32_t t = cnt[w][d];
       cnt[w][d] = total;
       total += t;
     }
-    uint32_t incl = total;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t u = __shfl_up_sync(FULL_MASK, incl, o);
-      if (lane >= o) incl += u;
-    }
-    if (lane == 31) scan_tmp[warp] = incl;
-    __syncthreads();
-    uint32_t base = 0;
-#pragma unroll
-    for (int w = 0; w < kSortWarps; ++w)
-      if (w < warp) base += scan_tmp[w];
-    digit_start[d] = base + incl - total;
-    gofs[d] = p.counts[((size_t)seg * kRadix + d) * p.max_tiles + tile];
+    digit_start[d] = block_exclusive_scan_256(total, scan_tmp, nullptr);
   }
   __syncthreads();
 
@@ -220,7 +218,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_downsweep(const SortPass p)
 }
 
 struct SortLayout {
-  size_t off_offsets, off_counts, off_keys_a, off_keys_b, off_vals_a, off_vals_b, total;
+  size_t off_offsets, off_counts, off_totals, off_keys_a, off_keys_b, off_vals_a, off_vals_b, total;
   int max_tiles;
 };
 static SortLayout sort_layout(int num_segments, long long total, long long max_len, bool with_vals) {
@@ -232,6 +230,8 @@ static SortLayout sort_layout(int num_segments, long long total, long long max_l
   o = align_up(o + (size_t)(num_segments + 1) * sizeof(long long), 256);
   l.off_counts = o;
   o = align_up(o + (size_t)num_segments * kRadix * l.max_tiles * sizeof(uint32_t), 256);
+  l.off_totals = o;
+  o = align_up(o + (size_t)num_segments * kRadix * sizeof(uint32_t), 256);
   l.off_keys_a = o;
   o = align_up(o + (size_t)total * 4, 256);
   l.off_keys_b = o;
@@ -248,12 +248,12 @@ static SortLayout sort_layout(int num_segments, long long total, long long max_l
 // Prefix sums at cut points (float64, deterministic two-level reduction).
 constexpr int kCutChunk = 2048;
 constexpr int kCutThreads = 256;
-constexpr int kMaxCutValues = 4;
+constexpr int kMaxCutValues = 8;
 
 struct CutParams {
   const float* values[kMaxCutValues];
+  const int32_t* perms[kMaxCutValues];  // per value array: gather permutation or NULL
   int num_values;
-  const int32_t* perm;
   const long long* seg_offsets;
   const long long* cuts;  // [num_segments][num_cuts]
   int num_cuts;
@@ -274,23 +274,24 @@ __device__ __forceinline__ double block_sum_256(double v, double* red) {
   return t;  // valid in thread 0
 }
 
+// grid (block, value, segment)
 __global__ void __launch_bounds__(kCutThreads) cut_block_totals(const CutParams p) {
   __shared__ double red[kCutThreads / 32];
-  const int seg = blockIdx.y, blk = blockIdx.x;
+  const int blk = blockIdx.x, v = blockIdx.y, seg = blockIdx.z;
   const long long seg_lo = p.seg_offsets[seg];
   const long long len = p.seg_offsets[seg + 1] - seg_lo;
   const long long lo = (long long)blk * kCutChunk;
   if (lo >= len) return;
   const long long hi = min(len, lo + kCutChunk);
-  double acc[kMaxCutValues] = {0.0, 0.0, 0.0, 0.0};
+  const float* val = p.values[v];
+  const int32_t* perm = p.perms[v];
+  double acc = 0.0;
   for (long long i = lo + threadIdx.x; i < hi; i += kCutThreads) {
-    const long long src = seg_lo + (p.perm ? (long long)p.perm[seg_lo + i] : i);
-    for (int v = 0; v < p.num_values; ++v) acc[v] += (double)p.values[v][src];
+    const long long src = seg_lo + (perm ? (long long)perm[seg_lo + i] : i);
+    acc += (double)val[src];
   }
-  for (int v = 0; v < p.num_values; ++v) {
-    const double t = block_sum_256(acc[v], red);
-    if (threadIdx.x == 0) p.block_tot[((size_t)seg * p.num_values + v) * p.max_blocks + blk] = t;
-  }
+  const double t = block_sum_256(acc, red);
+  if (threadIdx.x == 0) p.block_tot[((size_t)seg * p.num_values + v) * p.max_blocks + blk] = t;
 }
 
 // one block per (cut, value, segment)
@@ -301,11 +302,13 @@ __global__ void __launch_bounds__(kCutThreads) cut_prefix_finish(const CutParams
   const long long cut = p.cuts[(size_t)seg * p.num_cuts + c];
   const long long full_blocks = cut / kCutChunk;
   const double* bt = p.block_tot + ((size_t)seg * p.num_values + v) * p.max_blocks;
+  const float* val = p.values[v];
+  const int32_t* perm = p.perms[v];
   double acc = 0.0;
   for (long long b = threadIdx.x; b < full_blocks; b += kCutThreads) acc += bt[b];
   for (long long i = full_blocks * kCutChunk + threadIdx.x; i < cut; i += kCutThreads) {
-    const long long src = seg_lo + (p.perm ? (long long)p.perm[seg_lo + i] : i);
-    acc += (double)p.values[v][src];
+    const long long src = seg_lo + (perm ? (long long)perm[seg_lo + i] : i);
+    acc += (double)val[src];
   }
   const double t = block_sum_256(acc, red);
   if (threadIdx.x == 0) p.out[((size_t)seg * p.num_values + v) * p.num_cuts + c] = t;
@@ -330,12 +333,6 @@ static CutLayout cut_layout(int num_segments, long long max_len, int num_values,
   return l;
 }
 
-static long long max_len_of(const int64_t* off, int n) {
-  long long m = 0;
-  for (int i = 0; i < n; ++i) m = off[i + 1] - off[i] > m ? off[i + 1] - off[i] : m;
-  return m;
-}
-
 }  // namespace ub
 
 extern "C" {
@@ -346,18 +343,15 @@ size_t ub_segmented_sort_workspace_bytes(int32_t num_segments, int64_t total, in
   return ub::sort_layout(num_segments, total, max_segment_len, with_perm != 0).total;
 }
 
-int ub_segmented_sort(const float* keys, int32_t num_segments, const int64_t* seg_offsets_host,
-                      float* out_sorted_keys, int32_t* out_perm, void* workspace,
+int ub_segmented_sort(const float* keys, int32_t num_segments, const int64_t* seg_offsets, int64_t total,
+                      int64_t max_segment_len, float* out_sorted_keys, int32_t* out_perm, void* workspace,
                       size_t workspace_bytes, void* stream_v) {
   using namespace ub;
-  UB_REQUIRE(num_segments >= 1 && num_segments <= 65535 && seg_offsets_host != nullptr, UB_ERR_BAD_ARG,
+  UB_REQUIRE(num_segments >= 1 && num_segments <= 65535 && seg_offsets != nullptr, UB_ERR_BAD_ARG,
              "segmented_sort: bad segments");
-  const int64_t* off = seg_offsets_host;
-  for (int s = 0; s < num_segments; ++s)
-    UB_REQUIRE(off[s + 1] >= off[s] && off[s] >= 0, UB_ERR_BAD_ARG,
-               "segmented_sort: segment offsets must be non-decreasing");
-  const long long total = off[num_segments];
-  const long long max_len = max_len_of(off, num_segments);
+  UB_REQUIRE(total >= 0 && max_segment_len >= 0 && max_segment_len <= total, UB_ERR_BAD_ARG,
+             "segmented_sort: bad total / max_segment_len");
+  const long long max_len = max_segment_len;
   UB_REQUIRE(max_len <= 0x7FFFFFFFLL, UB_ERR_UNSUPPORTED, "segmented_sort: segment longer than 2^31-1");
   UB_REQUIRE(out_sorted_keys != nullptr || out_perm != nullptr, UB_ERR_BAD_ARG,
              "segmented_sort: nothing to output");
@@ -369,9 +363,6 @@ int ub_segmented_sort(const float* keys, int32_t num_segments, const int64_t* se
              "segmented_sort: workspace %zu B < required %zu B", workspace_bytes, lay.total);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   char* ws = static_cast<char*>(workspace);
-  if (cudaMemcpyAsync(ws + lay.off_offsets, off, (size_t)(num_segments + 1) * sizeof(int64_t),
-                      cudaMemcpyHostToDevice, stream) != cudaSuccess)
-    return check_launch("segmented_sort offsets copy");
 
   uint32_t* ka = reinterpret_cast<uint32_t*>(ws + lay.off_keys_a);
   uint32_t* kb = reinterpret_cast<uint32_t*>(ws + lay.off_keys_b);
@@ -379,10 +370,12 @@ int ub_segmented_sort(const float* keys, int32_t num_segments, const int64_t* se
   int32_t* vb = reinterpret_cast<int32_t*>(ws + lay.off_vals_b);
 
   dim3 grid((unsigned)lay.max_tiles, (unsigned)num_segments);
+  dim3 grid_scan(kRadix, (unsigned)num_segments);
   for (int pass = 0; pass < 4; ++pass) {
     SortPass p{};
-    p.seg_offsets = reinterpret_cast<const long long*>(ws + lay.off_offsets);
+    p.seg_offsets = reinterpret_cast<const long long*>(seg_offsets);
     p.counts = reinterpret_cast<uint32_t*>(ws + lay.off_counts);
+    p.totals = reinterpret_cast<uint32_t*>(ws + lay.off_totals);
     p.max_tiles = lay.max_tiles;
     p.shift = pass * 8;
     p.first_pass = pass == 0;
@@ -398,7 +391,7 @@ int ub_segmented_sort(const float* keys, int32_t num_segments, const int64_t* se
       p.out_vals = out_perm;
     }
     sort_upsweep<<<grid, kSortThreads, 0, stream>>>(p);
-    sort_scan<<<num_segments, 1024, 0, stream>>>(p.counts, p.seg_offsets, p.max_tiles);
+    sort_scan_rows<<<grid_scan, kSortThreads, 0, stream>>>(p);
     if (with_vals)
       sort_downsweep<true><<<grid, kSortThreads, 0, stream>>>(p);
     else
@@ -415,53 +408,40 @@ size_t ub_cut_prefix_sums_workspace_bytes(int32_t num_segments, int64_t max_segm
   return ub::cut_layout(num_segments, max_segment_len, num_values, num_cuts).total;
 }
 
-int ub_cut_prefix_sums(const float* const* values_host, int32_t num_values, const int32_t* perm,
-                       int32_t num_segments, const int64_t* seg_offsets_host,
-                       const int64_t* cuts_host, int32_t num_cuts, double* out_sums,
+int ub_cut_prefix_sums(const float* const* values_host, const int32_t* const* perms_host,
+                       int32_t num_values, int32_t num_segments, const int64_t* seg_offsets,
+                       int64_t max_segment_len, const int64_t* cuts, int32_t num_cuts, double* out_sums,
                        void* workspace, size_t workspace_bytes, void* stream_v) {
   using namespace ub;
   UB_REQUIRE(values_host != nullptr && num_values >= 1 && num_values <= kMaxCutValues, UB_ERR_BAD_ARG,
              "cut_prefix_sums: num_values must be in [1, %d]", kMaxCutValues);
-  UB_REQUIRE(num_segments >= 1 && num_segments <= 65535 && seg_offsets_host != nullptr, UB_ERR_BAD_ARG,
+  UB_REQUIRE(num_segments >= 1 && num_segments <= 65535 && seg_offsets != nullptr, UB_ERR_BAD_ARG,
              "cut_prefix_sums: bad segments");
-  UB_REQUIRE(num_cuts >= 1 && cuts_host != nullptr && out_sums != nullptr, UB_ERR_BAD_ARG,
+  UB_REQUIRE(num_cuts >= 1 && cuts != nullptr && out_sums != nullptr && max_segment_len >= 0, UB_ERR_BAD_ARG,
              "cut_prefix_sums: bad cuts / output");
-  const int64_t* off = seg_offsets_host;
-  for (int s = 0; s < num_segments; ++s) {
-    UB_REQUIRE(off[s + 1] >= off[s] && off[s] >= 0, UB_ERR_BAD_ARG,
-               "cut_prefix_sums: segment offsets must be non-decreasing");
-    for (int c = 0; c < num_cuts; ++c) {
-      const int64_t cut = cuts_host[(size_t)s * num_cuts + c];
-      UB_REQUIRE(cut >= 0 && cut <= off[s + 1] - off[s], UB_ERR_BAD_ARG,
-                 "cut_prefix_sums: cut %lld outside segment %d", (long long)cut, s);
-    }
-  }
   for (int v = 0; v < num_values; ++v)
-    UB_REQUIRE(values_host[v] != nullptr || off[num_segments] == 0, UB_ERR_BAD_ARG,
+    UB_REQUIRE(values_host[v] != nullptr || max_segment_len == 0, UB_ERR_BAD_ARG,
                "cut_prefix_sums: values[%d] is NULL", v);
-  const long long max_len = max_len_of(off, num_segments);
+  const long long max_len = max_segment_len;
   const CutLayout lay = cut_layout(num_segments, max_len, num_values, num_cuts);
   UB_REQUIRE(workspace != nullptr && workspace_bytes >= lay.total, UB_ERR_WORKSPACE,
              "cut_prefix_sums: workspace %zu B < required %zu B", workspace_bytes, lay.total);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   char* ws = static_cast<char*>(workspace);
-  if (cudaMemcpyAsync(ws + lay.off_offsets, off, (size_t)(num_segments + 1) * sizeof(int64_t),
-                      cudaMemcpyHostToDevice, stream) != cudaSuccess ||
-      cudaMemcpyAsync(ws + lay.off_cuts, cuts_host, (size_t)num_segments * num_cuts * sizeof(int64_t),
-                      cudaMemcpyHostToDevice, stream) != cudaSuccess)
-    return check_launch("cut_prefix_sums host copies");
   CutParams p{};
-  for (int v = 0; v < num_values; ++v) p.values[v] = values_host[v];
+  for (int v = 0; v < num_values; ++v) {
+    p.values[v] = values_host[v];
+    p.perms[v] = perms_host ? perms_host[v] : nullptr;
+  }
   p.num_values = num_values;
-  p.perm = perm;
-  p.seg_offsets = reinterpret_cast<const long long*>(ws + lay.off_offsets);
-  p.cuts = reinterpret_cast<const long long*>(ws + lay.off_cuts);
+  p.seg_offsets = reinterpret_cast<const long long*>(seg_offsets);
+  p.cuts = reinterpret_cast<const long long*>(cuts);
   p.num_cuts = num_cuts;
   p.block_tot = reinterpret_cast<double*>(ws + lay.off_tot);
   p.max_blocks = lay.max_blocks;
   p.out = out_sums;
   if (max_len > 0) {
-    dim3 g1((unsigned)lay.max_blocks, (unsigned)num_segments);
+    dim3 g1((unsigned)lay.max_blocks, (unsigned)num_values, (unsigned)num_segments);
     cut_block_totals<<<g1, kCutThreads, 0, stream>>>(p);
   }
   dim3 g2((unsigned)num_cuts, (unsigned)num_values, (unsigned)num_segments);

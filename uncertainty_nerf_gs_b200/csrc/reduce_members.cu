@@ -6,34 +6,41 @@
 //
 // One streaming pass: every member image is read exactly once through its own pointer (no
 // torch.stack copy), each thread owns 4 consecutive pixels (128-bit loads), and the K values of an
-// element never leave registers.  The spread uses shifted sums in float64 (shift = first member),
-// which is exact for identical members and has no mean^2/var cancellation; torch's CPU kernel
-// (Welford with float64 accumulators) agrees to float32 rounding.
+// element never leave registers.  All output keys of a view (rgb, depth, accumulation, ...) go
+// through ONE launch: blockIdx.y selects the key ("job").  The spread uses shifted sums in float64
+// (shift = first member), which is exact for identical members and has no mean^2/var
+// cancellation; torch's CPU kernel (Welford with float64 accumulators) agrees to float32 rounding.
 #include "ub_common.cuh"
 
 namespace ub {
 
-struct ReduceParams {
-  const float* member[UB_MAX_MEMBERS];
-  int num_members;
+constexpr int kMaxJobs = UB_MAX_REDUCE_JOBS;
+constexpr int kMaxBatchMembers = UB_MAX_REDUCE_BATCH_MEMBERS;
+
+struct ReduceJob {
   long long num_pixels;
+  int channels;
   int spread_mode;
   float* out_mean;
   float* out_spread;
+  int vec_ok;
+};
+struct ReduceBatch {
+  const float* member[kMaxJobs][kMaxBatchMembers];
+  ReduceJob job[kMaxJobs];
+  int num_members;
 };
 
 template <int C>
-__device__ __forceinline__ void reduce_pixels(const ReduceParams& p, long long pix0, int npix,
-                                              bool vec) {
-  // npix pixels starting at pix0 (npix == 4 on the vector path)
+__device__ __forceinline__ void reduce_pixels(const float* const* member, int K, const ReduceJob& jb,
+                                              long long pix0, int npix, bool vec) {
   constexpr int E = 4 * C;  // elements per thread
-  const int K = p.num_members;
   float x0[E];
   double s1[E], s2[E];
   const long long e0 = pix0 * C;
   const int ne = npix * C;
   if (vec) {
-    const float4* src = reinterpret_cast<const float4*>(p.member[0] + e0);
+    const float4* src = reinterpret_cast<const float4*>(member[0] + e0);
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       float4 v = src[j];
@@ -44,7 +51,7 @@ __device__ __forceinline__ void reduce_pixels(const ReduceParams& p, long long p
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < E; ++i) x0[i] = i < ne ? p.member[0][e0 + i] : 0.f;
+    for (int i = 0; i < E; ++i) x0[i] = i < ne ? member[0][e0 + i] : 0.f;
   }
 #pragma unroll
   for (int i = 0; i < E; ++i) {
@@ -54,7 +61,7 @@ __device__ __forceinline__ void reduce_pixels(const ReduceParams& p, long long p
   for (int k = 1; k < K; ++k) {
     float x[E];
     if (vec) {
-      const float4* src = reinterpret_cast<const float4*>(p.member[k] + e0);
+      const float4* src = reinterpret_cast<const float4*>(member[k] + e0);
 #pragma unroll
       for (int j = 0; j < C; ++j) {
         float4 v = src[j];
@@ -65,7 +72,7 @@ __device__ __forceinline__ void reduce_pixels(const ReduceParams& p, long long p
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < E; ++i) x[i] = i < ne ? p.member[k][e0 + i] : 0.f;
+      for (int i = 0; i < E; ++i) x[i] = i < ne ? member[k][e0 + i] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < E; ++i) {
@@ -78,19 +85,19 @@ __device__ __forceinline__ void reduce_pixels(const ReduceParams& p, long long p
   float mean[E];
 #pragma unroll
   for (int i = 0; i < E; ++i) mean[i] = (float)((double)x0[i] + s1[i] * inv_k);
-  if (p.out_mean) {
+  if (jb.out_mean) {
     if (vec) {
-      float4* dst = reinterpret_cast<float4*>(p.out_mean + e0);
+      float4* dst = reinterpret_cast<float4*>(jb.out_mean + e0);
 #pragma unroll
       for (int j = 0; j < C; ++j)
         dst[j] = make_float4(mean[4 * j], mean[4 * j + 1], mean[4 * j + 2], mean[4 * j + 3]);
     } else {
 #pragma unroll
       for (int i = 0; i < E; ++i)
-        if (i < ne) p.out_mean[e0 + i] = mean[i];
+        if (i < ne) jb.out_mean[e0 + i] = mean[i];
     }
   }
-  if (p.spread_mode != UB_SPREAD_NONE && p.out_spread) {
+  if (jb.spread_mode != UB_SPREAD_NONE && jb.out_spread) {
     float spread[4];
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
@@ -100,104 +107,136 @@ __device__ __forceinline__ void reduce_pixels(const ReduceParams& p, long long p
         const int i = px * C + c;
         double var = (s2[i] - s1[i] * s1[i] * inv_k) / (double)(K - 1);  // K == 1 -> NaN like torch
         if (var < 0.0) var = 0.0;
-        const float v = p.spread_mode == UB_SPREAD_STD ? (float)sqrt(var) : (float)var;
+        const float v = jb.spread_mode == UB_SPREAD_STD ? (float)sqrt(var) : (float)var;
         acc = c == 0 ? v : acc + v;
       }
       spread[px] = C == 1 ? acc : acc / (float)C;
     }
     if (vec) {
-      *reinterpret_cast<float4*>(p.out_spread + pix0) =
+      *reinterpret_cast<float4*>(jb.out_spread + pix0) =
           make_float4(spread[0], spread[1], spread[2], spread[3]);
     } else {
 #pragma unroll
       for (int px = 0; px < 4; ++px)
-        if (px < npix) p.out_spread[pix0 + px] = spread[px];
+        if (px < npix) jb.out_spread[pix0 + px] = spread[px];
     }
   }
 }
 
-template <int C>
-__global__ void __launch_bounds__(256) reduce_members_kernel(const ReduceParams p, int vec_ok) {
-  const long long groups = (p.num_pixels + 3) / 4;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
-    const long long pix0 = g * 4;
-    const int npix = (int)min(4LL, p.num_pixels - pix0);
-    reduce_pixels<C>(p, pix0, npix, vec_ok && npix == 4);
-  }
-}
-
-// Any channel count: one thread per pixel, scalar loads.
-__global__ void __launch_bounds__(256) reduce_members_any_c(const ReduceParams p, int C) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const int K = p.num_members;
+// any channel count: one thread per pixel, scalar loads
+__device__ __forceinline__ void reduce_pixel_any_c(const float* const* member, int K, const ReduceJob& jb,
+                                                   long long px) {
+  const int C = jb.channels;
   const double inv_k = 1.0 / (double)K;
-  for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < p.num_pixels; px += stride) {
-    float acc = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const long long e = px * C + c;
-      const float x0 = p.member[0][e];
-      double s1 = 0.0, s2 = 0.0;
-      for (int k = 1; k < K; ++k) {
-        const double d = (double)p.member[k][e] - (double)x0;
-        s1 += d;
-        s2 += d * d;
-      }
-      if (p.out_mean) p.out_mean[e] = (float)((double)x0 + s1 * inv_k);
-      double var = (s2 - s1 * s1 * inv_k) / (double)(K - 1);
-      if (var < 0.0) var = 0.0;
-      const float v = p.spread_mode == UB_SPREAD_STD ? (float)sqrt(var) : (float)var;
-      acc = c == 0 ? v : acc + v;
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const long long e = px * C + c;
+    const float x0 = member[0][e];
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 1; k < K; ++k) {
+      const double d = (double)member[k][e] - (double)x0;
+      s1 += d;
+      s2 += d * d;
     }
-    if (p.spread_mode != UB_SPREAD_NONE && p.out_spread) p.out_spread[px] = C == 1 ? acc : acc / (float)C;
+    if (jb.out_mean) jb.out_mean[e] = (float)((double)x0 + s1 * inv_k);
+    double var = (s2 - s1 * s1 * inv_k) / (double)(K - 1);
+    if (var < 0.0) var = 0.0;
+    const float v = jb.spread_mode == UB_SPREAD_STD ? (float)sqrt(var) : (float)var;
+    acc = c == 0 ? v : acc + v;
+  }
+  if (jb.spread_mode != UB_SPREAD_NONE && jb.out_spread) jb.out_spread[px] = C == 1 ? acc : acc / (float)C;
+}
+
+__global__ void __launch_bounds__(256) reduce_members_batched_kernel(const __grid_constant__ ReduceBatch b) {
+  const ReduceJob& jb = b.job[blockIdx.y];
+  const float* const* member = b.member[blockIdx.y];
+  const int K = b.num_members;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (jb.channels == 1 || jb.channels == 3) {
+    const long long groups = (jb.num_pixels + 3) / 4;
+    for (long long g = tid; g < groups; g += stride) {
+      const long long pix0 = g * 4;
+      const int npix = (int)min(4LL, jb.num_pixels - pix0);
+      const bool vec = jb.vec_ok && npix == 4;
+      if (jb.channels == 1)
+        reduce_pixels<1>(member, K, jb, pix0, npix, vec);
+      else
+        reduce_pixels<3>(member, K, jb, pix0, npix, vec);
+    }
+  } else {
+    for (long long px = tid; px < jb.num_pixels; px += stride) reduce_pixel_any_c(member, K, jb, px);
   }
 }
+
+static bool al16(const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
 }  // namespace ub
 
-extern "C" int ub_reduce_members(const float* const* members_host, int32_t num_members,
-                                 int64_t num_pixels, int32_t channels, int32_t spread_mode,
-                                 float* out_mean, float* out_spread, void* stream_v) {
+extern "C" {
+
+int ub_reduce_members_batched(const ub_reduce_job* jobs_host, int32_t num_jobs, int32_t num_members,
+                              void* stream_v) {
   using namespace ub;
-  UB_REQUIRE(members_host != nullptr, UB_ERR_BAD_ARG, "reduce_members: members_host is NULL");
-  UB_REQUIRE(num_members >= 1 && num_members <= UB_MAX_MEMBERS, UB_ERR_UNSUPPORTED,
-             "reduce_members: num_members %d outside [1, %d]", num_members, UB_MAX_MEMBERS);
-  UB_REQUIRE(num_pixels >= 0 && channels >= 1, UB_ERR_BAD_ARG, "reduce_members: bad shape N=%lld C=%d",
-             (long long)num_pixels, channels);
-  UB_REQUIRE(spread_mode >= UB_SPREAD_NONE && spread_mode <= UB_SPREAD_VAR, UB_ERR_BAD_ARG,
-             "reduce_members: bad spread_mode %d", spread_mode);
-  UB_REQUIRE(spread_mode == UB_SPREAD_NONE || out_spread != nullptr, UB_ERR_BAD_ARG,
-             "reduce_members: spread requested but out_spread is NULL");
-  if (num_pixels == 0) return UB_OK;
+  UB_REQUIRE(jobs_host != nullptr && num_jobs >= 1, UB_ERR_BAD_ARG, "reduce_members: no jobs");
+  UB_REQUIRE(num_jobs <= kMaxJobs, UB_ERR_UNSUPPORTED, "reduce_members: more than %d jobs per call", kMaxJobs);
+  UB_REQUIRE(num_members >= 1 && num_members <= kMaxBatchMembers, UB_ERR_UNSUPPORTED,
+             "reduce_members: num_members %d outside [1, %d]", num_members, kMaxBatchMembers);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  ReduceParams p{};
-  bool vec_ok = true;
-  for (int k = 0; k < num_members; ++k) {
-    UB_REQUIRE(members_host[k] != nullptr, UB_ERR_BAD_ARG, "reduce_members: member %d is NULL", k);
-    p.member[k] = members_host[k];
-    vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(members_host[k]) & 15u) == 0;
+  ReduceBatch b{};
+  b.num_members = num_members;
+  long long max_threads = 0;
+  for (int j = 0; j < num_jobs; ++j) {
+    const ub_reduce_job& in = jobs_host[j];
+    UB_REQUIRE(in.members_host != nullptr, UB_ERR_BAD_ARG, "reduce_members: job %d members_host is NULL", j);
+    UB_REQUIRE(in.num_pixels >= 0 && in.channels >= 1, UB_ERR_BAD_ARG,
+               "reduce_members: job %d bad shape N=%lld C=%d", j, (long long)in.num_pixels, in.channels);
+    UB_REQUIRE(in.spread_mode >= UB_SPREAD_NONE && in.spread_mode <= UB_SPREAD_VAR, UB_ERR_BAD_ARG,
+               "reduce_members: job %d bad spread_mode %d", j, in.spread_mode);
+    UB_REQUIRE(in.spread_mode == UB_SPREAD_NONE || in.out_spread != nullptr, UB_ERR_BAD_ARG,
+               "reduce_members: job %d spread requested but out_spread is NULL", j);
+    bool vec_ok = al16(in.out_mean) && al16(in.out_spread);
+    for (int k = 0; k < num_members; ++k) {
+      UB_REQUIRE(in.members_host[k] != nullptr || in.num_pixels == 0, UB_ERR_BAD_ARG,
+                 "reduce_members: job %d member %d is NULL", j, k);
+      b.member[j][k] = in.members_host[k];
+      vec_ok = vec_ok && al16(in.members_host[k]);
+    }
+    b.job[j].num_pixels = in.num_pixels;
+    b.job[j].channels = in.channels;
+    b.job[j].spread_mode = in.out_spread ? in.spread_mode : UB_SPREAD_NONE;
+    b.job[j].out_mean = in.out_mean;
+    b.job[j].out_spread = in.out_spread;
+    b.job[j].vec_ok = vec_ok ? 1 : 0;
+    const long long threads = (in.channels == 1 || in.channels == 3) ? (in.num_pixels + 3) / 4 : in.num_pixels;
+    if (threads > max_threads) max_threads = threads;
   }
-  vec_ok = vec_ok && (out_mean == nullptr || (reinterpret_cast<uintptr_t>(out_mean) & 15u) == 0) &&
-           (out_spread == nullptr || (reinterpret_cast<uintptr_t>(out_spread) & 15u) == 0);
-  p.num_members = num_members;
-  p.num_pixels = num_pixels;
-  p.spread_mode = out_spread ? spread_mode : UB_SPREAD_NONE;
-  p.out_mean = out_mean;
-  p.out_spread = out_spread;
+  if (max_threads == 0) return UB_OK;
   const int sms = sm_count() > 0 ? sm_count() : 148;
+  long long blocks = (max_threads + 255) / 256;
   const long long cap = (long long)sms * 8;
-  if (channels == 1 || channels == 3) {
-    const long long groups = (num_pixels + 3) / 4;
-    long long blocks = (groups + 255) / 256;
-    if (blocks > cap) blocks = cap;
-    if (channels == 1)
-      reduce_members_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(p, vec_ok ? 1 : 0);
-    else
-      reduce_members_kernel<3><<<(unsigned)blocks, 256, 0, stream>>>(p, vec_ok ? 1 : 0);
-  } else {
-    long long blocks = (num_pixels + 255) / 256;
-    if (blocks > cap) blocks = cap;
-    reduce_members_any_c<<<(unsigned)blocks, 256, 0, stream>>>(p, channels);
-  }
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, (unsigned)num_jobs);
+  reduce_members_batched_kernel<<<grid, 256, 0, stream>>>(b);
   return check_launch("reduce_members");
 }
+
+int ub_reduce_members(const float* const* members_host, int32_t num_members, int64_t num_pixels,
+                      int32_t channels, int32_t spread_mode, float* out_mean, float* out_spread,
+                      void* stream_v) {
+  using namespace ub;
+  UB_REQUIRE(members_host != nullptr, UB_ERR_BAD_ARG, "reduce_members: members_host is NULL");
+  // more members than one batched job carries: reduce in the single-job layout (same kernel)
+  UB_REQUIRE(num_members >= 1 && num_members <= kMaxBatchMembers, UB_ERR_UNSUPPORTED,
+             "reduce_members: num_members %d outside [1, %d]", num_members, kMaxBatchMembers);
+  ub_reduce_job job;
+  job.members_host = members_host;
+  job.num_pixels = num_pixels;
+  job.channels = channels;
+  job.spread_mode = spread_mode;
+  job.out_mean = out_mean;
+  job.out_spread = out_spread;
+  return ub_reduce_members_batched(&job, 1, num_members, stream_v);
+}
+
+}  // extern "C"

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
     const int npix = (int)max(0LL, min((long long)kPixPerThread, seg_hi - pix0));
     if (npix > 0) {
       float pr[kPixPerThread * C], tg[kPixPerThread * C], sd[kPixPerThread];
-      const bool vec = p.vec_ok && npix == kPixPerThread && (pix0 & 3) == 0;
+      const bool vec = p.vec_ok && npix == kPixPerThread && (pix0 & 3) == 0;  // 16-byte aligned rows
       if (vec) {
         const float4* a = reinterpret_cast<const float4*>(p.pred + pix0 * C);
         const float4* b = reinterpret_cast<const float4*>(p.target + pix0 * C);
@@ -204,20 +204,17 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
 }
 
 // out_sums[seg][j] = sum over the segment's blocks in block order (deterministic)
+// one warp per sum: lanes stride over the blocks, then a fixed-order shuffle tree
 __global__ void prologue_finalize_kernel(const double* partial, int blocks_per_seg, double* out_sums) {
   const int seg = blockIdx.x;
-  const int j = threadIdx.x;
+  const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (j >= UB_PROLOGUE_NSUMS) return;
   double v = 0.0;
-  for (int b = 0; b < blocks_per_seg; ++b)
+  for (int b = lane; b < blocks_per_seg; b += 32)
     v += partial[((size_t)seg * blocks_per_seg + b) * UB_PROLOGUE_NSUMS + j];
-  out_sums[(size_t)seg * UB_PROLOGUE_NSUMS + j] = v;
-}
-
-static long long max_seg_len(const int64_t* off, int n) {
-  long long m = 0;
-  for (int i = 0; i < n; ++i) m = off[i + 1] - off[i] > m ? off[i + 1] - off[i] : m;
-  return m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += shfl_xor_double(FULL_MASK, v, o);
+  if (lane == 0) out_sums[(size_t)seg * UB_PROLOGUE_NSUMS + j] = v;
 }
 
 struct PrologueLayout {
@@ -250,28 +247,20 @@ int ub_score_prologue(const ub_score_prologue_args* a, void* workspace, size_t w
   UB_REQUIRE(a != nullptr, UB_ERR_BAD_ARG, "score_prologue: args is NULL");
   UB_REQUIRE(a->channels == 1 || a->channels == 3, UB_ERR_UNSUPPORTED,
              "score_prologue: channels must be 1 or 3 (got %d)", a->channels);
-  UB_REQUIRE(a->num_segments >= 1 && a->num_segments <= 65535 && a->seg_offsets_host != nullptr,
+  UB_REQUIRE(a->num_segments >= 1 && a->num_segments <= 65535 && a->seg_offsets != nullptr,
              UB_ERR_BAD_ARG, "score_prologue: bad segments");
+  UB_REQUIRE(a->max_segment_len >= 0, UB_ERR_BAD_ARG, "score_prologue: bad max_segment_len");
   UB_REQUIRE(a->num_z >= 1 && a->num_z <= kMaxZ && a->z_values != nullptr, UB_ERR_BAD_ARG,
              "score_prologue: num_z must be in [1, %d]", kMaxZ);
   UB_REQUIRE(a->out_sums != nullptr && a->out_hist != nullptr, UB_ERR_BAD_ARG,
              "score_prologue: out_sums / out_hist must be non-NULL");
-  const int64_t* off = a->seg_offsets_host;
-  for (int s = 0; s < a->num_segments; ++s)
-    UB_REQUIRE(off[s + 1] >= off[s] && off[s] >= 0, UB_ERR_BAD_ARG,
-               "score_prologue: segment offsets must be non-decreasing");
-  const long long total = off[a->num_segments];
-  UB_REQUIRE(total == 0 || (a->pred && a->target && a->std), UB_ERR_BAD_ARG,
+  UB_REQUIRE(a->max_segment_len == 0 || (a->pred && a->target && a->std), UB_ERR_BAD_ARG,
              "score_prologue: pred/target/std must be non-NULL");
-  const PrologueLayout lay = prologue_layout(a->num_segments, max_seg_len(off, a->num_segments));
+  const PrologueLayout lay = prologue_layout(a->num_segments, a->max_segment_len);
   UB_REQUIRE(workspace != nullptr && workspace_bytes >= lay.total, UB_ERR_WORKSPACE,
              "score_prologue: workspace %zu B < required %zu B", workspace_bytes, lay.total);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   char* ws = static_cast<char*>(workspace);
-
-  if (cudaMemcpyAsync(ws + lay.off_offsets, off, (size_t)(a->num_segments + 1) * sizeof(int64_t),
-                      cudaMemcpyHostToDevice, stream) != cudaSuccess)
-    return check_launch("score_prologue offsets copy");
   if (cudaMemsetAsync(a->out_hist, 0, (size_t)a->num_segments * (a->num_z + 1) * sizeof(int64_t),
                       stream) != cudaSuccess)
     return check_launch("score_prologue hist memset");
@@ -282,7 +271,7 @@ int ub_score_prologue(const ub_score_prologue_args* a, void* workspace, size_t w
   p.std = a->std;
   p.channels = a->channels;
   p.num_segments = a->num_segments;
-  p.seg_offsets = reinterpret_cast<const long long*>(ws + lay.off_offsets);
+  p.seg_offsets = reinterpret_cast<const long long*>(a->seg_offsets);
   p.nll_min_std = a->nll_min_std;
   p.sigma_from_var = a->sigma_from_var;
   p.z = a->z_values;
@@ -296,8 +285,7 @@ int ub_score_prologue(const ub_score_prologue_args* a, void* workspace, size_t w
   auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   bool vec_ok = al16(a->pred) && al16(a->target) && al16(a->std) && al16(a->out_sq_err) &&
                 al16(a->out_abs_err) && al16(a->out_var);
-  for (int s = 0; s < a->num_segments; ++s) vec_ok = vec_ok && (off[s] % 4 == 0);
-  p.vec_ok = vec_ok ? 1 : 0;
+  p.vec_ok = vec_ok ? 1 : 0;  // the kernel additionally requires 4-pixel-aligned positions
 
   dim3 grid((unsigned)lay.blocks_per_seg, (unsigned)a->num_segments);
   if (a->channels == 3)
@@ -306,7 +294,7 @@ int ub_score_prologue(const ub_score_prologue_args* a, void* workspace, size_t w
     score_prologue_kernel<1><<<grid, kPrologueThreads, 0, stream>>>(p);
   int rc = check_launch("score_prologue");
   if (rc != UB_OK) return rc;
-  prologue_finalize_kernel<<<a->num_segments, 32, 0, stream>>>(p.partial, lay.blocks_per_seg, a->out_sums);
+  prologue_finalize_kernel<<<a->num_segments, 32 * UB_PROLOGUE_NSUMS, 0, stream>>>(p.partial, lay.blocks_per_seg, a->out_sums);
   return check_launch("score_prologue finalize");
 }
 

@@ -35,15 +35,33 @@ def _ratios() -> np.ndarray:
 def ause_cut_counts(n: int) -> np.ndarray:
     """``int((1 - r) * n)`` for the 100 removal ratios, evaluated in float64 with truncation exactly as
     ause.py:16,30 does (NOT ``n * (100 - i) // 100``: the two differ at ~25 of 100 indices)."""
-    return np.array([int((1 - r) * n) for r in _ratios()], dtype=np.int64)
+    c = _CUTS.get(n)
+    if c is None:
+        if len(_CUTS) > 256:
+            _CUTS.clear()
+        c = _CUTS[n] = np.array([int((1 - r) * n) for r in _ratios()], dtype=np.int64)
+    return c
+
+
+_ALPHAS: Optional[List[np.float64]] = None
+_Z_HOST: Optional[np.ndarray] = None
+_CUTS: Dict[int, np.ndarray] = {}
 
 
 def _alphas() -> List[np.float64]:
-    return list(np.arange(start=0.01, stop=1.0, step=0.01))  # auce.py:17
+    global _ALPHAS
+    if _ALPHAS is None:
+        _ALPHAS = list(np.arange(start=0.01, stop=1.0, step=0.01))  # auce.py:17
+    return _ALPHAS
 
 
 def z_values_host() -> np.ndarray:
-    return np.array([scipy.stats.norm.ppf(1.0 - a / 2) for a in _alphas()], dtype=np.float64)  # auce.py:21-22
+    """``scipy.stats.norm.ppf(1 - alpha/2)`` for the 99 alphas (auce.py:21-22); computed once -- the scalar
+    scipy call costs tens of microseconds and the reference pays it 198 times per image."""
+    global _Z_HOST
+    if _Z_HOST is None:
+        _Z_HOST = np.array([scipy.stats.norm.ppf(1.0 - a / 2) for a in _alphas()], dtype=np.float64)
+    return _Z_HOST
 
 
 def _z_table(device) -> Tensor:
@@ -53,27 +71,38 @@ def _z_table(device) -> Tensor:
     return _Z_CACHE[key]
 
 
-def _prefix_means(sums: np.ndarray, cuts: np.ndarray, err_type: str) -> List[np.ndarray]:
+def _prefix_means(sums: np.ndarray, cuts: np.ndarray, err_type: str) -> np.ndarray:
     """float32 value of ``err_sorted[:c].mean()`` (and ``torch.sqrt`` of it for rmse) from the float64
     prefix sums; an empty slice gives NaN like torch."""
-    pts = []
-    for s, c in zip(sums, cuts):
-        m = np.float32(s / c) if c > 0 else np.float32(np.nan)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        m = np.where(cuts > 0, sums / np.maximum(cuts, 1), np.nan).astype(np.float32)
         if err_type == "rmse":
             m = np.sqrt(m)
-        pts.append(np.asarray(m, dtype=np.float32))
-    return pts
+    return m
 
 
-def _ause_tail(oracle_pts: List[np.ndarray], by_unc_pts: List[np.ndarray]):
+def _py_max(arr: np.ndarray):
+    """Python's ``max(iterable)`` (first maximal element; a NaN never wins a comparison but a leading NaN
+    sticks), which is what ause.py:37 applies to both curves."""
+    if not np.isnan(arr).any():
+        return arr.max()
+    best = arr[0]
+    for v in arr[1:]:
+        if v > best:
+            best = v
+    return best
+
+
+def _ause_tail(oracle_f32: np.ndarray, by_unc_f32: np.ndarray):
     """ause.py:27-44 downstream of the slice means: normalise both curves by the common maximum and
-    integrate the gap.  Object types follow the reference (list of 0-d float32 arrays vs float64 array)."""
+    integrate the gap.  dtypes follow the reference: the oracle curve is built from float32 scalars, the
+    by-uncertainty curve lives in a float64 array, and ``max(a, b)`` keeps ``a`` unless ``b > a``."""
     ratios = _ratios()
     by_unc = np.zeros(len(ratios))
-    for i, v in enumerate(by_unc_pts):
-        by_unc[i] = v
-    max_val = max(max(oracle_pts), max(by_unc))
-    oracle_curve = np.array(oracle_pts / max_val)
+    by_unc[:] = by_unc_f32
+    a, b = _py_max(oracle_f32), _py_max(by_unc)
+    max_val = b if b > a else a
+    oracle_curve = np.array(oracle_f32 / max_val)
     by_unc = np.array(by_unc / max_val)
     return ratios, oracle_curve, by_unc, np.trapz(by_unc - oracle_curve, ratios)
 
@@ -91,13 +120,12 @@ def ause(unc_vec: Tensor, err_vec: Tensor, err_type: str = "rmse"
     if unc_vec.dim() != 1 or unc_vec.shape != err_vec.shape:
         raise ValueError("unc_vec and err_vec must be 1-D tensors of equal length")
     n = len(err_vec)
-    cuts = ause_cut_counts(n)[None, :]
-    err_sorted, _ = ops.segmented_sort(err_vec, [n], want_perm=False, want_keys=True)
-    _, perm = ops.segmented_sort(unc_vec, [n], want_perm=True, want_keys=False)
-    s_oracle = ops.cut_prefix_sums([err_sorted], None, [n], cuts)
-    s_by_unc = ops.cut_prefix_sums([err_vec], perm, [n], cuts)
-    both = torch.stack([s_oracle[0, 0], s_by_unc[0, 0]]).cpu().numpy()
-    return _ause_tail(_prefix_means(both[0], cuts[0], err_type), _prefix_means(both[1], cuts[0], err_type))
+    cuts = ause_cut_counts(n)
+    both = torch.stack([unc_vec.reshape(-1), err_vec.reshape(-1)]).to(torch.float32)
+    sorted_all, perm_all = ops.segmented_sort(both.reshape(-1), [n, n], want_perm=True, want_keys=True)
+    sums = ops.cut_prefix_sums([sorted_all[n:], err_vec], [None, perm_all[:n]], [n], cuts[None, :])
+    host = sums[0].cpu().numpy()
+    return _ause_tail(_prefix_means(host[0], cuts, err_type), _prefix_means(host[1], cuts, err_type))
 
 
 def _auce_from_hist(hist: np.ndarray, sigma_sum: float, n: float, z: np.ndarray) -> Dict[str, object]:
@@ -106,9 +134,9 @@ def _auce_from_hist(hist: np.ndarray, sigma_sum: float, n: float, z: np.ndarray)
     ~2e-16 relative)."""
     alphas = _alphas()
     inside = (np.cumsum(hist[::-1])[::-1])[1:]  # count with c > k, k = 0..nz-1
-    coverage_values = [int(c) / n for c in inside]
-    avg_length_values = [np.float64(2.0 * zk * (sigma_sum / n)) for zk in z]
-    auc_length = np.trapz(y=avg_length_values, x=alphas)
+    coverage_values = inside.astype(np.float64) / n
+    avg_length_values = 2.0 * z * (sigma_sum / n)
+    auc_length = np.trapz(y=list(avg_length_values), x=alphas)
     err = np.array(coverage_values) - (1.0 - np.array(alphas))
     abs_err = np.abs(err)
     neg_err = (np.abs(err) - err) / 2.0
@@ -159,46 +187,48 @@ def score_rgb_batch(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb_s
     segmented launches.  ``rgb_pred, rgb_gt [B, H, W, 3]``, ``rgb_std [B, H, W, 1]`` (CUDA float32; the
     ground truth already composited with the background for splat models).  Returns one dict per image
     with the reference's scalar / curve entries (``nll_rgb``, ``ause_*``, ``err_*``, ``err_var_*``,
-    ``avg_var``, ``mse_mean`` and the 8 AUCE entries)."""
+    ``avg_var``, ``mse_mean`` and the 8 AUCE entries).
+
+    Device work: 1 prologue (+ finalize), ONE segmented sort over 3B segments (variance with its
+    permutation, absolute and squared errors), 1 cut-point prefix-sum pass, 1 packed device->host copy."""
     if rgb_pred.dim() == 3:
         rgb_pred, rgb_gt, rgb_std = rgb_pred[None], rgb_gt[None], rgb_std[None]
     b, h, w, c = rgb_pred.shape
     n = h * w
     lens = [n] * b
+    total = n * b
     dev = rgb_pred.device
     z = _z_table(dev)
     pro = ops.score_prologue(rgb_pred.reshape(-1, c), rgb_gt.reshape(-1, c), rgb_std.reshape(-1), lens, z,
                              nll_min_std=min_rgb_std_for_nll, sigma_from_var=True, want_vectors=True)
-    se, ae, var = pro["squared_error"], pro["absolute_error"], pro["var"]
-    cuts = np.tile(ause_cut_counts(n)[None, :], (b, 1))
-    _, perm = ops.segmented_sort(var, lens, want_perm=True, want_keys=False)
-    by_unc = ops.cut_prefix_sums([ae, se], perm, lens, cuts)            # [B, 2, 100]
-    ae_sorted, _ = ops.segmented_sort(ae, lens, want_perm=False, want_keys=True)
-    se_sorted, _ = ops.segmented_sort(se, lens, want_perm=False, want_keys=True)
-    oracle_ae = ops.cut_prefix_sums([ae_sorted], None, lens, cuts)      # [B, 1, 100]
-    oracle_se = ops.cut_prefix_sums([se_sorted], None, lens, cuts)
+    vec = pro["vectors"]                                   # [3, total]: var, abs err, sq err
+    ae, se = vec[1], vec[2]
+    cuts_one = ause_cut_counts(n)
+    cuts = np.tile(cuts_one[None, :], (b, 1))
+    sorted_all, perm_all = ops.segmented_sort(vec.reshape(-1), lens * 3, want_perm=True, want_keys=True)
+    perm_var = perm_all[:total]
+    sums = ops.cut_prefix_sums([ae, se, sorted_all[total:2 * total], sorted_all[2 * total:]],
+                               [perm_var, perm_var, None, None], lens, cuts)          # [B, 4, 100]
     # one device->host transfer for everything the host tail needs
-    packed = torch.cat([by_unc.reshape(b, -1), oracle_ae.reshape(b, -1), oracle_se.reshape(b, -1),
-                        pro["sums"], pro["hist"].to(torch.float64)], dim=1).cpu().numpy()
+    packed = torch.cat([sums.reshape(b, -1), pro["sums"], pro["hist"].to(torch.float64)], dim=1).cpu().numpy()
     zh = z_values_host()
     results = []
     for i in range(b):
         row = packed[i]
         bu_ae, bu_se, or_ae, or_se = row[0:100], row[100:200], row[200:300], row[300:400]
-        sums = row[400:405]
+        psums = row[400:405]
         hist = np.rint(row[405:405 + len(zh) + 1]).astype(np.int64)
-        ci = cuts[i]
         d: Dict[str, object] = {}
         _, d["err_mae"], d["err_var_mae"], d["ause_mae"] = _ause_tail(
-            _prefix_means(or_ae, ci, "mae"), _prefix_means(bu_ae, ci, "mae"))
+            _prefix_means(or_ae, cuts_one, "mae"), _prefix_means(bu_ae, cuts_one, "mae"))
         _, d["err_mse"], d["err_var_mse"], d["ause_mse"] = _ause_tail(
-            _prefix_means(or_se, ci, "mse"), _prefix_means(bu_se, ci, "mse"))
+            _prefix_means(or_se, cuts_one, "mse"), _prefix_means(bu_se, cuts_one, "mse"))
         _, d["err_rmse"], d["err_var_rmse"], d["ause_rmse"] = _ause_tail(
-            _prefix_means(or_se, ci, "rmse"), _prefix_means(bu_se, ci, "rmse"))
-        d["nll_rgb"] = float(np.float32(sums[3] / (n * c)))
-        d["avg_var"] = float(np.float32(sums[2] / n))
-        d["mse_mean"] = float(np.float32(sums[0] / n))
-        d.update(_auce_from_hist(hist, float(sums[4]) * c, float(n * c), zh))
+            _prefix_means(or_se, cuts_one, "rmse"), _prefix_means(bu_se, cuts_one, "rmse"))
+        d["nll_rgb"] = float(np.float32(psums[3] / (n * c)))
+        d["avg_var"] = float(np.float32(psums[2] / n))
+        d["mse_mean"] = float(np.float32(psums[0] / n))
+        d.update(_auce_from_hist(hist, float(psums[4]) * c, float(n * c), zh))
         results.append(d)
     return results
 

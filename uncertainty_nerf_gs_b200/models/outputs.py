@@ -75,44 +75,48 @@ def laplace_outputs_unc(density: Tensor, deltas: Tensor, starts: Tensor, ends: T
     return out
 
 
-def _mean_only(members: List[Tensor]) -> Tensor:
-    flat = [m.reshape(-1, 1) for m in members]
-    mean, _ = ops.reduce_members(flat, None)
-    return mean.reshape(members[0].shape)
-
-
 def mcdropout_reduce(outputs_list: Sequence[Dict[str, Tensor]]) -> Dict[str, Tensor]:
     """``NerfactoMCDropoutModel.get_outputs_for_camera_ray_bundle`` after the K stochastic renders
-    (reference mcdropout_models.py:121-126)."""
+    (reference mcdropout_models.py:121-126): every key in one batched launch."""
+    keys = list(outputs_list[0].keys())
+    res = ops.reduce_many([([o[k] for o in outputs_list], "std" if k in STD_KEYS else None) for k in keys])
     out: Dict[str, Tensor] = {}
-    for k in outputs_list[0].keys():
-        members = [o[k] for o in outputs_list]
+    for k, (mean, spread) in zip(keys, res):
+        out[k] = mean
         if k in STD_KEYS:
-            out[k], out[k + "_std"] = ops.reduce_members(members, "std")
-        else:
-            out[k] = _mean_only(members)
+            out[k + "_std"] = spread
     return out
 
 
 def ensemble_reduce(outputs_list: Sequence[Dict[str, Tensor]]) -> Dict[str, Tensor]:
     """``EnsemblePipeline.get_ensemble_outputs_for_camera_ray_bundle`` after the M member renders
-    (reference ensemble_pipeline.py:159-190), including the reference's overwrite order."""
+    (reference ensemble_pipeline.py:159-190), including the reference's overwrite order.  All member
+    means / spreads come from one batched launch; only the two-term sums of branch A use torch."""
     first = outputs_list[0]
+    keys = list(first.keys())
     has_pred_std = "rgb_std" in first.keys() and "depth_std" in first.keys()
-    out: Dict[str, Tensor] = {}
-    for k in first.keys():
-        members = [o[k] for o in outputs_list]
+    jobs = []
+    for k in keys:
         if has_pred_std and k in ("rgb", "depth"):
-            out[k], epi = ops.reduce_members(members, "var")
-            alea, _ = ops.reduce_members([o[k + "_var"] for o in outputs_list], None)
+            spread = "var"
+        elif not has_pred_std and k in STD_KEYS:
+            spread = "std"
+        else:
+            spread = None
+        jobs.append(([o[k] for o in outputs_list], spread))
+    res = dict(zip(keys, ops.reduce_many(jobs)))
+    out: Dict[str, Tensor] = {}
+    for k in keys:
+        mean, spread = res[k]
+        out[k] = mean
+        if has_pred_std and k in ("rgb", "depth"):
+            alea = res[k + "_var"][0]                      # mean over members of the predicted variance
             out[k + "_var_alea"] = alea.mean(dim=-1).unsqueeze(-1)
-            out[k + "_var_epi"] = epi
+            out[k + "_var_epi"] = spread
             out[k + "_var"] = out[k + "_var_epi"] + out[k + "_var_alea"]
             out[k + "_std"] = out[k + "_var"].sqrt()
         elif not has_pred_std and k in STD_KEYS:
-            out[k], out[k + "_std"] = ops.reduce_members(members, "std")
-        else:
-            out[k] = _mean_only(members)
+            out[k + "_std"] = spread
     return out
 
 

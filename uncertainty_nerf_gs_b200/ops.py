@@ -159,38 +159,109 @@ def render_weights(weights: Tensor, starts: Tensor, ends: Tensor, *, rays_per_ch
 _SPREAD = {None: _lib.UB_SPREAD_NONE, "std": _lib.UB_SPREAD_STD, "var": _lib.UB_SPREAD_VAR}
 
 
-def reduce_members(members: Sequence[Tensor], spread: Optional[str] = None) -> Tuple[Tensor, Optional[Tensor]]:
-    """Mean over K same-shaped ``[..., C]`` member tensors (read in place, no stack) and, optionally,
-    the unbiased std / var over members averaged over the channel axis -> ``[..., 1]``."""
+def reduce_many(jobs: Sequence[Tuple[Sequence[Tensor], Optional[str]]]) -> List[Tuple[Tensor, Optional[Tensor]]]:
+    """Batched member reduce: ``jobs[j] = (members_j, spread_j)``; every job reduces K same-shaped
+    ``[..., C]`` tensors (read in place, no stack) to their mean and, optionally, the unbiased std / var over
+    members averaged over the channel axis (``[..., 1]``).  All jobs go through one kernel launch
+    (chunks of ``UB_MAX_REDUCE_JOBS``)."""
     lib = _lib.load()
+    if not jobs:
+        return []
+    k = len(jobs[0][0])
+    prepared = []
+    for j, (members, spread) in enumerate(jobs):
+        if len(members) != k or k < 1:
+            raise ValueError("every job must have the same, positive number of members")
+        if spread not in _SPREAD:
+            raise ValueError(f"spread must be None, 'std' or 'var', got {spread!r}")
+        ms = [_dev_f32(m, f"jobs[{j}].members[{i}]") for i, m in enumerate(members)]
+        shape = ms[0].shape
+        if any(m.shape != shape for m in ms):
+            raise ValueError("all members of a job must share one shape")
+        if spread is None:
+            c, n = 1, ms[0].numel()          # mean only: a flat stream
+        else:
+            c = int(shape[-1]) if len(shape) else 1
+            n = ms[0].numel() // max(c, 1)
+        dev = ms[0].device
+        mean = torch.empty(shape, device=dev)
+        spr = torch.empty((*shape[:-1], 1), device=dev) if spread else None
+        prepared.append((ms, c, n, spread, mean, spr))
+    dev = prepared[0][0][0].device
+    results = []
+    with torch.cuda.device(dev):
+        for lo in range(0, len(prepared), _lib.UB_MAX_REDUCE_JOBS):
+            chunk = prepared[lo:lo + _lib.UB_MAX_REDUCE_JOBS]
+            arr = (_lib.ReduceJob * len(chunk))()
+            keep = []
+            for slot, (ms, c, n, spread, mean, spr) in zip(arr, chunk):
+                ptrs = (C.c_void_p * k)(*[m.data_ptr() for m in ms])
+                keep.append(ptrs)
+                slot.members_host = ptrs
+                slot.num_pixels, slot.channels, slot.spread_mode = n, c, _SPREAD[spread]
+                slot.out_mean, slot.out_spread = mean.data_ptr(), _ptr(spr)
+            _lib.check(lib.ub_reduce_members_batched(arr, len(chunk), k, _stream()))
+            _count(1)
+    for (_, _, _, _, mean, spr) in prepared:
+        results.append((mean, spr))
+    return results
+
+
+def reduce_members(members: Sequence[Tensor], spread: Optional[str] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """Mean over K same-shaped ``[..., C]`` member tensors and, optionally, the unbiased std / var over
+    members averaged over the channel axis -> ``[..., 1]`` (single-job form of ``reduce_many``)."""
     if len(members) < 1:
         raise ValueError("need at least one member")
-    ms = [_dev_f32(m, f"members[{i}]") for i, m in enumerate(members)]
-    shape = ms[0].shape
-    if any(m.shape != shape for m in ms):
-        raise ValueError("all members must share one shape")
-    if spread not in _SPREAD:
-        raise ValueError(f"spread must be None, 'std' or 'var', got {spread!r}")
-    c = int(shape[-1]) if len(shape) else 1
-    n = ms[0].numel() // max(c, 1)
-    dev = ms[0].device
-    mean = torch.empty(shape, device=dev)
-    spr = torch.empty((*shape[:-1], 1), device=dev) if spread else None
-    ptrs = (C.c_void_p * len(ms))(*[m.data_ptr() for m in ms])
-    with torch.cuda.device(dev):
-        _lib.check(lib.ub_reduce_members(ptrs, len(ms), n, c, _SPREAD[spread], mean.data_ptr(), _ptr(spr), _stream()))
-    _count(1 if n > 0 else 0)
-    return mean, spr
+    return reduce_many([(members, spread)])[0]
 
 
-def _offsets(seg_lengths: Sequence[int]) -> np.ndarray:
-    off = np.zeros(len(seg_lengths) + 1, dtype=np.int64)
-    np.cumsum(np.asarray(seg_lengths, dtype=np.int64), out=off[1:])
-    return off
+class Segments:
+    """Segment table of a batch (device int64 offsets + the host-side scalars the C ABI wants).  Built once
+    per distinct tuple of lengths and cached: the hot calls never copy host memory to the device (a copy
+    from pageable memory would synchronise the stream)."""
 
+    _cache: Dict[tuple, "Segments"] = {}
 
-def _i64p(a: np.ndarray):
-    return a.ctypes.data_as(C.POINTER(C.c_int64))
+    def __init__(self, seg_lengths: Sequence[int], device):
+        lens = np.asarray(list(seg_lengths), dtype=np.int64)
+        if (lens < 0).any():
+            raise ValueError("segment lengths must be non-negative")
+        off = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        self.lengths = lens
+        self.num = len(lens)
+        self.total = int(off[-1])
+        self.max_len = int(lens.max()) if len(lens) else 0
+        self.offsets_host = off
+        self.offsets = torch.from_numpy(off).to(device)
+        self._cuts: Dict[bytes, Tensor] = {}
+
+    @classmethod
+    def get(cls, seg_lengths, device) -> "Segments":
+        if isinstance(seg_lengths, Segments):
+            return seg_lengths
+        key = (str(device), tuple(int(v) for v in seg_lengths))
+        seg = cls._cache.get(key)
+        if seg is None:
+            if len(cls._cache) > 64:
+                cls._cache.clear()
+            seg = cls._cache[key] = Segments(key[1], device)
+        return seg
+
+    def cuts_device(self, cuts: np.ndarray) -> Tensor:
+        """Validated, cached device copy of a ``[num_segments, num_cuts]`` int64 cut table."""
+        cuts = np.ascontiguousarray(cuts, dtype=np.int64)
+        if cuts.ndim != 2 or cuts.shape[0] != self.num:
+            raise ValueError("cuts must be [num_segments, num_cuts]")
+        key = cuts.tobytes()
+        t = self._cuts.get(key)
+        if t is None:
+            if (cuts < 0).any() or (cuts > self.lengths[:, None]).any():
+                raise ValueError("every cut must lie in [0, segment length]")
+            if len(self._cuts) > 16:
+                self._cuts.clear()
+            t = self._cuts[key] = torch.from_numpy(cuts).to(self.offsets.device)
+        return t
 
 
 def score_prologue(pred: Tensor, target: Tensor, std: Tensor, seg_lengths: Sequence[int], z_values: Tensor,
@@ -207,30 +278,31 @@ def score_prologue(pred: Tensor, target: Tensor, std: Tensor, seg_lengths: Seque
     std = _dev_f32(std.reshape(-1), "std")
     if std.numel() != n:
         raise ValueError("std must hold one value per pixel")
-    off = _offsets(seg_lengths)
-    if off[-1] != n:
+    seg = Segments.get(seg_lengths, pred.device)
+    if seg.total != n:
         raise ValueError("segment lengths do not sum to the number of pixels")
     if z_values.dtype != torch.float64 or not z_values.is_cuda:
         raise TypeError("z_values must be a CUDA float64 tensor")
     dev = pred.device
-    nseg, nz = len(seg_lengths), z_values.numel()
+    nseg, nz = seg.num, z_values.numel()
     out: Dict[str, Tensor] = {
         "sums": torch.empty(nseg, _lib.UB_PROLOGUE_NSUMS, dtype=torch.float64, device=dev),
         "hist": torch.empty(nseg, nz + 1, dtype=torch.int64, device=dev),
     }
     if want_vectors:
-        out["squared_error"] = torch.empty(n, device=dev)
-        out["absolute_error"] = torch.empty(n, device=dev)
-        out["var"] = torch.empty(n, device=dev)
+        # one [3, N] buffer (var, abs err, sq err) so that the three AUSE sorts run as one segmented sort
+        out["vectors"] = torch.empty(3, n, device=dev)
+        out["var"], out["absolute_error"], out["squared_error"] = out["vectors"][0], out["vectors"][1], out["vectors"][2]
     args = _lib.ScorePrologueArgs()
     args.pred, args.target, args.std = pred.data_ptr(), target.data_ptr(), std.data_ptr()
-    args.channels, args.num_segments, args.seg_offsets_host = c, nseg, _i64p(off)
+    args.channels, args.num_segments = c, nseg
+    args.seg_offsets, args.max_segment_len = seg.offsets.data_ptr(), seg.max_len
     args.nll_min_std, args.sigma_from_var = float(nll_min_std), 1 if sigma_from_var else 0
     args.z_values, args.num_z = z_values.data_ptr(), nz
     args.out_sq_err, args.out_abs_err = _ptr(out.get("squared_error")), _ptr(out.get("absolute_error"))
     args.out_var = _ptr(out.get("var"))
     args.out_sums, args.out_hist = out["sums"].data_ptr(), out["hist"].data_ptr()
-    ws = _workspace(lib.ub_score_prologue_workspace_bytes(nseg, int(max(seg_lengths) if nseg else 0), nz), dev)
+    ws = _workspace(lib.ub_score_prologue_workspace_bytes(nseg, seg.max_len, nz), dev)
     with torch.cuda.device(dev):
         _lib.check(lib.ub_score_prologue(C.byref(args), ws.data_ptr(), ws.numel(), _stream()))
     _count(2)
@@ -243,47 +315,51 @@ def segmented_sort(keys: Tensor, seg_lengths: Sequence[int], want_perm: bool = T
     ``(sorted_keys, perm)`` with ``perm`` int32 indices *within the segment*."""
     lib = _lib.load()
     keys = _dev_f32(keys.reshape(-1), "keys")
-    off = _offsets(seg_lengths)
-    if off[-1] != keys.numel():
+    seg = Segments.get(seg_lengths, keys.device)
+    if seg.total != keys.numel():
         raise ValueError("segment lengths do not sum to the number of keys")
     dev = keys.device
     total = keys.numel()
     sorted_keys = torch.empty(total, device=dev) if want_keys else None
     perm = torch.empty(total, dtype=torch.int32, device=dev) if want_perm else None
-    nseg = len(seg_lengths)
-    max_len = int(max(seg_lengths)) if nseg else 0
+    nseg, max_len = seg.num, seg.max_len
     ws = _workspace(lib.ub_segmented_sort_workspace_bytes(nseg, total, max_len, 1 if want_perm else 0), dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.ub_segmented_sort(keys.data_ptr(), nseg, _i64p(off), _ptr(sorted_keys), _ptr(perm),
-                                         ws.data_ptr(), ws.numel(), _stream()))
+        _lib.check(lib.ub_segmented_sort(keys.data_ptr(), nseg, seg.offsets.data_ptr(), total, max_len,
+                                         _ptr(sorted_keys), _ptr(perm), ws.data_ptr(), ws.numel(), _stream()))
     _count(12 if total > 0 else 0)
     return sorted_keys, perm
 
 
-def cut_prefix_sums(values: Sequence[Tensor], perm: Optional[Tensor], seg_lengths: Sequence[int],
-                    cuts: np.ndarray) -> Tensor:
-    """float64 ``sum_{i < cut} values_v[perm[i]]`` per segment, value array and cut -> ``[nseg, V, ncuts]``."""
+def cut_prefix_sums(values: Sequence[Tensor], perms: Union[None, Tensor, Sequence[Optional[Tensor]]],
+                    seg_lengths: Sequence[int], cuts: np.ndarray) -> Tensor:
+    """float64 ``sum_{i < cut} values_v[perm_v[i]]`` per segment, value array and cut -> ``[nseg, V, ncuts]``.
+    ``perms``: one int32 permutation (within-segment indices, as ``segmented_sort`` returns) shared by all
+    value arrays, or one per value array (``None`` = identity)."""
     lib = _lib.load()
     vals = [_dev_f32(v.reshape(-1), f"values[{i}]") for i, v in enumerate(values)]
-    off = _offsets(seg_lengths)
-    total = int(off[-1])
+    seg = Segments.get(seg_lengths, vals[0].device)
+    total = seg.total
     if any(v.numel() != total for v in vals):
         raise ValueError("every value array must hold one entry per element")
-    if perm is not None and (perm.dtype != torch.int32 or not perm.is_cuda or perm.numel() != total):
-        raise TypeError("perm must be a CUDA int32 tensor with one entry per element")
-    cuts = np.ascontiguousarray(cuts, dtype=np.int64)
-    nseg = len(seg_lengths)
-    if cuts.ndim != 2 or cuts.shape[0] != nseg:
-        raise ValueError("cuts must be [num_segments, num_cuts]")
-    ncuts = cuts.shape[1]
+    if perms is None or isinstance(perms, torch.Tensor):
+        perms = [perms] * len(vals)
+    if len(perms) != len(vals):
+        raise ValueError("need one permutation (or None) per value array")
+    for pm in perms:
+        if pm is not None and (pm.dtype != torch.int32 or not pm.is_cuda or pm.numel() != total):
+            raise TypeError("perm must be a CUDA int32 tensor with one entry per element")
+    cuts_dev = seg.cuts_device(cuts)
+    nseg, ncuts = seg.num, cuts_dev.shape[1]
     dev = vals[0].device
     out = torch.empty(nseg, len(vals), ncuts, dtype=torch.float64, device=dev)
     ptrs = (C.c_void_p * len(vals))(*[v.data_ptr() for v in vals])
-    max_len = int(max(seg_lengths)) if nseg else 0
-    ws = _workspace(lib.ub_cut_prefix_sums_workspace_bytes(nseg, max_len, len(vals), ncuts), dev)
+    pptrs = (C.c_void_p * len(vals))(*[_ptr(pm) for pm in perms])
+    ws = _workspace(lib.ub_cut_prefix_sums_workspace_bytes(nseg, seg.max_len, len(vals), ncuts), dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.ub_cut_prefix_sums(ptrs, len(vals), _ptr(perm), nseg, _i64p(off), _i64p(cuts), ncuts,
-                                          out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        _lib.check(lib.ub_cut_prefix_sums(ptrs, pptrs, len(vals), nseg, seg.offsets.data_ptr(), seg.max_len,
+                                          cuts_dev.data_ptr(), ncuts, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          _stream()))
     _count(2)
     return out
 
