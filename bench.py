@@ -252,11 +252,13 @@ def run_ours(args, rank, world, local_rank):
     launches0 = ops.LAUNCH_COUNT
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        torch.cuda.profiler.start()  # no-op unless run under `ncu --profile-from-start off`
         ev0.record()
         for _ in range(steps):
             records = step(timers)
         ev1.record()
         barrier()
+        torch.cuda.profiler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ops.LAUNCH_COUNT - launches0
     comp_ms = [a.elapsed_time(b) for a, b in timers]
