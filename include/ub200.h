@@ -122,6 +122,15 @@ size_t ub_render_weights_workspace_bytes(int64_t num_rays, int64_t rays_per_chun
 int ub_render_weights(const ub_render_weights_args* args, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* Mean volume-rendering weights over num_draws Gaussian density draws (nerfacto-laplace with sampled
+ * density): replaces models/laplace/laplace_model.py:486-507 without materialising [draws, R, S].
+ * density, density_var, deltas [R,S]; noise: optional standard-normal draws [num_draws, R, S] (NULL:
+ * in-kernel Philox4x32-10 seeded with `seed`, statistical parity only); out_weights [R,S] feeds
+ * ub_render_weights.  num_samples <= 256. */
+int ub_average_sampled_weights(const float* density, const float* density_var, const float* deltas,
+                               const float* noise, int64_t num_rays, int32_t num_samples,
+                               int32_t num_draws, uint64_t seed, float* out_weights, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (B) Fused per-pixel mean / variance across K ensemble members or MC-dropout passes.
  * Replaces torch.stack(...).mean(0) / .std(0).mean(-1) / .var(0).mean(-1):

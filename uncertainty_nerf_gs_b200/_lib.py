@@ -73,6 +73,7 @@ SIGNATURES = {
     "ub_composite_rays": (C.c_int, [C.POINTER(CompositeRaysArgs), fp, C.c_size_t, fp]),
     "ub_render_weights_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "ub_render_weights": (C.c_int, [C.POINTER(RenderWeightsArgs), fp, C.c_size_t, fp]),
+    "ub_average_sampled_weights": (C.c_int, [fp, fp, fp, fp, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, fp, fp]),
     "ub_reduce_members": (C.c_int, [C.POINTER(fp), C.c_int32, C.c_int64, C.c_int32, C.c_int32, fp, fp, fp]),
     "ub_reduce_members_batched": (C.c_int, [C.POINTER(ReduceJob), C.c_int32, C.c_int32, fp]),
     "ub_score_prologue_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int32]),

@@ -123,6 +123,44 @@ __device__ __forceinline__ void reduce_pixels(const float* const* member, int K,
   }
 }
 
+// mean-only fast path (the bulk of a view's keys, e.g. the [H,W,48] density tensor): a flat stream,
+// 8 consecutive floats per thread, the loads of up to 4 members issued before any arithmetic, float32
+// shifted sums (x0 + sum(x_k - x0) / K: exact for identical members, <= 2 ulp otherwise).
+__device__ __forceinline__ void reduce_flat_mean8(const float* const* member, int K, float* out, long long e0) {
+  float4 a0 = *reinterpret_cast<const float4*>(member[0] + e0);
+  float4 a1 = *reinterpret_cast<const float4*>(member[0] + e0 + 4);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k = 1; k < K; k += 4) {
+    float4 v[4][2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (k + u < K) {
+        v[u][0] = *reinterpret_cast<const float4*>(member[k + u] + e0);
+        v[u][1] = *reinterpret_cast<const float4*>(member[k + u] + e0 + 4);
+      } else {
+        v[u][0] = a0;
+        v[u][1] = a1;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[0] += v[u][0].x - a0.x;
+      s[1] += v[u][0].y - a0.y;
+      s[2] += v[u][0].z - a0.z;
+      s[3] += v[u][0].w - a0.w;
+      s[4] += v[u][1].x - a1.x;
+      s[5] += v[u][1].y - a1.y;
+      s[6] += v[u][1].z - a1.z;
+      s[7] += v[u][1].w - a1.w;
+    }
+  }
+  const float inv_k = 1.0f / (float)K;
+  *reinterpret_cast<float4*>(out + e0) =
+      make_float4(a0.x + s[0] * inv_k, a0.y + s[1] * inv_k, a0.z + s[2] * inv_k, a0.w + s[3] * inv_k);
+  *reinterpret_cast<float4*>(out + e0 + 4) =
+      make_float4(a1.x + s[4] * inv_k, a1.y + s[5] * inv_k, a1.z + s[6] * inv_k, a1.w + s[7] * inv_k);
+}
+
 // any channel count: one thread per pixel, scalar loads
 __device__ __forceinline__ void reduce_pixel_any_c(const float* const* member, int K, const ReduceJob& jb,
                                                    long long px) {
@@ -153,6 +191,19 @@ __global__ void __launch_bounds__(256) reduce_members_batched_kernel(const __gri
   const int K = b.num_members;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (jb.spread_mode == UB_SPREAD_NONE && jb.vec_ok && jb.out_mean) {
+    const long long n = jb.num_pixels * jb.channels;
+    const long long groups = n / 8;
+    for (long long g = tid; g < groups; g += stride) reduce_flat_mean8(member, K, jb.out_mean, g * 8);
+    const float inv_k = 1.0f / (float)K;
+    for (long long e = groups * 8 + tid; e < n; e += stride) {
+      const float x0 = member[0][e];
+      float acc = 0.f;
+      for (int k = 1; k < K; ++k) acc += member[k][e] - x0;
+      jb.out_mean[e] = x0 + acc * inv_k;
+    }
+    return;
+  }
   if (jb.channels == 1 || jb.channels == 3) {
     const long long groups = (jb.num_pixels + 3) / 4;
     for (long long g = tid; g < groups; g += stride) {
@@ -208,7 +259,8 @@ int ub_reduce_members_batched(const ub_reduce_job* jobs_host, int32_t num_jobs, 
     b.job[j].out_mean = in.out_mean;
     b.job[j].out_spread = in.out_spread;
     b.job[j].vec_ok = vec_ok ? 1 : 0;
-    const long long threads = (in.channels == 1 || in.channels == 3) ? (in.num_pixels + 3) / 4 : in.num_pixels;
+    long long threads = (in.channels == 1 || in.channels == 3) ? (in.num_pixels + 3) / 4 : in.num_pixels;
+    if (b.job[j].spread_mode == UB_SPREAD_NONE && vec_ok) threads = (in.num_pixels * in.channels + 7) / 8;
     if (threads > max_threads) max_threads = threads;
   }
   if (max_threads == 0) return UB_OK;

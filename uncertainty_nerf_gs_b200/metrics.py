@@ -243,3 +243,69 @@ def per_image_rgb_scalars(d: Dict[str, object]) -> Dict[str, float]:
         "rgb_auc_abs_error": d["auc_abs_error_values"], "rgb_auc_length": d["auc_length_values"],
         "rgb_auc_neg_error": d["auc_neg_error_values"],
     }
+
+
+def score_depth_batch(depth: Tensor, depth_std: Tensor, depth_gt: Tensor, scales: Sequence[float],
+                      min_depth_std_for_nll: float = 1.0) -> List[Dict[str, object]]:
+    """``get_unc_metrics_depth`` (eval_uncertainty.py:415-644) for a batch of views, downstream of file
+    loading and without the resize branch.  ``depth, depth_std, depth_gt [B, H, W]`` (or ``[B, H, W, 1]``);
+    ``scales[b]`` is the per-dataset scale ``a``.  Per view: scale, clamp to ``[1e-3, max gt]``, keep the
+    pixels with ``gt > 0`` (a ragged segment per view), then the same kernels as the rgb path with one
+    channel and sigma = std: prologue (se / ae / var, NLL with eps = ``min_depth_std_for_nll``, interval
+    histogram), one segmented sort over 3B ragged segments, cut-point prefix sums.  The cheap per-view
+    elementwise preparation uses torch ops (same fp32 semantics as the reference's own torch lines)."""
+    if depth.dim() == 4:
+        depth, depth_std = depth[..., 0], depth_std[..., 0]
+    if depth_gt.dim() == 4:
+        depth_gt = depth_gt[..., 0]
+    b = depth.shape[0]
+    dev = depth.device
+    preds, stds, gts, lens = [], [], [], []
+    for i in range(b):
+        gt = depth_gt[i]
+        max_d = gt.max().float()
+        d = float(scales[i]) * depth[i]
+        s = float(scales[i]) * depth_std[i]
+        mask = gt > 0
+        dm = torch.clamp(d[mask], min=1e-3)
+        dm = torch.minimum(dm, max_d)
+        preds.append(dm)
+        stds.append(s[mask])
+        gts.append(gt[mask])
+        lens.append(int(dm.numel()))
+    pred = torch.cat(preds).reshape(-1, 1).contiguous()
+    std = torch.cat(stds).contiguous()
+    gt = torch.cat(gts).reshape(-1, 1).contiguous()
+    total = pred.shape[0]
+    z = _z_table(dev)
+    pro = ops.score_prologue(pred, gt, std, lens, z, nll_min_std=min_depth_std_for_nll, sigma_from_var=False,
+                             want_vectors=True)
+    vec = pro["vectors"]
+    ae, se = vec[1], vec[2]
+    cuts = np.stack([ause_cut_counts(n) for n in lens])
+    sorted_all, perm_all = ops.segmented_sort(vec.reshape(-1), lens * 3, want_perm=True, want_keys=True)
+    perm_var = perm_all[:total]
+    sums = ops.cut_prefix_sums([ae, se, sorted_all[total:2 * total], sorted_all[2 * total:]],
+                               [perm_var, perm_var, None, None], lens, cuts)
+    packed = torch.cat([sums.reshape(b, -1), pro["sums"], pro["hist"].to(torch.float64)], dim=1).cpu().numpy()
+    zh = z_values_host()
+    results = []
+    for i in range(b):
+        row, n, ci = packed[i], lens[i], cuts[i]
+        bu_ae, bu_se, or_ae, or_se = row[0:100], row[100:200], row[200:300], row[300:400]
+        psums = row[400:405]
+        hist = np.rint(row[405:405 + len(zh) + 1]).astype(np.int64)
+        d: Dict[str, object] = {}
+        _, d["err_mse"], d["err_var_mse"], d["ause_mse"] = _ause_tail(
+            _prefix_means(or_se, ci, "mse"), _prefix_means(bu_se, ci, "mse"))
+        _, d["err_mae"], d["err_var_mae"], d["ause_mae"] = _ause_tail(
+            _prefix_means(or_ae, ci, "mae"), _prefix_means(bu_ae, ci, "mae"))
+        _, d["err_rmse"], d["err_var_rmse"], d["ause_rmse"] = _ause_tail(
+            _prefix_means(or_se, ci, "rmse"), _prefix_means(bu_se, ci, "rmse"))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            d["nll_depth"] = float(np.float32(psums[3] / n)) if n else float("nan")
+            d["avg_var"] = float(np.float32(psums[2] / n)) if n else float("nan")
+            d["mse_mean"] = float(np.float32(psums[0] / n)) if n else float("nan")
+        d.update(_auce_from_hist(hist, float(psums[4]), float(n), zh))
+        results.append(d)
+    return results

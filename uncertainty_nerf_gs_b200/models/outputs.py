@@ -47,7 +47,9 @@ def active_nerfacto_outputs(density: Tensor, deltas: Tensor, starts: Tensor, end
 
 
 def laplace_outputs_unc(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor, rgb: Tensor,
-                        rgb_var: Tensor, *, averaged_weights: Optional[Tensor] = None, background="last_sample",
+                        rgb_var: Tensor, *, averaged_weights: Optional[Tensor] = None,
+                        density_var: Optional[Tensor] = None, density_noise: Optional[Tensor] = None,
+                        num_draws: int = 100, seed: int = 0, background="last_sample",
                         rays_per_chunk: Optional[int] = None, proposal_levels: Sequence[Level] = ()
                         ) -> Dict[str, Tensor]:
     """``NerfactoLaplaceModel.get_outputs_unc`` downstream of ``field.forward_unc``
@@ -57,6 +59,10 @@ def laplace_outputs_unc(density: Tensor, deltas: Tensor, starts: Tensor, ends: T
     deterministic weights (``use_deterministic_density``)."""
     o = ops.composite_rays(density, deltas, starts, ends, rgb, rgb_var, background=background, beta_mode="raw",
                            rays_per_chunk=rays_per_chunk, eval_mode=True)
+    if averaged_weights is None and density_var is not None:
+        # use_deterministic_density=False: mean weights of `num_draws` density draws (:486-507)
+        averaged_weights = ops.average_sampled_weights(density, density_var, deltas, num_draws=num_draws,
+                                                       noise=density_noise, seed=seed)
     if averaged_weights is not None:
         g = ops.render_weights(averaged_weights, starts, ends, rays_per_chunk=rays_per_chunk,
                                want=("accumulation", "depth", "expected_depth", "depth_std"))

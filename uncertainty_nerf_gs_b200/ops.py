@@ -156,6 +156,31 @@ def render_weights(weights: Tensor, starts: Tensor, ends: Tensor, *, rays_per_ch
     return out
 
 
+def average_sampled_weights(density: Tensor, density_var: Tensor, deltas: Tensor, num_draws: int = 100,
+                            noise: Optional[Tensor] = None, seed: int = 0) -> Tensor:
+    """Mean weights of ``num_draws`` draws ``relu(N(density, sqrt(density_var)))`` (laplace_model.py:486-507)
+    -> ``[R, S, 1]``.  ``noise [num_draws, R, S]`` (standard normal) makes the result comparable with the
+    oracle; without it the draws come from an in-kernel Philox generator."""
+    lib = _lib.load()
+    density = _dev_f32(_squeeze_last(density, "density", 2), "density")
+    R, S = density.shape
+    density_var = _dev_f32(_squeeze_last(density_var, "density_var", 2), "density_var")
+    deltas = _dev_f32(_squeeze_last(deltas, "deltas", 2), "deltas")
+    if density_var.shape != (R, S) or deltas.shape != (R, S):
+        raise ValueError("density_var / deltas must match density")
+    if noise is not None:
+        noise = _dev_f32(noise.reshape(-1, R, S), "noise")
+        if noise.shape[0] != num_draws:
+            raise ValueError("noise must be [num_draws, R, S]")
+    out = torch.empty(R, S, 1, device=density.device)
+    with torch.cuda.device(density.device):
+        _lib.check(lib.ub_average_sampled_weights(density.data_ptr(), density_var.data_ptr(), deltas.data_ptr(),
+                                                  _ptr(noise), R, S, int(num_draws), int(seed), out.data_ptr(),
+                                                  _stream()))
+    _count(1 if R > 0 else 0)
+    return out
+
+
 _SPREAD = {None: _lib.UB_SPREAD_NONE, "std": _lib.UB_SPREAD_STD, "var": _lib.UB_SPREAD_VAR}
 
 
