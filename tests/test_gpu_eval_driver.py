@@ -1,0 +1,44 @@
+"""GPU: the batched eval driver (score -> records -> reference aggregation -> metrics.json) against the
+oracle running the reference's per-view loop semantics (eval_uncertainty.py:896-1077)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics as om
+from uncertainty_nerf_gs_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def test_driver_matches_reference_aggregation(built_library, tmp_path):
+    from uncertainty_nerf_gs_b200 import eval_driver, pipeline
+
+    imgs = [synthetic.scoring_image(48, 64, seed=i) for i in range(5)]
+    views = [({"rgb": p.cuda(), "rgb_std": s.cuda()}, g.cuda()) for p, s, g in imgs]
+    records, extras = eval_driver.score_views(views, batch_size=2)
+    results = eval_driver.average_uncertainty_metrics(records, extras)
+
+    per_image, curves = [], {k: [] for k in ("err_var_mse", "coverage_values")}
+    for p, s, g in imgs:
+        d = om.unc_metrics_rgb(p, g, s)
+        per_image.append(om.per_image_rgb_scalars(d))
+        for k in curves:
+            curves[k].append(np.asarray(d[k], dtype=np.float64))
+    ref_scalars = om.aggregate_scalars(per_image)
+    for k, v in ref_scalars.items():
+        np.testing.assert_allclose(results[k], v, rtol=1e-5, atol=1e-9, err_msg=k)
+    np.testing.assert_allclose(results["err_var_mse"], om.aggregate_curves(curves["err_var_mse"]), rtol=1e-5)
+    assert np.array_equal(results["coverage_values"], om.aggregate_curves(curves["coverage_values"]))
+    assert "num_rays_per_sec" in results and "fps" in results
+
+    out = tmp_path / "run" / "metrics.json"
+    eval_driver.write_metrics_json(out, "exp", "active-nerfacto", "ckpt/step-000029999.ckpt", results)
+    info = json.loads(out.read_text())
+    assert list(info.keys()) == ["experiment_name", "method_name", "checkpoint", "results"]
+    for k in ("rgb_ause_mse", "rgb_ause_mae", "rgb_ause_rmse", "rgb_mse", "rgb_rmse", "rgb_nll", "rgb_avg_var",
+              "rgb_auc_abs_error", "rgb_auc_length", "rgb_auc_neg_error", "num_rays_per_sec", "fps"):
+        assert isinstance(info["results"][k], float)
+    eval_driver.save_curves(tmp_path / "plots", results)
+    assert np.load(tmp_path / "plots" / "rgb_coverage_values.npy").shape == (99,)

@@ -1,0 +1,21 @@
+"""CPU: the plugin glue imports without nerfstudio, names the reference's methods, and refuses to patch when
+the reference package is not installed."""
+import pytest
+
+
+def test_plugin_module_imports_without_nerfstudio():
+    from uncertainty_nerf_gs_b200.models import nerfstudio_plugin as plug
+
+    assert plug.METHOD_NAMES == ("active-nerfacto", "active-splatfacto", "nerfacto-mcdropout", "nerfacto-laplace")
+    assert "active-nerfacto" in plug.ENSEMBLE_METHOD_NAMES and "nerfacto" in plug.ENSEMBLE_METHOD_NAMES
+    with pytest.raises(ImportError):
+        plug.patch_reference_models()      # nerfuncertainty / nerfstudio are not installed here
+
+
+def test_output_key_order_constants():
+    from uncertainty_nerf_gs_b200 import pipeline
+    from uncertainty_nerf_gs_b200.models import outputs
+
+    assert outputs.STD_KEYS == ("rgb", "depth", "expected_depth")
+    assert pipeline.RECORD_LEN == 6 * 100 + 5 * 99 + 10 + 1
+    assert pipeline.SCALAR_KEYS[:3] == ("rgb_ause_mse", "rgb_ause_mae", "rgb_ause_rmse")

@@ -181,8 +181,8 @@ def auce(mean_values: ArrayLike, sigma_values: ArrayLike, target_values: ArrayLi
     return _auce_from_hist(hist, sigma_sum, float(n), z_values_host())
 
 
-def score_rgb_batch(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb_std_for_nll: float = 3e-2
-                    ) -> List[Dict[str, object]]:
+def score_rgb_batch_async(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb_std_for_nll: float = 3e-2
+                          ) -> "PendingScores":
     """``get_unc_metrics_rgb`` (eval_uncertainty.py:306-402) for a batch of images in one set of
     segmented launches.  ``rgb_pred, rgb_gt [B, H, W, 3]``, ``rgb_std [B, H, W, 1]`` (CUDA float32; the
     ground truth already composited with the background for splat models).  Returns one dict per image
@@ -209,28 +209,53 @@ def score_rgb_batch(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb_s
     perm_var = perm_all[:total]
     sums = ops.cut_prefix_sums([ae, se, sorted_all[total:2 * total], sorted_all[2 * total:]],
                                [perm_var, perm_var, None, None], lens, cuts)          # [B, 4, 100]
-    # one device->host transfer for everything the host tail needs
-    packed = torch.cat([sums.reshape(b, -1), pro["sums"], pro["hist"].to(torch.float64)], dim=1).cpu().numpy()
-    zh = z_values_host()
-    results = []
-    for i in range(b):
-        row = packed[i]
-        bu_ae, bu_se, or_ae, or_se = row[0:100], row[100:200], row[200:300], row[300:400]
-        psums = row[400:405]
-        hist = np.rint(row[405:405 + len(zh) + 1]).astype(np.int64)
-        d: Dict[str, object] = {}
-        _, d["err_mae"], d["err_var_mae"], d["ause_mae"] = _ause_tail(
-            _prefix_means(or_ae, cuts_one, "mae"), _prefix_means(bu_ae, cuts_one, "mae"))
-        _, d["err_mse"], d["err_var_mse"], d["ause_mse"] = _ause_tail(
-            _prefix_means(or_se, cuts_one, "mse"), _prefix_means(bu_se, cuts_one, "mse"))
-        _, d["err_rmse"], d["err_var_rmse"], d["ause_rmse"] = _ause_tail(
-            _prefix_means(or_se, cuts_one, "rmse"), _prefix_means(bu_se, cuts_one, "rmse"))
-        d["nll_rgb"] = float(np.float32(psums[3] / (n * c)))
-        d["avg_var"] = float(np.float32(psums[2] / n))
-        d["mse_mean"] = float(np.float32(psums[0] / n))
-        d.update(_auce_from_hist(hist, float(psums[4]) * c, float(n * c), zh))
-        results.append(d)
-    return results
+    # one device->host transfer for everything the host tail needs (asynchronous into pinned memory)
+    packed_dev = torch.cat([sums.reshape(b, -1), pro["sums"], pro["hist"].to(torch.float64)], dim=1)
+    packed_host = torch.empty(packed_dev.shape, dtype=packed_dev.dtype, pin_memory=True)
+    packed_host.copy_(packed_dev, non_blocking=True)
+    done = torch.cuda.Event()
+    done.record()
+    return PendingScores(packed_host, packed_dev, done, b, n, c, cuts_one)
+
+
+class PendingScores:
+    """Device work of ``score_rgb_batch`` in flight: ``finish()`` waits for the packed result and runs the
+    numpy tail.  Lets a driver enqueue the next view before the previous one's record is read back."""
+
+    def __init__(self, packed_host, packed_dev, done, b, n, c, cuts_one):
+        self.packed_host, self.packed_dev, self.done = packed_host, packed_dev, done
+        self.b, self.n, self.c, self.cuts_one = b, n, c, cuts_one
+
+    def finish(self) -> List[Dict[str, object]]:
+        self.done.synchronize()
+        packed = self.packed_host.numpy()
+        b, n, c, cuts_one = self.b, self.n, self.c, self.cuts_one
+        zh = z_values_host()
+        results = []
+        for i in range(b):
+            row = packed[i]
+            bu_ae, bu_se, or_ae, or_se = row[0:100], row[100:200], row[200:300], row[300:400]
+            psums = row[400:405]
+            hist = np.rint(row[405:405 + len(zh) + 1]).astype(np.int64)
+            d: Dict[str, object] = {}
+            _, d["err_mae"], d["err_var_mae"], d["ause_mae"] = _ause_tail(
+                _prefix_means(or_ae, cuts_one, "mae"), _prefix_means(bu_ae, cuts_one, "mae"))
+            _, d["err_mse"], d["err_var_mse"], d["ause_mse"] = _ause_tail(
+                _prefix_means(or_se, cuts_one, "mse"), _prefix_means(bu_se, cuts_one, "mse"))
+            _, d["err_rmse"], d["err_var_rmse"], d["ause_rmse"] = _ause_tail(
+                _prefix_means(or_se, cuts_one, "rmse"), _prefix_means(bu_se, cuts_one, "rmse"))
+            d["nll_rgb"] = float(np.float32(psums[3] / (n * c)))
+            d["avg_var"] = float(np.float32(psums[2] / n))
+            d["mse_mean"] = float(np.float32(psums[0] / n))
+            d.update(_auce_from_hist(hist, float(psums[4]) * c, float(n * c), zh))
+            results.append(d)
+        return results
+
+
+def score_rgb_batch(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb_std_for_nll: float = 3e-2
+                    ) -> List[Dict[str, object]]:
+    """Synchronous form: ``score_rgb_batch_async(...).finish()``."""
+    return score_rgb_batch_async(rgb_pred, rgb_gt, rgb_std, min_rgb_std_for_nll).finish()
 
 
 def per_image_rgb_scalars(d: Dict[str, object]) -> Dict[str, float]:

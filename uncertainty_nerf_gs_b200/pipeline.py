@@ -60,6 +60,28 @@ def evaluate_view(members: Sequence[Dict[str, Tensor]], rgb_gt: Tensor, height: 
     return d
 
 
+class PendingView:
+    """A view whose device work has been enqueued; ``finish()`` returns the reference's per-image entries."""
+
+    def __init__(self, pending_scores):
+        self._pending = pending_scores
+
+    def finish(self) -> Dict[str, object]:
+        d = self._pending.finish()[0]
+        d.update(metrics.per_image_rgb_scalars(d))
+        return d
+
+
+def evaluate_view_async(members: Sequence[Dict[str, Tensor]], rgb_gt: Tensor, height: int, width: int,
+                        rays_per_chunk: int = 1 << 15, min_rgb_std_for_nll: float = 3e-2,
+                        timers: Optional[list] = None) -> PendingView:
+    """``evaluate_view`` without the final host synchronisation: a driver streaming over a test set enqueues
+    view i+1 before reading view i's record back, so the device never waits for the numpy tail."""
+    outs = render_members(members, height, width, rays_per_chunk, timers)
+    red = mo.ensemble_reduce(outs) if len(outs) > 1 else outs[0]
+    return PendingView(metrics.score_rgb_batch_async(red["rgb"], rgb_gt, red["rgb_std"], min_rgb_std_for_nll))
+
+
 class HostViewEvaluator:
     """End-to-end entry: the caller holds one view's member ray samples and ground truth in *pinned host*
     memory; every call copies them to the device on a copy stream (member m+1 uploads while member m
