@@ -12,7 +12,13 @@
 // float32 in sample order exactly like the reference loop.
 #include "ub_common.cuh"
 
+#include <stdlib.h>
+
 namespace ub {
+
+// tensor-core path (laplace_moments_tc.cu); UB_ERR_UNSUPPORTED when the shape does not fit it
+int launch_laplace_tc(const float* x, long long num_points, const float* params, int n_samples, int act,
+                      float* o_mean, float* o_mean2, float* o_sigma2, cudaStream_t stream);
 
 constexpr int kLapThreads = 128;
 constexpr int kLapH = 64;
@@ -166,9 +172,17 @@ extern "C" int ub_laplace_ll_moments(const float* x, int64_t num_points, int32_t
   UB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0, UB_ERR_UNSUPPORTED,
              "laplace_ll_moments: x must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (out_dim == 3)
+  if (out_dim == 3) {
+    // rgb head: tcgen05 3xTF32 path unless UB_LAPLACE_FMA=1 forces the fp32-FMA kernel
+    static const bool force_fma = [] { const char* e = getenv("UB_LAPLACE_FMA"); return e && atoi(e) != 0; }();
+    if (!force_fma) {
+      const int rc = launch_laplace_tc(x, num_points, sampled_params, n_samples, activation, out_mean, out_mean2,
+                                       out_sigma2, stream);
+      if (rc != UB_ERR_UNSUPPORTED) return rc;
+    }
     return launch_laplace<3, 2>(x, num_points, sampled_params, n_samples, activation, out_mean, out_mean2,
                                 out_sigma2, stream);
+  }
   return launch_laplace<1, 2>(x, num_points, sampled_params, n_samples, activation, out_mean, out_mean2,
                               out_sigma2, stream);
 }
