@@ -245,8 +245,13 @@ int ub_cut_prefix_sums(const float* const* values_host, const int32_t* const* pe
  * order of torch parameters_to_vector) accumulate E[y] and E[y^2]; sigma2 = E[y^2] - E[y]^2.
  * activation: 0 identity, 1 sigmoid (rgb head, :468-476), 2 trunc_exp == exp (density head,
  * :331-339).  out_mean / out_sigma2 [num_points, out_dim]; out_mean2 optional.
+ * The rgb head (out_dim 3, 3 * n_samples <= 304) runs as a [P,64]x[64,300] GEMM on the tensor cores
+ * (tcgen05.mma kind::tf32 with a 3-term hi/lo split, float32 accumulators in tensor memory); the
+ * density head and other shapes use the fp32-FMA kernel.
  * ---------------------------------------------------------------------------------------- */
 enum { UB_ACT_IDENTITY = 0, UB_ACT_SIGMOID = 1, UB_ACT_EXP = 2 };
+/* OR-ed into `activation`: keep the rgb head on the fp32-FMA kernel instead of the tcgen05 3xTF32 path */
+#define UB_ACT_FLAG_NO_TENSOR_CORES 0x100
 
 int ub_laplace_ll_moments(const float* x, int64_t num_points, int32_t hidden, int32_t out_dim,
                           const float* sampled_params, int32_t n_samples, int32_t activation,

@@ -1,0 +1,74 @@
+"""GPU: the remaining BASELINE.json configurations at their full sizes, checked through size-independent
+properties (the CPU oracle needs seconds per image) plus an oracle spot check:
+
+* configs[2]: AUSE / AUCE / NLL over 200 test views of 800 x 800 in one batch of segmented launches;
+* configs[3]: active-splatfacto compositing of 1 M pre-binned Gaussians at 1297 x 840.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics as om
+from uncertainty_nerf_gs_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def test_auce_ause_over_200_views(built_library):
+    from uncertainty_nerf_gs_b200.metrics import score_rgb_batch
+
+    b, h, w = 200, 800, 800
+    g = torch.Generator(device="cuda").manual_seed(0)
+    pred = torch.rand(b, h, w, 3, generator=g, device="cuda")
+    std = torch.clamp(0.1 * torch.rand(b, h, w, 1, generator=g, device="cuda"), min=0.03)
+    gt = torch.clamp(pred + std * torch.randn(b, h, w, 3, generator=g, device="cuda"), 0.0, 1.0)
+    outs = score_rgb_batch(pred, gt, std)
+    assert len(outs) == b
+    n = h * w
+    for d in outs[::17]:
+        cov = d["coverage_values"]
+        assert cov.shape == (99,) and (np.diff(cov) <= 0).all() and 0.0 <= cov[-1] <= cov[0] <= 1.0
+        assert np.allclose(np.rint(cov * 3 * n), cov * 3 * n, atol=1e-6)       # integer counts / (3 N)
+        assert d["err_mse"].shape == (100,) and np.isfinite(d["ause_rmse"])
+        assert abs(d["err_var_mse"][0] - d["err_mse"][0]) < 1e-6              # full-image mean is order independent
+        assert d["auc_abs_error_values"] >= 0 and d["avg_var"] > 0
+    # spot check two images against the oracle (the reference's per-image path)
+    for i in (0, 199):
+        ref = om.unc_metrics_rgb(pred[i].cpu(), gt[i].cpu(), std[i].cpu())
+        assert np.array_equal(outs[i]["coverage_values"], ref["coverage_values"])
+        np.testing.assert_allclose(outs[i]["ause_mae"], ref["ause_mae"], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(outs[i]["err_var_rmse"], ref["err_var_rmse"], rtol=1e-5)
+        np.testing.assert_allclose(outs[i]["nll_rgb"], ref["nll_rgb"], rtol=1e-5)
+
+
+def test_splat_one_million_gaussians_full_view(built_library):
+    from uncertainty_nerf_gs_b200 import binning
+    from uncertainty_nerf_gs_b200.models.outputs import active_splatfacto_outputs
+
+    h, w, g = 840, 1297, 1_000_000
+    sc = synthetic.splat_scene(g, h, w, seed=0, device="cuda")
+    ids, bins = binning.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], h, w)
+    assert bins.shape == (82 * 53, 2)
+    d = sc["depths"][ids.long()]
+    lo, hi = bins[:, 0].long(), bins[:, 1].long()
+    inner = torch.ones(ids.numel(), dtype=torch.bool, device="cuda")
+    inner[lo[lo < ids.numel()]] = False                                       # first entry of every tile
+    assert bool((d[1:][inner[1:]] >= d[:-1][inner[1:]]).all())                # depth-sorted inside every tile
+    bg = torch.tensor([0.2, 0.4, 0.6], device="cuda")
+    out = active_splatfacto_outputs(sc["xys"], sc["depths"], sc["conics"], sc["opacities"], sc["rgbs"], sc["betas"],
+                                    ids, bins, h, w, bg)
+    a = out["accumulation"]
+    assert a.shape == (h, w, 1) and float(a.min()) >= 0.0 and float(a.max()) <= 1.0
+    assert float(out["rgb"].max()) <= 1.0 and float(out["rgb"].min()) >= 0.0
+    covered = a[..., 0] > 0
+    dmin, dmax = float(sc["depths"].min()), float(sc["depths"].max())
+    dep = out["depth"][..., 0][covered]
+    assert float(dep.min()) >= dmin * (1 - 1e-4) and float(dep.max()) <= dmax * (1 + 1e-4)   # convex combination
+    assert float(out["uncertainty"].min()) >= 0.0 and bool(torch.isfinite(out["depth_std"]).all())
+    assert torch.equal(out["rgb_var"], out["uncertainty"] ** 2)
+    # translation property: shifting every colour by c shifts the composited image by c * alpha (+ background)
+    from uncertainty_nerf_gs_b200 import ops
+    col = sc["rgbs"]
+    base, al = ops.composite_tiles(sc["xys"], sc["conics"], sc["opacities"], col, ids, bins, h, w, [0, 0, 0])
+    shifted, _ = ops.composite_tiles(sc["xys"], sc["conics"], sc["opacities"], col + 0.25, ids, bins, h, w, [0, 0, 0])
+    torch.testing.assert_close(shifted, base + 0.25 * al, rtol=1e-4, atol=1e-5)

@@ -104,3 +104,34 @@ def test_empty_tiles_and_background(built_library):
                                      torch.zeros(tiles, 2, dtype=torch.int32, device="cuda"), h, w, [0.5, 0.25, 1.0])
     assert float(alpha.abs().max()) == 0.0
     assert torch.equal(out, torch.tensor([0.5, 0.25, 1.0], device="cuda").expand(h, w, 3))
+
+
+@pytest.mark.parametrize("n_samples,n_points", [(100, 4099), (1, 130), (33, 257), (101, 64)])
+def test_laplace_tensor_core_path_vs_fma_and_oracle(built_library, n_samples, n_points):
+    """rgb head on tcgen05 (3xTF32 split) against the fp32-FMA kernel and the oracle: partial last chunk
+    (3 * n_samples not a multiple of 16), partial last tile, single draw."""
+    from uncertainty_nerf_gs_b200 import ops
+
+    lap = synthetic.laplace_head(n_points, 64, 3, n_samples, seed=n_samples)
+    theta = ol.posterior_samples(lap["mu_q"], lap["ggn"], lap["eps_draws"])
+    mu, mu2, _ = ol.sample_laplace(lap["x"], theta, 3, torch.sigmoid)
+    tc = ops.laplace_ll_moments(lap["x"].cuda(), theta.cuda(), 3, "sigmoid", want_mean2=True, tensor_cores=True)
+    fma = ops.laplace_ll_moments(lap["x"].cuda(), theta.cuda(), 3, "sigmoid", want_mean2=True, tensor_cores=False)
+    for out in (tc, fma):
+        torch.testing.assert_close(out["mean"].cpu(), mu, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(out["mean2"].cpu(), mu2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(tc["mean"], fma["mean"], rtol=1e-5, atol=1e-6)
+
+
+def test_laplace_tensor_core_path_large_magnitudes(built_library):
+    """Pre-activations of magnitude ~30 (saturating sigmoids) and features spanning 6 orders of magnitude:
+    the hi/lo split must keep float32-level accuracy."""
+    from uncertainty_nerf_gs_b200 import ops
+
+    lap = synthetic.laplace_head(2000, 64, 3, 100, seed=77)
+    x = lap["x"] * torch.logspace(-3, 3, 64)[None, :] * 0.05
+    theta = ol.posterior_samples(lap["mu_q"] * 3.0, lap["ggn"], lap["eps_draws"])
+    mu, mu2, _ = ol.sample_laplace(x, theta, 3, torch.sigmoid)
+    out = ops.laplace_ll_moments(x.cuda(), theta.cuda(), 3, "sigmoid", want_mean2=True)
+    torch.testing.assert_close(out["mean"].cpu(), mu, rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(out["mean2"].cpu(), mu2, rtol=2e-5, atol=2e-6)

@@ -165,6 +165,8 @@ extern "C" int ub_laplace_ll_moments(const float* x, int64_t num_points, int32_t
              "laplace_ll_moments: hidden must be %d (nerfacto head width), got %d", kLapH, hidden);
   UB_REQUIRE(out_dim == 1 || out_dim == 3, UB_ERR_UNSUPPORTED,
              "laplace_ll_moments: out_dim must be 1 (density) or 3 (rgb), got %d", out_dim);
+  const bool no_tc = (activation & UB_ACT_FLAG_NO_TENSOR_CORES) != 0;
+  activation &= ~UB_ACT_FLAG_NO_TENSOR_CORES;
   UB_REQUIRE(activation >= UB_ACT_IDENTITY && activation <= UB_ACT_EXP, UB_ERR_BAD_ARG,
              "laplace_ll_moments: bad activation %d", activation);
   if (num_points == 0) return UB_OK;
@@ -175,7 +177,7 @@ extern "C" int ub_laplace_ll_moments(const float* x, int64_t num_points, int32_t
   if (out_dim == 3) {
     // rgb head: tcgen05 3xTF32 path unless UB_LAPLACE_FMA=1 forces the fp32-FMA kernel
     static const bool force_fma = [] { const char* e = getenv("UB_LAPLACE_FMA"); return e && atoi(e) != 0; }();
-    if (!force_fma) {
+    if (!force_fma && !no_tc) {
       const int rc = launch_laplace_tc(x, num_points, sampled_params, n_samples, activation, out_mean, out_mean2,
                                        out_sigma2, stream);
       if (rc != UB_ERR_UNSUPPORTED) return rc;

@@ -394,7 +394,7 @@ _ACTS = {"identity": _lib.UB_ACT_IDENTITY, "sigmoid": _lib.UB_ACT_SIGMOID, "exp"
 
 
 def laplace_ll_moments(x: Tensor, sampled_params: Tensor, out_dim: int, activation: str,
-                       want_mean2: bool = False) -> Dict[str, Tensor]:
+                       want_mean2: bool = False, tensor_cores: bool = True) -> Dict[str, Tensor]:
     """E[y], E[y^2]-E[y]^2 of ``y = act(x W_s^T + b_s)`` over the rows of ``sampled_params``
     (``[n_samples, out_dim*hidden + out_dim]``, torch ``parameters_to_vector`` order)."""
     lib = _lib.load()
@@ -413,7 +413,8 @@ def laplace_ll_moments(x: Tensor, sampled_params: Tensor, out_dim: int, activati
         out["mean2"] = torch.empty(p, out_dim, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.ub_laplace_ll_moments(x.data_ptr(), p, h, out_dim, sampled_params.data_ptr(),
-                                             sampled_params.shape[0], _ACTS[activation], out["mean"].data_ptr(),
+                                             sampled_params.shape[0],
+                                             _ACTS[activation] | (0 if tensor_cores else 0x100), out["mean"].data_ptr(),
                                              _ptr(out.get("mean2")), out["sigma2"].data_ptr(), _stream()))
     _count(1 if p > 0 else 0)
     return out
