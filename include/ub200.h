@@ -99,6 +99,43 @@ size_t ub_composite_rays_workspace_bytes(int64_t num_rays, int64_t rays_per_chun
 int ub_composite_rays(const ub_composite_rays_args* args, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* Backward of ub_composite_rays in training mode (eval_mode 0, beta used as is) w.r.t. density, sample
+ * colours and beta: what `ns-train` needs to run active-nerfacto through the fused compositor (losses:
+ * models/activenerfacto/activenerfacto_model.py:155-191; the interlevel / distortion losses consume the
+ * `weights` output, whose gradient is an input here).  The forward is recomputed from its inputs; only
+ * the forward's median depth (a constant: computed under no_grad in the reference, :99-100) and its
+ * workspace (clip bounds of the expected depth) are needed.  Every g_* pointer may be NULL (zero
+ * gradient); every out_g_* pointer may be NULL.  num_samples in {16, 32, 48, 64, 96}; per-sample tensors
+ * 16-byte aligned. */
+typedef struct ub_composite_rays_bwd_args {
+  const float* density;          /* [R,S] forward inputs                                              */
+  const float* deltas;
+  const float* starts;
+  const float* ends;
+  const float* rgb;              /* [R,S,3]                                                           */
+  const float* beta;             /* [R,S] or NULL                                                     */
+  int64_t num_rays;
+  int32_t num_samples;
+  int32_t background_mode;       /* UB_BG_*                                                           */
+  float background_rgb[3];
+  int64_t rays_per_chunk;
+  const float* depth;            /* [R] median depth returned by the forward                          */
+  const void* chunk_workspace;   /* the forward's workspace (needed with g_expected_depth)            */
+  const float* g_rgb;            /* [R,3] incoming gradients                                          */
+  const float* g_accumulation;   /* [R]                                                               */
+  const float* g_expected_depth; /* [R]                                                               */
+  const float* g_rgb_var;        /* [R]                                                               */
+  const float* g_rgb_std;        /* [R]                                                               */
+  const float* g_depth_var;      /* [R]                                                               */
+  const float* g_depth_std;      /* [R]                                                               */
+  const float* g_weights;        /* [R,S]                                                             */
+  float* out_g_density;          /* [R,S]                                                             */
+  float* out_g_rgb;              /* [R,S,3]                                                           */
+  float* out_g_beta;             /* [R,S]                                                             */
+} ub_composite_rays_bwd_args;
+
+int ub_composite_rays_backward(const ub_composite_rays_bwd_args* args, void* stream);
+
 /* Same renderers driven by given weights instead of densities:
  *   prop_depth_i   models/activenerfacto/activenerfacto_model.py:150-151
  *   depth / depth_var / expected_depth / accumulation from the averaged sampled weights,

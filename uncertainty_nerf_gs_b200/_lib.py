@@ -38,6 +38,18 @@ class CompositeRaysArgs(C.Structure):
     ]
 
 
+class CompositeRaysBwdArgs(C.Structure):
+    _fields_ = [
+        ("density", fp), ("deltas", fp), ("starts", fp), ("ends", fp), ("rgb", fp), ("beta", fp),
+        ("num_rays", C.c_int64), ("num_samples", C.c_int32), ("background_mode", C.c_int32),
+        ("background_rgb", C.c_float * 3), ("rays_per_chunk", C.c_int64),
+        ("depth", fp), ("chunk_workspace", fp),
+        ("g_rgb", fp), ("g_accumulation", fp), ("g_expected_depth", fp), ("g_rgb_var", fp), ("g_rgb_std", fp),
+        ("g_depth_var", fp), ("g_depth_std", fp), ("g_weights", fp),
+        ("out_g_density", fp), ("out_g_rgb", fp), ("out_g_beta", fp),
+    ]
+
+
 class RenderWeightsArgs(C.Structure):
     _fields_ = [
         ("weights", fp), ("starts", fp), ("ends", fp),
@@ -71,6 +83,7 @@ SIGNATURES = {
     "ub_sm_count": (C.c_int, []),
     "ub_composite_rays_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "ub_composite_rays": (C.c_int, [C.POINTER(CompositeRaysArgs), fp, C.c_size_t, fp]),
+    "ub_composite_rays_backward": (C.c_int, [C.POINTER(CompositeRaysBwdArgs), fp]),
     "ub_render_weights_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "ub_render_weights": (C.c_int, [C.POINTER(RenderWeightsArgs), fp, C.c_size_t, fp]),
     "ub_average_sampled_weights": (C.c_int, [fp, fp, fp, fp, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, fp, fp]),

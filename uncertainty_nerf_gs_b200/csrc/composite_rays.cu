@@ -631,10 +631,16 @@ static int launch_tma(const CompositeParams& p, cudaStream_t stream) {
   constexpr size_t smem = NST * stage_bytes + 2 * NST * sizeof(uint64_t);
   static_assert(smem <= 227 * 1024, "stage ring exceeds shared memory");
   auto kern = composite_rays_tma<S, NCW, NST>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    set_error("composite_rays: cannot reserve %zu B shared memory (%s)", smem, cudaGetErrorString(e));
-    return UB_ERR_LAUNCH;
+  static bool configured[64] = {};  // per device: the attribute call costs a few microseconds per launch
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("composite_rays: cannot reserve %zu B shared memory (%s)", smem, cudaGetErrorString(e));
+      return UB_ERR_LAUNCH;
+    }
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const long long tiles = (p.num_rays + kRaysPerTile - 1) / kRaysPerTile;
   int grid = sm_count();

@@ -102,25 +102,33 @@ def composite_rays(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor
     args.beta_mode = _BETA_MODES[beta_mode]
     args.rays_per_chunk = int(rays_per_chunk) if rays_per_chunk else 0
     args.eval_mode = 1 if eval_mode else 0
-    out = {
-        "rgb": torch.empty(R, 3, device=dev), "accumulation": torch.empty(R, 1, device=dev),
-        "depth": torch.empty(R, 1, device=dev), "expected_depth": torch.empty(R, 1, device=dev),
-        "depth_var": torch.empty(R, 1, device=dev), "depth_std": torch.empty(R, 1, device=dev),
-    }
-    args.out_rgb, args.out_accumulation = out["rgb"].data_ptr(), out["accumulation"].data_ptr()
-    args.out_depth, args.out_expected_depth = out["depth"].data_ptr(), out["expected_depth"].data_ptr()
-    args.out_depth_var, args.out_depth_std = out["depth_var"].data_ptr(), out["depth_std"].data_ptr()
+    # one allocation for all per-ray outputs (rows of a [10, R] buffer + the chunk workspace behind it):
+    # the wrapper, not the kernel, bounds the latency of small (training-sized) batches
+    ws_bytes = lib.ub_composite_rays_workspace_bytes(R, args.rays_per_chunk)
+    buf = torch.empty(10 * R + (ws_bytes + 3) // 4 + 4, device=dev)
+    base = buf.data_ptr()
+    row = lambda i, c: buf[i * R:(i + c) * R].view(R, c)
+    out = {"rgb": row(0, 3), "accumulation": row(3, 1), "depth": row(4, 1), "expected_depth": row(5, 1),
+           "depth_var": row(8, 1), "depth_std": row(9, 1)}
+    f = 4 * R
+    args.out_rgb, args.out_accumulation = base, base + 3 * f
+    args.out_depth, args.out_expected_depth = base + 4 * f, base + 5 * f
+    args.out_depth_var, args.out_depth_std = base + 8 * f, base + 9 * f
     if beta is not None:
-        out["rgb_var"] = torch.empty(R, 1, device=dev)
-        out["rgb_std"] = torch.empty(R, 1, device=dev)
-        args.out_rgb_var, args.out_rgb_std = out["rgb_var"].data_ptr(), out["rgb_std"].data_ptr()
+        out["rgb_var"], out["rgb_std"] = row(6, 1), row(7, 1)
+        args.out_rgb_var, args.out_rgb_std = base + 6 * f, base + 7 * f
     if return_weights:
         out["weights"] = torch.empty(R, S, 1, device=dev)
         args.out_weights = out["weights"].data_ptr()
-    ws_bytes = lib.ub_composite_rays_workspace_bytes(R, args.rays_per_chunk)
-    ws = _workspace(ws_bytes, dev)
-    with torch.cuda.device(dev):
-        _lib.check(lib.ub_composite_rays(C.byref(args), ws.data_ptr(), ws.numel(), _stream()))
+    ws_ptr = base + 10 * f
+    ws_ptr += (-ws_ptr) % 16
+    ws_off = (ws_ptr - base) // 4
+    out["_workspace"] = buf[ws_off:ws_off + (ws_bytes + 3) // 4]   # chunk clip bounds (used by the backward)
+    if torch.cuda.current_device() == dev.index:
+        _lib.check(lib.ub_composite_rays(C.byref(args), ws_ptr, ws_bytes, _stream()))
+    else:
+        with torch.cuda.device(dev):
+            _lib.check(lib.ub_composite_rays(C.byref(args), ws_ptr, ws_bytes, _stream()))
     _count(2 if R > 0 else 0)
     return out
 
