@@ -305,11 +305,40 @@ int ub_laplace_ll_moments(const float* x, int64_t num_points, int32_t hidden, in
  * ---------------------------------------------------------------------------------------- */
 #define UB_TILE 16
 #define UB_MAX_SPLAT_CHANNELS 8
+#define UB_MAX_SPLAT_PLANES 4
 
 int ub_composite_tiles(const float* xys, const float* conics, const float* opacities,
                        const float* colors, int32_t channels, const int32_t* gaussian_ids,
                        const int32_t* tile_bins, int32_t img_height, int32_t img_width,
                        const float* background_host, float* out, float* out_alpha, void* stream);
+
+/* Same pass with the colours given as up to UB_MAX_SPLAT_PLANES separate tensors ("planes", e.g. rgb [G,3],
+ * beta [G,1], depth [G,1]; at most UB_MAX_SPLAT_CHANNELS channels in total) and one output image per plane
+ * (outs_host[p]: [H, W, plane_channels[p]], may be NULL).  planes_host / plane_channels_host / outs_host are
+ * HOST arrays.  background_host: one value per channel in plane order (NULL = 0).  channel_max_keys:
+ * optional DEVICE uint32 [total channels]; receives, per channel, the order-preserving key of the maximum
+ * of the output image (the `depth_im.max()` of activesplatfacto_model.py:319; consumed by
+ * ub_splat_normalize). */
+int ub_composite_tiles_planes(const float* xys, const float* conics, const float* opacities,
+                              const float* const* planes_host, const int32_t* plane_channels_host,
+                              int32_t num_planes, const int32_t* gaussian_ids, const int32_t* tile_bins,
+                              int32_t img_height, int32_t img_width, const float* background_host,
+                              float* const* outs_host, float* out_alpha, uint32_t* channel_max_keys,
+                              void* stream);
+
+/* In-place post-processing of one output plane [num_pixels, channels]:
+ *   clamp_max_one   : image = min(image, 1)                       activesplatfacto_model.py:275
+ *   divide_by_alpha : image = alpha > 0 ? image / alpha : max     activesplatfacto_model.py:319, 356
+ * max_key: DEVICE pointer to the plane's entry of channel_max_keys. */
+int ub_splat_normalize(float* image, int32_t channels, const float* alpha, int64_t num_pixels,
+                       int32_t clamp_max_one, int32_t divide_by_alpha, const uint32_t* max_key, void* stream);
+
+/* out_sq_residual[g] = (depth_g - depth_image[floor(y_g), floor(x_g)])^2 when the centre pixel satisfies
+ * 0 < x < W and 0 < y < H (strict, as the reference's mask), else depth_g^2: the colours of the
+ * depth-variance pass, activesplatfacto_model.py:325-349.  depth_image [H, W] is the normalised depth. */
+int ub_splat_depth_residual(const float* xys, const float* depths, const float* depth_image,
+                            int32_t img_height, int32_t img_width, int64_t num_gaussians,
+                            float* out_sq_residual, void* stream);
 
 #ifdef __cplusplus
 }

@@ -133,22 +133,16 @@ def active_splatfacto_outputs(xys: Tensor, depths: Tensor, conics: Tensor, opaci
     (reference activesplatfacto_model.py:260-367): one fused pass for rgb + beta + depth, the
     per-Gaussian squared depth residual, and a second pass for the depth variance."""
     g = xys.shape[0]
-    colors = torch.cat([rgbs.reshape(g, 3), betas.reshape(g, 1), depths.reshape(g, 1)], dim=1)
     bg = [float(v) for v in background.tolist()] + [0.0, 0.0]
-    img, alpha = ops.composite_tiles(xys, conics, opacities, colors, gaussian_ids, tile_bins, height, width, bg)
-    rgb = torch.clamp(img[..., 0:3], max=1.0)
-    uncertainty = img[..., 3:4]
-    depth_raw = img[..., 4:5]
-    depth_im = torch.where(alpha > 0, depth_raw / alpha, depth_raw.detach().max())
-    # squared residual of every Gaussian's depth against the rendered depth at its centre pixel (:325-341)
-    pix = torch.floor(xys).long()
-    valid = (pix[:, 0] > 0) & (pix[:, 0] < width) & (pix[:, 1] > 0) & (pix[:, 1] < height)
-    resid = depths.reshape(g).clone()
-    pv = pix[valid]
-    resid[valid] -= depth_im[pv[:, 1], pv[:, 0], 0]
-    dvar_raw, _ = ops.composite_tiles(xys, conics, opacities, (resid ** 2).reshape(g, 1), gaussian_ids, tile_bins,
-                                      height, width, [0.0])
-    depth_var = torch.where(alpha > 0, dvar_raw / alpha, dvar_raw.detach().max())
+    (rgb, uncertainty, depth_im), alpha, keys = ops.composite_tiles_planes(
+        xys, conics, opacities, [rgbs.reshape(g, 3), betas.reshape(g, 1), depths.reshape(g, 1)], gaussian_ids,
+        tile_bins, height, width, bg, want_max=True)
+    ops.splat_normalize_(rgb, clamp_max_one=True)                       # rgb = clamp(rgb, max=1)         (:275)
+    ops.splat_normalize_(depth_im, alpha, keys[4:5])                    # depth / alpha, else max(depth)   (:319)
+    resid2 = ops.splat_depth_residual(xys, depths, depth_im)            # per-Gaussian squared residual    (:325-349)
+    (depth_var,), _, vkeys = ops.composite_tiles_planes(xys, conics, opacities, [resid2], gaussian_ids, tile_bins,
+                                                        height, width, [0.0], want_max=True)
+    ops.splat_normalize_(depth_var, alpha, vkeys[0:1])                  # / alpha, else max                (:356)
     return {
         "rgb": rgb,
         "depth": depth_im,

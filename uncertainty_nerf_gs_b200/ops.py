@@ -456,3 +456,68 @@ def composite_tiles(xys: Tensor, conics: Tensor, opacities: Tensor, colors: Tens
                                           out.data_ptr(), alpha.data_ptr(), _stream()))
     _count(1)
     return out, alpha
+
+
+def composite_tiles_planes(xys: Tensor, conics: Tensor, opacities: Tensor, planes: Sequence[Tensor],
+                           gaussian_ids: Tensor, tile_bins: Tensor, height: int, width: int,
+                           background: Optional[Sequence[float]] = None, want_max: bool = False
+                           ) -> Tuple[List[Tensor], Tensor, Optional[Tensor]]:
+    """One compositing pass over several colour planes (``[G, c_p]`` each, <= 8 channels in total) ->
+    ``([H, W, c_p] per plane, alpha [H, W, 1], per-channel max keys or None)``."""
+    lib = _lib.load()
+    xys, conics = _dev_f32(xys, "xys"), _dev_f32(conics, "conics")
+    opacities = _dev_f32(opacities.reshape(-1), "opacities")
+    g = xys.shape[0]
+    pls = [_dev_f32(p.reshape(g, -1), f"planes[{i}]") for i, p in enumerate(planes)]
+    chs = [int(p.shape[1]) for p in pls]
+    if xys.shape != (g, 2) or conics.shape != (g, 3) or opacities.numel() != g:
+        raise ValueError("xys [G,2], conics [G,3], opacities [G] must match the colour planes")
+    for name, t in (("gaussian_ids", gaussian_ids), ("tile_bins", tile_bins)):
+        if t.dtype != torch.int32 or not t.is_cuda:
+            raise TypeError(f"{name} must be a CUDA int32 tensor")
+    gaussian_ids, tile_bins = gaussian_ids.contiguous(), tile_bins.contiguous()
+    tiles = ((width + _lib.UB_TILE - 1) // _lib.UB_TILE) * ((height + _lib.UB_TILE - 1) // _lib.UB_TILE)
+    if tile_bins.shape != (tiles, 2):
+        raise ValueError(f"tile_bins must be [{tiles}, 2]")
+    dev = xys.device
+    total = sum(chs)
+    outs = [torch.empty(height, width, c, device=dev) for c in chs]
+    alpha = torch.empty(height, width, 1, device=dev)
+    keys = torch.empty(total, dtype=torch.int32, device=dev) if want_max else None
+    bg = (C.c_float * total)(*([0.0] * total if background is None else [float(v) for v in background]))
+    pp = (C.c_void_p * len(pls))(*[p.data_ptr() for p in pls])
+    pc = (C.c_int32 * len(pls))(*chs)
+    po = (C.c_void_p * len(pls))(*[o.data_ptr() for o in outs])
+    with torch.cuda.device(dev):
+        _lib.check(lib.ub_composite_tiles_planes(xys.data_ptr(), conics.data_ptr(), opacities.data_ptr(), pp, pc,
+                                                 len(pls), gaussian_ids.data_ptr(), tile_bins.data_ptr(), height,
+                                                 width, bg, po, alpha.data_ptr(), _ptr(keys), _stream()))
+    _count(1)
+    return outs, alpha, keys
+
+
+def splat_normalize_(image: Tensor, alpha: Optional[Tensor] = None, max_key: Optional[Tensor] = None,
+                     clamp_max_one: bool = False) -> Tensor:
+    """In place: ``min(image, 1)`` and / or ``alpha > 0 ? image / alpha : max`` (activesplatfacto_model.py:275,319)."""
+    lib = _lib.load()
+    ch = int(image.shape[-1])
+    n = image.numel() // ch
+    with torch.cuda.device(image.device):
+        _lib.check(lib.ub_splat_normalize(image.data_ptr(), ch, _ptr(alpha), n, 1 if clamp_max_one else 0,
+                                          1 if alpha is not None else 0, _ptr(max_key), _stream()))
+    _count(1)
+    return image
+
+
+def splat_depth_residual(xys: Tensor, depths: Tensor, depth_image: Tensor) -> Tensor:
+    """Squared residual of every Gaussian's depth against the rendered depth at its centre pixel -> ``[G, 1]``."""
+    lib = _lib.load()
+    xys, depths = _dev_f32(xys, "xys"), _dev_f32(depths.reshape(-1), "depths")
+    depth_image = _dev_f32(depth_image, "depth_image")
+    h, w = int(depth_image.shape[0]), int(depth_image.shape[1])
+    out = torch.empty(depths.numel(), 1, device=xys.device)
+    with torch.cuda.device(xys.device):
+        _lib.check(lib.ub_splat_depth_residual(xys.data_ptr(), depths.data_ptr(), depth_image.data_ptr(), h, w,
+                                               depths.numel(), out.data_ptr(), _stream()))
+    _count(1)
+    return out
