@@ -340,6 +340,27 @@ int ub_splat_depth_residual(const float* xys, const float* depths, const float* 
                             int32_t img_height, int32_t img_width, int64_t num_gaussians,
                             float* out_sq_residual, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (f2) Tile binning of projected Gaussians (setup step; the compositing above takes its outputs).
+ * Replaces what gsplat does inside every rasterize_gaussians call of activesplatfacto_model.py:260-355
+ * (tile rectangle = centre +- radius in tile units, (tile << 32 | depth) keys, stable sort, tile ranges).
+ * Two phases because the output size is data dependent:
+ *   ub_bin_count      out_offsets [G] = exclusive prefix of the per-Gaussian tile counts, *out_total (DEVICE
+ *                     int64) = number of intersections I; the caller reads it back to size the outputs;
+ *   ub_bin_gaussians  out_gaussian_ids [I] int32 sorted by (tile, depth, intersection order),
+ *                     out_tile_bins [tiles, 2] int32 ([p, p) for an empty tile, p = start of the next one).
+ * xys [G,2], depths [G] float32, radii [G] int32 (radius <= 0: culled).
+ * ---------------------------------------------------------------------------------------- */
+size_t ub_bin_count_workspace_bytes(int64_t num_gaussians);
+int ub_bin_count(const float* xys, const int32_t* radii, int64_t num_gaussians, int32_t img_height,
+                 int32_t img_width, int64_t* out_offsets, int64_t* out_total, void* workspace,
+                 size_t workspace_bytes, void* stream);
+size_t ub_bin_gaussians_workspace_bytes(int64_t num_intersections);
+int ub_bin_gaussians(const float* xys, const float* depths, const int32_t* radii, int64_t num_gaussians,
+                     int32_t img_height, int32_t img_width, const int64_t* offsets, int64_t num_intersections,
+                     int32_t* out_gaussian_ids, int32_t* out_tile_bins, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle import compositing as oc, laplace as ol, reduce as orc, ref_loader, splat as osp  # noqa: E402
-from uncertainty_nerf_gs_b200 import binning, synthetic  # noqa: E402
+from uncertainty_nerf_gs_b200 import synthetic  # noqa: E402
 
 
 def main():
@@ -87,7 +87,7 @@ def main():
                         sigma2=s2.numpy())
 
     sc = synthetic.splat_scene(400, 40, 56, seed=2, mean_scale_px=4.0)
-    ids, bins = binning.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], 40, 56)
+    ids, bins = osp.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], 40, 56)
     so = osp.active_splatfacto_outputs(sc["xys"], sc["depths"], sc["conics"], sc["opacities"], sc["rgbs"],
                                        sc["betas"], ids, bins, 40, 56, torch.tensor([0.1, 0.2, 0.3]))
     np.savez_compressed(os.path.join(HERE, "splat_golden.npz"), ids=ids.numpy(), bins=bins.numpy(),

@@ -49,6 +49,9 @@ def test_splat_one_million_gaussians_full_view(built_library):
     sc = synthetic.splat_scene(g, h, w, seed=0, device="cuda")
     ids, bins = binning.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], h, w)
     assert bins.shape == (82 * 53, 2)
+    from oracle import splat as osp
+    ids_ref, bins_ref = osp.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], h, w)   # torch restatement, on the GPU
+    assert torch.equal(ids, ids_ref) and torch.equal(bins, bins_ref)
     d = sc["depths"][ids.long()]
     lo, hi = bins[:, 0].long(), bins[:, 1].long()
     inner = torch.ones(ids.numel(), dtype=torch.bool, device="cuda")

@@ -46,8 +46,27 @@ def test_laplace_chunked_samples(built_library):
 
 def _scene(n, h, w, seed):
     sc = synthetic.splat_scene(n, h, w, seed=seed, mean_scale_px=4.0)
-    ids, bins = binning.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], h, w)
+    ids, bins = osp.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], h, w)
     return sc, ids, bins
+
+
+@pytest.mark.parametrize("n,hw", [(400, (40, 56)), (5000, (100, 130)), (1, (16, 16)), (300, (17, 33))])
+def test_cuda_binning_is_bit_exact(built_library, n, hw):
+    """ub_bin_count / ub_bin_gaussians against the torch restatement of gsplat's scheme: identical lists."""
+    h, w = hw
+    sc = synthetic.splat_scene(n, h, w, seed=n, mean_scale_px=4.0)
+    sc["radii"][::7] = 0                                    # culled Gaussians
+    sc["depths"][1::5] = sc["depths"][0]                    # depth ties: intersection order must break them
+    ids_ref, bins_ref = osp.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], h, w)
+    ids, bins = binning.bin_gaussians(sc["xys"].cuda(), sc["depths"].cuda(), sc["radii"].cuda(), h, w)
+    assert torch.equal(ids.cpu(), ids_ref) and torch.equal(bins.cpu(), bins_ref)
+
+
+def test_cuda_binning_no_intersections(built_library):
+    sc = synthetic.splat_scene(50, 32, 32, seed=1)
+    sc["radii"][:] = 0
+    ids, bins = binning.bin_gaussians(sc["xys"].cuda(), sc["depths"].cuda(), sc["radii"].cuda(), 32, 32)
+    assert ids.numel() == 0 and bins.shape == (4, 2) and int(bins.abs().max()) == 0
 
 
 def _close_fraction(a, b, rtol, atol):

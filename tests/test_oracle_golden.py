@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import compositing as oc, laplace as ol, metrics as om, reduce as orc, ref_loader, splat as osp
-from uncertainty_nerf_gs_b200 import binning, synthetic
+from uncertainty_nerf_gs_b200 import synthetic
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -127,7 +127,7 @@ def test_laplace_oracle_golden():
 def test_splat_oracle_golden():
     z = _load("splat_golden.npz")
     sc = synthetic.splat_scene(400, 40, 56, seed=2, mean_scale_px=4.0)
-    ids, bins = binning.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], 40, 56)
+    ids, bins = osp.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], 40, 56)
     assert np.array_equal(ids.numpy(), z["ids"]) and np.array_equal(bins.numpy(), z["bins"])
     so = osp.active_splatfacto_outputs(sc["xys"], sc["depths"], sc["conics"], sc["opacities"], sc["rgbs"],
                                        sc["betas"], ids, bins, 40, 56, torch.tensor([0.1, 0.2, 0.3]))

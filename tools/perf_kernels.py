@@ -87,6 +87,9 @@ def splat():
     sc = synthetic.splat_scene(G, H, W, seed=0, device=dev)
     ids, bins = binning.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], H, W)
     I = ids.numel()
+    msb = timeit(lambda i: binning.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], H, W), iters=10)
+    print(json.dumps({"kernel": "bin_gaussians (count+scan+expand+2 sorts+ranges)", "gaussians": G, "intersections": I,
+                      "ms": msb, "Mintersections_s": I / msb / 1e3}))
     planes = [sc["rgbs"], sc["betas"], sc["depths"][:, None].contiguous()]
     ms5 = timeit(lambda i: ops.composite_tiles_planes(sc["xys"], sc["conics"], sc["opacities"], planes, ids, bins, H, W), iters=10)
     ms3 = timeit(lambda i: ops.composite_tiles(sc["xys"], sc["conics"], sc["opacities"], sc["rgbs"], ids, bins, H, W), iters=10)

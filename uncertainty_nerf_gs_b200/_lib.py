@@ -98,6 +98,11 @@ SIGNATURES = {
                                      fp, C.c_int32, fp, fp, C.c_size_t, fp]),
     "ub_laplace_ll_moments": (C.c_int, [fp, C.c_int64, C.c_int32, C.c_int32, fp, C.c_int32, C.c_int32,
                                         fp, fp, fp, fp]),
+    "ub_bin_count_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "ub_bin_count": (C.c_int, [fp, fp, C.c_int64, C.c_int32, C.c_int32, fp, fp, fp, C.c_size_t, fp]),
+    "ub_bin_gaussians_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "ub_bin_gaussians": (C.c_int, [fp, fp, fp, C.c_int64, C.c_int32, C.c_int32, fp, C.c_int64, fp, fp, fp,
+                                   C.c_size_t, fp]),
     "ub_composite_tiles_planes": (C.c_int, [fp, fp, fp, C.POINTER(fp), C.POINTER(C.c_int32), C.c_int32, fp, fp,
                                             C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(fp), fp, fp, fp]),
     "ub_splat_normalize": (C.c_int, [fp, C.c_int32, fp, C.c_int64, C.c_int32, C.c_int32, fp, fp]),

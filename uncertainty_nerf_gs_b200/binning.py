@@ -1,18 +1,20 @@
-"""Tile binning of projected 2-D Gaussians (setup step, NOT on the timed hot path).
+"""Tile binning of projected 2-D Gaussians on the device (setup step, NOT on the timed hot path).
 
-BASELINE.json's splat configuration composites over *pre-binned* per-tile lists, so binning happens
-once outside the timed region.  This module builds those lists with plain torch ops (any device),
-following the published gsplat 0.1.x scheme the reference relies on through
-``gsplat.rasterize_gaussians`` (reference activesplatfacto_model.py:260-273; gsplat itself is not
-vendored): tile rectangle from centre +- radius, one (tile << 32 | depth bits) int64 key per
-(Gaussian, tile) intersection, stable sort, per-tile [start, end) ranges.  A CUDA version reusing the
-radix sort is the "next" row (f2) of SURVEY.md section 8.
+BASELINE.json's splat configuration composites over *pre-binned* per-tile lists, so binning happens once
+outside the timed region.  ``bin_gaussians`` builds those lists with the CUDA kernels of ``csrc/binning.cu``
+(count -> scan -> expand -> two stable radix sorts (depth, then tile) -> ranges), following the published
+gsplat 0.1.x scheme the reference relies on through ``gsplat.rasterize_gaussians`` (reference
+activesplatfacto_model.py:260-273; gsplat itself is not vendored).  The torch restatement used to check it
+lives in ``oracle/splat.py``.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Tuple
 
 import torch
+
+from . import _lib, ops
 
 Tensor = torch.Tensor
 TILE = 16
@@ -23,32 +25,28 @@ def tile_grid(height: int, width: int) -> Tuple[int, int]:
 
 
 def bin_gaussians(xys: Tensor, depths: Tensor, radii: Tensor, height: int, width: int) -> Tuple[Tensor, Tensor]:
-    """Returns ``(gaussian_ids [I] int32 sorted by (tile, depth), tile_bins [tiles, 2] int32)``."""
-    tiles_x, tiles_y = tile_grid(height, width)
+    """Returns ``(gaussian_ids [I] int32 sorted by (tile, depth), tile_bins [tiles, 2] int32)`` (CUDA tensors)."""
+    lib = _lib.load()
+    xys = ops._dev_f32(xys, "xys")
+    depths = ops._dev_f32(depths.reshape(-1), "depths")
+    if radii.dtype != torch.int32 or not radii.is_cuda:
+        raise TypeError("radii must be a CUDA int32 tensor")
+    radii = radii.contiguous()
+    g = xys.shape[0]
     dev = xys.device
-    r = radii.to(torch.float32)
-    cx, cy = xys[:, 0] / TILE, xys[:, 1] / TILE
-    tr = r / TILE
-    # (int) casts truncate toward zero, as the C code does
-    x0 = torch.clamp(torch.trunc(cx - tr).long(), 0, tiles_x)
-    x1 = torch.clamp(torch.trunc(cx + tr + 1).long(), 0, tiles_x)
-    y0 = torch.clamp(torch.trunc(cy - tr).long(), 0, tiles_y)
-    y1 = torch.clamp(torch.trunc(cy + tr + 1).long(), 0, tiles_y)
-    nx, ny = (x1 - x0).clamp(min=0), (y1 - y0).clamp(min=0)
-    hits = torch.where(radii > 0, nx * ny, torch.zeros_like(nx))
-    total = int(hits.sum().item())
-    ids = torch.repeat_interleave(torch.arange(xys.shape[0], device=dev), hits)
-    first = torch.cumsum(hits, 0) - hits
-    local = torch.arange(total, device=dev) - first[ids]
-    w = nx[ids].clamp(min=1)
-    ty = y0[ids] + local // w
-    tx = x0[ids] + local % w
-    tile = ty * tiles_x + tx
-    depth_bits = depths.to(torch.float32).contiguous().view(torch.int32).long()[ids] & 0xFFFFFFFF
-    keys = (tile << 32) | depth_bits
-    order = torch.sort(keys, stable=True).indices
-    sorted_tiles = tile[order]
-    gaussian_ids = ids[order].to(torch.int32)
-    bounds = torch.searchsorted(sorted_tiles, torch.arange(tiles_x * tiles_y + 1, device=dev))
-    tile_bins = torch.stack([bounds[:-1], bounds[1:]], dim=1).to(torch.int32)
-    return gaussian_ids.contiguous(), tile_bins.contiguous()
+    tiles_x, tiles_y = tile_grid(height, width)
+    offsets = torch.empty(g + 1, dtype=torch.int64, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    ws = ops._workspace(lib.ub_bin_count_workspace_bytes(g), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ub_bin_count(xys.data_ptr(), radii.data_ptr(), g, height, width, offsets.data_ptr(),
+                                    total.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream()))
+        n = int(total.item())          # the one host synchronisation of binning: the output size
+        ids = torch.empty(n, dtype=torch.int32, device=dev)
+        bins = torch.empty(tiles_x * tiles_y, 2, dtype=torch.int32, device=dev)
+        ws2 = ops._workspace(lib.ub_bin_gaussians_workspace_bytes(n), dev)
+        _lib.check(lib.ub_bin_gaussians(xys.data_ptr(), depths.data_ptr(), radii.data_ptr(), g, height, width,
+                                        offsets.data_ptr(), n, ids.data_ptr(), bins.data_ptr(), ws2.data_ptr(),
+                                        ws2.numel(), ops._stream()))
+    ops._count(4 + 4 + 24)
+    return ids, bins
