@@ -53,7 +53,9 @@ def parse_args():
 
 def workload_name(h, w, m):
     return (f"configs[1]: {w}x{h} view x {S} samples/ray x {m} active-nerfacto ensemble members -> "
-            f"variance compositing (chunk {CHUNK}) -> per-pixel member mean/variance -> AUSE(mae,mse,rmse)+AUCE+NLL")
+            f"variance compositing (chunk {CHUNK}) -> per-pixel member mean/variance over the 9 image keys "
+            f"(branch A: rgb/depth epistemic+aleatoric variance; the [R,S,1] density pass-through is not reduced) "
+            f"-> AUSE(mae,mse,rmse)+AUCE+NLL")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -122,12 +124,13 @@ class ClockSampler:
 # the reference's CPU torch path (oracle restatement), shared by cpu_baseline and --impl reference
 def cpu_reference_step(members, gt, h, w):
     from oracle import compositing as oc, metrics as om, reduce as orc
+    from uncertainty_nerf_gs_b200.pipeline import PER_SAMPLE_KEYS
 
     outs = []
     for m in members:
         o = oc.render_in_chunks(oc.active_nerfacto_outputs, CHUNK, m["density"], m["deltas"], m["starts"], m["ends"],
                                 m["rgb"], m["beta"])
-        outs.append({k: v.view(h, w, -1) for k, v in o.items()})
+        outs.append({k: v.view(h, w, -1) for k, v in o.items() if k not in PER_SAMPLE_KEYS})  # same keys as the GPU arm
     red = orc.ensemble_reduce(outs) if len(outs) > 1 else outs[0]
     return om.unc_metrics_rgb(red["rgb"], gt, red["rgb_std"], stable=False)  # the reference's literal sort call
 

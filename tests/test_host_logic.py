@@ -111,3 +111,37 @@ def test_synthetic_shapes():
     assert bool((inp["ends"] > inp["starts"]).all())
     p, s, g = synthetic.scoring_image(8, 9)
     assert p.shape == (8, 9, 3) and s.shape == (8, 9, 1) and float(s.min()) == pytest.approx(0.03)
+
+
+def test_batched_host_tails_equal_per_image_numpy():
+    """The [B, 100] tails must give, row by row, what the reference's 1-D numpy expressions give
+    (np.trapz pairwise sums, float32-vs-float64 division of the oracle curve, Python max with NaNs)."""
+    rng = np.random.default_rng(5)
+    ratios = np.linspace(0, 1, 100, endpoint=False)
+    o = (rng.random((6, 100)) * 3).astype(np.float32)
+    v = (rng.random((6, 100)) * 3).astype(np.float32)
+    o[1, 7] = np.nan
+    v[2, 0] = np.nan
+    v[3] = o[3] * 0.5                                  # oracle maximum wins -> float32 division
+    oo, vv, aa = metrics._ause_tail_batch(o, v)
+    for i in range(6):
+        by = np.zeros(100)
+        by[:] = v[i]                                   # ause.py:27-34 keeps this curve in a float64 array
+        a, b = metrics._py_max(o[i]), metrics._py_max(by)
+        mx = b if b > a else a
+        want_o, want_v = np.array(o[i] / mx), np.array(by / mx)
+        assert oo[i].dtype == want_o.dtype
+        assert np.array_equal(oo[i], want_o, equal_nan=True) and np.array_equal(vv[i], want_v, equal_nan=True)
+        assert np.array_equal(aa[i], np.trapz(want_v - want_o, ratios), equal_nan=True)
+    hist = rng.integers(0, 500, (4, 100))
+    n = hist.sum(1).astype(np.float64)
+    ss = rng.random(4) * 1e3
+    z = metrics.z_values_host()
+    rows = metrics._auce_from_hist_batch(hist, ss, n, z)
+    alphas = metrics._alphas()
+    for i in range(4):
+        cov = np.cumsum(hist[i][::-1])[::-1][1:] / n[i]
+        err = cov - (1.0 - np.array(alphas))
+        assert np.array_equal(rows[i]["coverage_values"], cov)
+        assert rows[i]["auc_abs_error_values"] == np.trapz(y=np.abs(err), x=alphas)
+        assert rows[i]["auc_length_values"] == np.trapz(y=list(2.0 * z * (ss[i] / n[i])), x=alphas)

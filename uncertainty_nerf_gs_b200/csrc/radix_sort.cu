@@ -12,7 +12,7 @@
 //   upsweep   : per-tile digit histogram                       -> counts[seg][digit][tile]
 //   scan      : one block per (digit, segment) scans its row of tile counts and records the digit
 //               total; the downsweep turns the 256 totals into digit bases itself
-//   downsweep : stable rank inside the tile (warp match-any multi-split, warp-private counters),
+//   downsweep : stable rank inside the tile (warp multi-split by 8 ballots, warp-private counters),
 //               local reorder through shared memory, run-coalesced scatter.
 // Pass 0 reads the float keys and synthesises the payload (index within the segment); pass 3
 // writes straight into the caller's outputs.  Ping-pong buffers live in the workspace and stay
@@ -115,10 +115,10 @@ __global__ void __launch_bounds__(kSortThreads) sort_scan_rows(const SortPass p)
 }
 
 template <bool WITH_VALS>
-__global__ void __launch_bounds__(kSortThreads) sort_downsweep(const SortPass p) {
+__global__ void __launch_bounds__(kSortThreads, 3) sort_downsweep(const SortPass p) {
   __shared__ uint32_t s_keys[kTile];
   __shared__ int32_t s_vals[WITH_VALS ? kTile : 1];
-  __shared__ uint32_t cnt[kSortWarps][kRadix + 1];
+  __shared__ uint32_t cnt[kSortWarps][kRadix];
   __shared__ uint32_t digit_start[kRadix];
   __shared__ uint32_t gofs[kRadix];
   __shared__ uint32_t scan_tmp[kSortWarps];
@@ -132,23 +132,36 @@ __global__ void __launch_bounds__(kSortThreads) sort_downsweep(const SortPass p)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  for (int i = threadIdx.x; i < kSortWarps * (kRadix + 1); i += kSortThreads) (&cnt[0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&cnt[0][0])[i] = 0u;
 
   // load: warp w owns positions [w*512, (w+1)*512) of the tile, item i of lane l = w*512 + i*32 + l
+  // All 16 loads are issued before the first use (clamped addresses, no branches in between): a load
+  // guarded by its own branch serialises into 16 dependent DRAM round trips.
   uint32_t key[kItems];
   int32_t val[kItems];
-  uint32_t rank[kItems];
+  uint32_t rank2[kItems / 2];  // two 16-bit ranks per register (rank < 4096)
+  const uint32_t* src_keys = p.first_pass ? reinterpret_cast<const uint32_t*>(p.in_float) : p.in_keys;
+  const long long tile_base = seg_lo + tile_lo;
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
     const int pos = warp * (32 * kItems) + i * 32 + lane;
-    if (pos < count) {
-      const long long g = seg_lo + tile_lo + pos;
-      key[i] = load_key(p, g);
-      if (WITH_VALS) val[i] = p.first_pass ? (int32_t)(tile_lo + pos) : p.in_vals[g];
-    } else {
-      key[i] = 0xFFFFFFFFu;
-      if (WITH_VALS) val[i] = 0;
+    key[i] = __ldcs(src_keys + tile_base + min(pos, count - 1));
+  }
+  if (WITH_VALS && !p.first_pass) {
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+      const int pos = warp * (32 * kItems) + i * 32 + lane;
+      val[i] = __ldcs(p.in_vals + tile_base + min(pos, count - 1));
     }
+  }
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) {
+    const int pos = warp * (32 * kItems) + i * 32 + lane;
+    if (p.first_pass) {
+      key[i] = sort_key_from_float(__uint_as_float(key[i]));
+      if (WITH_VALS) val[i] = (int32_t)(tile_lo + pos);
+    }
+    if (pos >= count) key[i] = 0xFFFFFFFFu;
   }
   // global base of every digit for this tile: exclusive scan of the 256 digit totals + row prefix
   {
@@ -162,8 +175,21 @@ __global__ void __launch_bounds__(kSortThreads) sort_downsweep(const SortPass p)
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
     const int pos = warp * (32 * kItems) + i * 32 + lane;
-    const uint32_t d = pos < count ? ((key[i] >> p.shift) & 0xFFu) : (uint32_t)kRadix;
+    // positions past the end carry key 0xFFFFFFFF: digit 255, ranked after every real key (they are the
+    // last positions of the tile), never stored
+    const uint32_t d = (key[i] >> p.shift) & 0xFFu;
+    (void)pos;
+#ifdef UB_SORT_MATCH_ANY
     const unsigned peers = __match_any_sync(FULL_MASK, d);
+#else
+    unsigned peers = FULL_MASK;  // 8 ballots: MATCH.ANY serialises over the distinct values of the warp
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const bool bit = (d >> b) & 1u;
+      const unsigned bal = __ballot_sync(FULL_MASK, bit);
+      peers &= bit ? bal : ~bal;
+    }
+#endif
     const int leader = __ffs(peers) - 1;
     uint32_t old = 0;
     if (lane == leader) {
@@ -171,7 +197,8 @@ __global__ void __launch_bounds__(kSortThreads) sort_downsweep(const SortPass p)
       cnt[warp][d] = old + __popc(peers);
     }
     old = __shfl_sync(FULL_MASK, old, leader);
-    rank[i] = old + __popc(peers & lt_mask);
+    const uint32_t rk = old + __popc(peers & lt_mask);
+    if (i & 1) rank2[i >> 1] |= rk << 16; else rank2[i >> 1] = rk;
     __syncwarp();
   }
   __syncthreads();
@@ -196,7 +223,8 @@ __global__ void __launch_bounds__(kSortThreads) sort_downsweep(const SortPass p)
     const int pos = warp * (32 * kItems) + i * 32 + lane;
     if (pos < count) {
       const uint32_t d = (key[i] >> p.shift) & 0xFFu;
-      const uint32_t dst = digit_start[d] + cnt[warp][d] + rank[i];
+      const uint32_t rk = (i & 1) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xFFFFu);
+      const uint32_t dst = digit_start[d] + cnt[warp][d] + rk;
       s_keys[dst] = key[i];
       if (WITH_VALS) s_vals[dst] = val[i];
     }

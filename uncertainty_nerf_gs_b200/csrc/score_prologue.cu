@@ -8,10 +8,19 @@
 //
 // The 99 coverage passes collapse into one histogram: the interval predicate is monotone in z
 // (z decreasing in k), so every element is characterised by the number c of leading thresholds
-// it satisfies; coverage_k = #{c > k}.  c is located with a float32 estimate and then *verified*
-// with the exact float64 predicate (NumPy >= 2 promotion: np.float64 z * float32 sigma ->
-// float64, no fused multiply-add); if the verification fails the element falls back to an exact
-// float64 binary search, so the counts are bit-exact regardless of the estimate.
+// it satisfies; coverage_k = #{c > k}.  The exact predicate is float64 (NumPy >= 2 promotion:
+// np.float64 z * float32 sigma -> float64, no fused multiply-add).  Evaluating it 99 (or even 7) times
+// per element makes the pass instruction-bound, so c is located in three tiers:
+//   1. r = |t - m| / sigma in float32 (relative error < 1e-6) indexes a shared-memory table over
+//      uniform bins of r, built per block from the z table.  A bin that holds no threshold within a
+//      relative guard band of 1e-5 determines c outright: the float64 outcome cannot differ, because
+//      the estimate error (4e-7 relative) plus the float64 rounding of m -+ z sigma (2^-52 (|m|/sigma
+//      + z) absolute, < 3e-10 once sigma >= 1e-6 |m| is required) is far inside the band (which
+//      also has an absolute part of 1e-9).                                  (~99 % of elements)
+//   2. A bin with exactly one threshold k in the band: c = k + [exact float64 predicate for z_k].
+//   3. Anything else (NaN / negative ratio, tiny sigma, several thresholds per bin): the float32
+//      binary search + float64 verification + exact float64 binary search of coverage_count().
+// The counts are therefore bit-exact whatever the estimate does.
 // Sums are accumulated in float64 per block and combined in a fixed order (deterministic).
 #include "ub_common.cuh"
 
@@ -19,8 +28,16 @@ namespace ub {
 
 constexpr int kPrologueThreads = 256;
 constexpr int kPixPerThread = 4;
-constexpr int kPixPerBlock = kPrologueThreads * kPixPerThread;
+constexpr int kPixPerChunk = kPrologueThreads * kPixPerThread;
+constexpr int kChunksPerBlock = 4;  // amortises the table build
+constexpr int kPixPerBlock = kPixPerChunk * kChunksPerBlock;
 constexpr int kMaxZ = 127;
+constexpr int kLutBins = 8192;            // uniform bins of r over [0, 1.001 z_0)
+constexpr float kLutGuard = 1e-5f;        // relative guard band around every bin (float32 estimate error)
+constexpr double kLutGuardAbs = 1e-9;     // absolute guard band (float64 rounding of m -+ z sigma)
+constexpr float kSigmaGuard = 1e6f;       // tiers 1/2 need sigma >= 1e-6 |m|: 2^-52 (|m|/sigma + z) << 1e-9
+constexpr unsigned kLutOneThreshold = 128u;  // entry = 128 + k: only threshold k is undecided
+constexpr unsigned kLutGeneric = 255u;
 
 struct PrologueParams {
   const float* pred;
@@ -39,6 +56,7 @@ struct PrologueParams {
   double* partial;  // [num_segments][blocks_per_seg][NSUMS]
   int blocks_per_seg;
   unsigned long long* hist;  // [num_segments][num_z + 1]
+  const unsigned char* lut;  // [kLutBins + 16] ratio table (workspace)
   int vec_ok;
 };
 
@@ -51,7 +69,7 @@ __device__ __forceinline__ bool interval_holds(double z, float m, float s, float
 }
 
 // number of leading thresholds (z strictly decreasing) whose interval contains t
-__device__ __forceinline__ int coverage_count(const double* __restrict__ zs_d,
+__device__ __noinline__ int coverage_count(const double* __restrict__ zs_d,
                                               const float* __restrict__ zs_f, int nz, float m,
                                               float s, float t) {
   // float32 estimate: count of z_k >= |t - m| / s
@@ -79,19 +97,58 @@ __device__ __forceinline__ int coverage_count(const double* __restrict__ zs_d,
   return lo;
 }
 
+// Ratio table, built once per call into the workspace: one bin per thread.  z strictly decreasing.
+// Entry for the bin [i w, (i+1) w) widened by the guard bands: see the tiers above.
+__global__ void __launch_bounds__(256) prologue_lut_kernel(const double* __restrict__ z, int nz,
+                                                           unsigned char* __restrict__ lut) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > kLutBins) return;
+  if (i == kLutBins) {  // r >= r_max > z_0 (1 + guard): no threshold holds
+    lut[i] = 0;
+    return;
+  }
+  const double r_max = fmax(z[0] * 1.001, 1e-30);
+  const double bin_w = r_max / kLutBins;
+  const double a = i * bin_w * (1.0 - (double)kLutGuard) - kLutGuardAbs;
+  const double b = (i + 1) * bin_w * (1.0 + (double)kLutGuard) + kLutGuardAbs;
+  int lo = 0, hi = nz;  // above = #{k : z_k > b}
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (z[mid] > b) lo = mid + 1; else hi = mid;
+  }
+  const int above = lo;
+  int inside = 0;
+  while (above + inside < nz && z[above + inside] >= a && inside < 2) ++inside;
+  lut[i] = inside == 0 ? (unsigned char)above
+                       : (inside == 1 ? (unsigned char)(kLutOneThreshold + above) : (unsigned char)kLutGeneric);
+}
+
+// tiers 2 and 3 (rare): one exact check, or the fully general search
+__device__ __noinline__ int coverage_count_slow(unsigned e, const double* __restrict__ zs_d,
+                                                const float* __restrict__ zs_f, int nz, float m, float s,
+                                                float t) {
+  if (e != kLutGeneric) {
+    const int k = (int)(e - kLutOneThreshold);
+    return k + (interval_holds(zs_d[k], m, s, t) ? 1 : 0);
+  }
+  return coverage_count(zs_d, zs_f, nz, m, s, t);
+}
+
 template <int C>
 __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const PrologueParams p) {
   __shared__ double z_d[kMaxZ + 1];
   __shared__ float z_f[kMaxZ + 1];
   __shared__ unsigned int hist_s[kPrologueThreads / 32][kMaxZ + 1];
   __shared__ double red[kPrologueThreads / 32][UB_PROLOGUE_NSUMS];
+  __shared__ __align__(16) unsigned char lut[kLutBins + 16];
 
   const int seg = blockIdx.y;
   const long long seg_lo = p.seg_offsets[seg], seg_hi = p.seg_offsets[seg + 1];
   const long long blk_lo = seg_lo + (long long)blockIdx.x * kPixPerBlock;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nz = p.num_z;
 
-  for (int i = threadIdx.x; i < p.num_z; i += blockDim.x) {
+  for (int i = threadIdx.x; i < nz; i += blockDim.x) {
     z_d[i] = p.z[i];
     z_f[i] = (float)p.z[i];
   }
@@ -99,86 +156,100 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
     (&hist_s[0][0])[i] = 0u;
   __syncthreads();
 
+  const float inv_w = (float)((double)kLutBins / fmax(z_d[0] * 1.001, 1e-30));
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.lut);
+    uint4* dst = reinterpret_cast<uint4*>(lut);
+    for (int i = threadIdx.x; i < (kLutBins + 16) / 16; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+
   double sums[UB_PROLOGUE_NSUMS] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  if (blk_lo < seg_hi) {
-    const long long pix0 = blk_lo + (long long)threadIdx.x * kPixPerThread;
+#pragma unroll 1
+  for (int chunk = 0; chunk < kChunksPerBlock; ++chunk) {
+    const long long pix0 = blk_lo + (long long)chunk * kPixPerChunk + (long long)threadIdx.x * kPixPerThread;
     const int npix = (int)max(0LL, min((long long)kPixPerThread, seg_hi - pix0));
-    if (npix > 0) {
-      float pr[kPixPerThread * C], tg[kPixPerThread * C], sd[kPixPerThread];
-      const bool vec = p.vec_ok && npix == kPixPerThread && (pix0 & 3) == 0;  // 16-byte aligned rows
-      if (vec) {
-        const float4* a = reinterpret_cast<const float4*>(p.pred + pix0 * C);
-        const float4* b = reinterpret_cast<const float4*>(p.target + pix0 * C);
+    if (npix <= 0) continue;
+    float pr[kPixPerThread * C], tg[kPixPerThread * C], sd[kPixPerThread];
+    const bool vec = p.vec_ok && npix == kPixPerThread && (pix0 & 3) == 0;  // 16-byte aligned rows
+    if (vec) {
+      const float4* a = reinterpret_cast<const float4*>(p.pred + pix0 * C);
+      const float4* b = reinterpret_cast<const float4*>(p.target + pix0 * C);
 #pragma unroll
-        for (int j = 0; j < C; ++j) {
-          const float4 x = a[j], y = b[j];
-          pr[4 * j] = x.x; pr[4 * j + 1] = x.y; pr[4 * j + 2] = x.z; pr[4 * j + 3] = x.w;
-          tg[4 * j] = y.x; tg[4 * j + 1] = y.y; tg[4 * j + 2] = y.z; tg[4 * j + 3] = y.w;
-        }
-        const float4 s4 = *reinterpret_cast<const float4*>(p.std + pix0);
-        sd[0] = s4.x; sd[1] = s4.y; sd[2] = s4.z; sd[3] = s4.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < kPixPerThread * C; ++i) {
-          const bool ok = i < npix * C;
-          pr[i] = ok ? p.pred[pix0 * C + i] : 0.f;
-          tg[i] = ok ? p.target[pix0 * C + i] : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < kPixPerThread; ++i) sd[i] = i < npix ? p.std[pix0 + i] : 1.f;
+      for (int j = 0; j < C; ++j) {
+        const float4 x = __ldcs(a + j), y = __ldcs(b + j);
+        pr[4 * j] = x.x; pr[4 * j + 1] = x.y; pr[4 * j + 2] = x.z; pr[4 * j + 3] = x.w;
+        tg[4 * j] = y.x; tg[4 * j + 1] = y.y; tg[4 * j + 2] = y.z; tg[4 * j + 3] = y.w;
       }
-      float se[kPixPerThread], ae[kPixPerThread], vr[kPixPerThread];
+      const float4 s4 = __ldcs(reinterpret_cast<const float4*>(p.std + pix0));
+      sd[0] = s4.x; sd[1] = s4.y; sd[2] = s4.z; sd[3] = s4.w;
+    } else {
 #pragma unroll
-      for (int px = 0; px < kPixPerThread; ++px) {
-        const float sdv = sd[px];
-        const float var = __fmul_rn(sdv, sdv);
-        const float sigma = p.sigma_from_var ? sqrtf(var) : sdv;
-        const float nll_s = fmaxf(sdv, p.nll_min_std);  // torch.maximum propagates NaN:
-        const float s_nll = sdv != sdv ? sdv : nll_s;
-        const float two_var = 2.0f * __fmul_rn(s_nll, s_nll);
-        const float log_s = logf(s_nll);
-        float se_px = 0.f, ae_px = 0.f;
-        double nll_px = 0.0;
+      for (int i = 0; i < kPixPerThread * C; ++i) {
+        const bool ok = i < npix * C;
+        pr[i] = ok ? p.pred[pix0 * C + i] : 0.f;
+        tg[i] = ok ? p.target[pix0 * C + i] : 0.f;
+      }
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float m = pr[px * C + c], t = tg[px * C + c];
-          const float d = m - t;
-          const float d2 = __fmul_rn(d, d);
-          se_px = c == 0 ? d2 : __fadd_rn(se_px, d2);
-          ae_px = c == 0 ? fabsf(d) : __fadd_rn(ae_px, fabsf(d));
-          if (px < npix) {
-            const float dt = t - m;
-            const float nll = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(dt, dt), two_var), log_s),
-                                        0.91893853320467274178f);
-            nll_px += (double)nll;
-            const int cnt = coverage_count(z_d, z_f, p.num_z, m, sigma, t);
-            atomicAdd(&hist_s[warp][cnt], 1u);
-          }
-        }
-        se[px] = se_px;
-        ae[px] = ae_px;
-        vr[px] = var;
+      for (int i = 0; i < kPixPerThread; ++i) sd[i] = i < npix ? p.std[pix0 + i] : 1.f;
+    }
+    float se[kPixPerThread], ae[kPixPerThread], vr[kPixPerThread];
+#pragma unroll
+    for (int px = 0; px < kPixPerThread; ++px) {
+      const float sdv = sd[px];
+      const float var = __fmul_rn(sdv, sdv);
+      const float sigma = p.sigma_from_var ? sqrtf(var) : sdv;
+      const float nll_s = fmaxf(sdv, p.nll_min_std);  // torch.maximum propagates NaN:
+      const float s_nll = sdv != sdv ? sdv : nll_s;
+      const float two_var = 2.0f * __fmul_rn(s_nll, s_nll);
+      const float log_s = logf(s_nll);
+      const float inv_sigma = __fdividef(1.0f, sigma);
+      const float sigma_guard = (sigma > 1e-30f && sigma < 1e30f) ? sigma * kSigmaGuard : -1.f;
+      float se_px = 0.f, ae_px = 0.f;
+      double nll_px = 0.0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float m = pr[px * C + c], t = tg[px * C + c];
+        const float d = m - t;
+        const float d2 = __fmul_rn(d, d);
+        se_px = c == 0 ? d2 : __fadd_rn(se_px, d2);
+        ae_px = c == 0 ? fabsf(d) : __fadd_rn(ae_px, fabsf(d));
         if (px < npix) {
-          sums[0] += (double)se_px;
-          sums[1] += (double)ae_px;
-          sums[2] += (double)var;
-          sums[3] += nll_px;
-          sums[4] += (double)sigma;
+          const float nll = __fadd_rn(__fadd_rn(__fdiv_rn(d2, two_var), log_s), 0.91893853320467274178f);
+          nll_px += (double)nll;
+          // coverage count, tiers 1-3
+          const float r = fabsf(d) * inv_sigma;
+          const unsigned bin = min((unsigned)__float2int_rz(r * inv_w), (unsigned)kLutBins);
+          const unsigned looked_up = lut[bin];
+          const unsigned e = (r >= 0.f && sigma_guard >= fabsf(m)) ? looked_up : kLutGeneric;
+          int cnt = (int)e;
+          if (e >= kLutOneThreshold) cnt = coverage_count_slow(e, z_d, z_f, nz, m, sigma, t);
+          atomicAdd(&hist_s[warp][cnt], 1u);
         }
       }
-      if (vec) {
-        if (p.o_se) *reinterpret_cast<float4*>(p.o_se + pix0) = make_float4(se[0], se[1], se[2], se[3]);
-        if (p.o_ae) *reinterpret_cast<float4*>(p.o_ae + pix0) = make_float4(ae[0], ae[1], ae[2], ae[3]);
-        if (p.o_var) *reinterpret_cast<float4*>(p.o_var + pix0) = make_float4(vr[0], vr[1], vr[2], vr[3]);
-      } else {
-#pragma unroll
-        for (int px = 0; px < kPixPerThread; ++px)
-          if (px < npix) {
-            if (p.o_se) p.o_se[pix0 + px] = se[px];
-            if (p.o_ae) p.o_ae[pix0 + px] = ae[px];
-            if (p.o_var) p.o_var[pix0 + px] = vr[px];
-          }
+      se[px] = se_px;
+      ae[px] = ae_px;
+      vr[px] = var;
+      if (px < npix) {
+        sums[0] += (double)se_px;
+        sums[1] += (double)ae_px;
+        sums[2] += (double)var;
+        sums[3] += nll_px;
+        sums[4] += (double)sigma;
       }
+    }
+    if (vec) {
+      if (p.o_se) *reinterpret_cast<float4*>(p.o_se + pix0) = make_float4(se[0], se[1], se[2], se[3]);
+      if (p.o_ae) *reinterpret_cast<float4*>(p.o_ae + pix0) = make_float4(ae[0], ae[1], ae[2], ae[3]);
+      if (p.o_var) *reinterpret_cast<float4*>(p.o_var + pix0) = make_float4(vr[0], vr[1], vr[2], vr[3]);
+    } else {
+#pragma unroll
+      for (int px = 0; px < kPixPerThread; ++px)
+        if (px < npix) {
+          if (p.o_se) p.o_se[pix0 + px] = se[px];
+          if (p.o_ae) p.o_ae[pix0 + px] = ae[px];
+          if (p.o_var) p.o_var[pix0 + px] = vr[px];
+        }
     }
   }
 
@@ -196,10 +267,10 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
     for (int w = 0; w < kPrologueThreads / 32; ++w) v += red[w][threadIdx.x];
     p.partial[((size_t)seg * p.blocks_per_seg + blockIdx.x) * UB_PROLOGUE_NSUMS + threadIdx.x] = v;
   }
-  for (int c = threadIdx.x; c <= p.num_z; c += blockDim.x) {
+  for (int c = threadIdx.x; c <= nz; c += blockDim.x) {
     unsigned int v = 0;
     for (int w = 0; w < kPrologueThreads / 32; ++w) v += hist_s[w][c];
-    if (v) atomicAdd(&p.hist[(size_t)seg * (p.num_z + 1) + c], (unsigned long long)v);
+    if (v) atomicAdd(&p.hist[(size_t)seg * (nz + 1) + c], (unsigned long long)v);
   }
 }
 
@@ -218,7 +289,7 @@ __global__ void prologue_finalize_kernel(const double* partial, int blocks_per_s
 }
 
 struct PrologueLayout {
-  size_t off_offsets, off_partial, total;
+  size_t off_offsets, off_partial, off_lut, total;
   int blocks_per_seg;
 };
 static PrologueLayout prologue_layout(int num_segments, long long max_len) {
@@ -227,7 +298,8 @@ static PrologueLayout prologue_layout(int num_segments, long long max_len) {
   if (l.blocks_per_seg < 1) l.blocks_per_seg = 1;
   l.off_offsets = 0;
   l.off_partial = align_up((size_t)(num_segments + 1) * sizeof(long long), 256);
-  l.total = l.off_partial + (size_t)num_segments * l.blocks_per_seg * UB_PROLOGUE_NSUMS * sizeof(double);
+  l.off_lut = align_up(l.off_partial + (size_t)num_segments * l.blocks_per_seg * UB_PROLOGUE_NSUMS * sizeof(double), 256);
+  l.total = l.off_lut + kLutBins + 16;
   return l;
 }
 
@@ -282,6 +354,9 @@ int ub_score_prologue(const ub_score_prologue_args* a, void* workspace, size_t w
   p.partial = reinterpret_cast<double*>(ws + lay.off_partial);
   p.blocks_per_seg = lay.blocks_per_seg;
   p.hist = reinterpret_cast<unsigned long long*>(a->out_hist);
+  unsigned char* lut = reinterpret_cast<unsigned char*>(ws + lay.off_lut);
+  p.lut = lut;
+  prologue_lut_kernel<<<(kLutBins + 1 + 255) / 256, 256, 0, stream>>>(a->z_values, a->num_z, lut);
   auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   bool vec_ok = al16(a->pred) && al16(a->target) && al16(a->std) && al16(a->out_sq_err) &&
                 al16(a->out_abs_err) && al16(a->out_var);

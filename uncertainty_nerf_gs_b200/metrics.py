@@ -28,8 +28,12 @@ if not hasattr(np, "trapz"):  # newer NumPy dropped the alias the reference call
 _Z_CACHE: Dict[str, Tensor] = {}
 
 
+_RATIOS = np.linspace(0, 1, 100, endpoint=False)  # ause.py:8
+_RATIOS.setflags(write=False)
+
+
 def _ratios() -> np.ndarray:
-    return np.linspace(0, 1, 100, endpoint=False)  # ause.py:8
+    return _RATIOS
 
 
 def ause_cut_counts(n: int) -> np.ndarray:
@@ -93,18 +97,40 @@ def _py_max(arr: np.ndarray):
     return best
 
 
+def _py_max_rows(arr: np.ndarray) -> np.ndarray:
+    """``_py_max`` of every row of ``arr [B, n]``."""
+    out = arr.max(axis=1)
+    bad = np.isnan(out)
+    for i in np.nonzero(bad)[0]:
+        out[i] = _py_max(arr[i])
+    return out
+
+
+def _ause_tail_batch(oracle_f32: np.ndarray, by_unc_f32: np.ndarray):
+    """ause.py:27-44 downstream of the slice means for ``[B, 100]`` curves at once: normalise both curves by
+    the common maximum and integrate the gap.  dtypes follow the reference row by row: the oracle curve is
+    built from float32 scalars, the by-uncertainty curve lives in a float64 array, and ``max(a, b)`` keeps
+    ``a`` (np.float32) unless ``b > a`` (np.float64) -- which decides whether the oracle curve is divided in
+    float32 or float64.  Returns ``(oracle_curves list, by_unc_curves [B,100] f64, ause [B] f64)``."""
+    by_unc = by_unc_f32.astype(np.float64)
+    a = _py_max_rows(oracle_f32)                      # float32
+    b = _py_max_rows(by_unc)                          # float64
+    b_wins = b > a
+    with np.errstate(divide="ignore", invalid="ignore"):
+        max64 = np.where(b_wins, b, a.astype(np.float64))
+        oracle32 = oracle_f32 / a[:, None]                                    # float32 / np.float32
+        oracle64 = oracle_f32.astype(np.float64) / max64[:, None]             # float32 / np.float64 -> float64
+        by_unc = by_unc / max64[:, None]
+        gap = by_unc - np.where(b_wins[:, None], oracle64, oracle32.astype(np.float64))
+        ause_vals = np.trapz(gap, _RATIOS, axis=-1)
+    oracle = [oracle64[i] if b_wins[i] else oracle32[i] for i in range(len(a))]
+    return oracle, by_unc, ause_vals
+
+
 def _ause_tail(oracle_f32: np.ndarray, by_unc_f32: np.ndarray):
-    """ause.py:27-44 downstream of the slice means: normalise both curves by the common maximum and
-    integrate the gap.  dtypes follow the reference: the oracle curve is built from float32 scalars, the
-    by-uncertainty curve lives in a float64 array, and ``max(a, b)`` keeps ``a`` unless ``b > a``."""
-    ratios = _ratios()
-    by_unc = np.zeros(len(ratios))
-    by_unc[:] = by_unc_f32
-    a, b = _py_max(oracle_f32), _py_max(by_unc)
-    max_val = b if b > a else a
-    oracle_curve = np.array(oracle_f32 / max_val)
-    by_unc = np.array(by_unc / max_val)
-    return ratios, oracle_curve, by_unc, np.trapz(by_unc - oracle_curve, ratios)
+    """Single-curve form of ``_ause_tail_batch`` with the reference's return tuple."""
+    o, b, a = _ause_tail_batch(np.asarray(oracle_f32)[None], np.asarray(by_unc_f32)[None])
+    return _RATIOS, o[0], b[0], a[0]
 
 
 def _check_err_type(err_type: str) -> None:
@@ -128,28 +154,43 @@ def ause(unc_vec: Tensor, err_vec: Tensor, err_type: str = "rmse"
     return _ause_tail(_prefix_means(host[0], cuts, err_type), _prefix_means(host[1], cuts, err_type))
 
 
-def _auce_from_hist(hist: np.ndarray, sigma_sum: float, n: float, z: np.ndarray) -> Dict[str, object]:
-    """auce.py:24-54 from the interval histogram: coverage_k = #{elements satisfying > k thresholds} / n;
-    mean interval length = 2 z_k mean(sigma) (equal to the reference's float64 ``mean(upper - lower)`` to
-    ~2e-16 relative)."""
-    alphas = _alphas()
-    inside = (np.cumsum(hist[::-1])[::-1])[1:]  # count with c > k, k = 0..nz-1
-    coverage_values = inside.astype(np.float64) / n
-    avg_length_values = 2.0 * z * (sigma_sum / n)
-    auc_length = np.trapz(y=list(avg_length_values), x=alphas)
-    err = np.array(coverage_values) - (1.0 - np.array(alphas))
+_ALPHA_ARR: Optional[np.ndarray] = None
+_ONE_MINUS_ALPHA: Optional[np.ndarray] = None
+
+
+def _auce_from_hist_batch(hist: np.ndarray, sigma_sum: np.ndarray, n: np.ndarray, z: np.ndarray) -> List[Dict[str, object]]:
+    """auce.py:24-54 from the interval histograms ``hist [B, nz+1]``: coverage_k = #{elements satisfying > k
+    thresholds} / n; mean interval length = 2 z_k mean(sigma) (equal to the reference's float64
+    ``mean(upper - lower)`` to ~2e-16 relative).  ``sigma_sum, n``: per-image float64."""
+    global _ALPHA_ARR, _ONE_MINUS_ALPHA
+    if _ALPHA_ARR is None:
+        _ALPHA_ARR = np.array(_alphas())
+        _ONE_MINUS_ALPHA = 1.0 - _ALPHA_ARR
+    inside = np.cumsum(hist[:, ::-1], axis=1)[:, ::-1][:, 1:]  # count with c > k, k = 0..nz-1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        coverage = inside.astype(np.float64) / n[:, None]
+        avg_len = (2.0 * z)[None, :] * (sigma_sum / n)[:, None]
+    err = coverage - _ONE_MINUS_ALPHA
     abs_err = np.abs(err)
-    neg_err = (np.abs(err) - err) / 2.0
-    return {
-        "coverage_values": np.array(coverage_values),
-        "avg_length_values": np.array(avg_length_values),
-        "coverage_error_values": np.array(err),
-        "abs_coverage_error_values": abs_err,
-        "neg_coverage_error_values": neg_err,
-        "auc_abs_error_values": np.trapz(y=abs_err, x=alphas),
-        "auc_length_values": auc_length,
-        "auc_neg_error_values": np.trapz(y=neg_err, x=alphas),
-    }
+    neg_err = (abs_err - err) / 2.0
+    auc_len = np.trapz(avg_len, _ALPHA_ARR, axis=-1)
+    auc_abs = np.trapz(abs_err, _ALPHA_ARR, axis=-1)
+    auc_neg = np.trapz(neg_err, _ALPHA_ARR, axis=-1)
+    return [{
+        "coverage_values": coverage[i],
+        "avg_length_values": avg_len[i],
+        "coverage_error_values": err[i],
+        "abs_coverage_error_values": abs_err[i],
+        "neg_coverage_error_values": neg_err[i],
+        "auc_abs_error_values": auc_abs[i],
+        "auc_length_values": auc_len[i],
+        "auc_neg_error_values": auc_neg[i],
+    } for i in range(hist.shape[0])]
+
+
+def _auce_from_hist(hist: np.ndarray, sigma_sum: float, n: float, z: np.ndarray) -> Dict[str, object]:
+    return _auce_from_hist_batch(np.asarray(hist)[None], np.array([sigma_sum], dtype=np.float64),
+                                 np.array([n], dtype=np.float64), z)[0]
 
 
 ArrayLike = Union[np.ndarray, Tensor]
@@ -231,23 +272,28 @@ class PendingScores:
         packed = self.packed_host.numpy()
         b, n, c, cuts_one = self.b, self.n, self.c, self.cuts_one
         zh = z_values_host()
+        bu_ae, bu_se, or_ae, or_se = packed[:, 0:100], packed[:, 100:200], packed[:, 200:300], packed[:, 300:400]
+        psums = packed[:, 400:405]
+        hist = np.rint(packed[:, 405:405 + len(zh) + 1]).astype(np.int64)
+        tails = {
+            "mae": _ause_tail_batch(_prefix_means(or_ae, cuts_one, "mae"), _prefix_means(bu_ae, cuts_one, "mae")),
+            "mse": _ause_tail_batch(_prefix_means(or_se, cuts_one, "mse"), _prefix_means(bu_se, cuts_one, "mse")),
+            "rmse": _ause_tail_batch(_prefix_means(or_se, cuts_one, "rmse"), _prefix_means(bu_se, cuts_one, "rmse")),
+        }
+        nll = (psums[:, 3] / (n * c)).astype(np.float32)
+        avg_var = (psums[:, 2] / n).astype(np.float32)
+        mse_mean = (psums[:, 0] / n).astype(np.float32)
+        auce_rows = _auce_from_hist_batch(hist, psums[:, 4] * c, np.full(b, float(n * c)), zh)
         results = []
         for i in range(b):
-            row = packed[i]
-            bu_ae, bu_se, or_ae, or_se = row[0:100], row[100:200], row[200:300], row[300:400]
-            psums = row[400:405]
-            hist = np.rint(row[405:405 + len(zh) + 1]).astype(np.int64)
             d: Dict[str, object] = {}
-            _, d["err_mae"], d["err_var_mae"], d["ause_mae"] = _ause_tail(
-                _prefix_means(or_ae, cuts_one, "mae"), _prefix_means(bu_ae, cuts_one, "mae"))
-            _, d["err_mse"], d["err_var_mse"], d["ause_mse"] = _ause_tail(
-                _prefix_means(or_se, cuts_one, "mse"), _prefix_means(bu_se, cuts_one, "mse"))
-            _, d["err_rmse"], d["err_var_rmse"], d["ause_rmse"] = _ause_tail(
-                _prefix_means(or_se, cuts_one, "rmse"), _prefix_means(bu_se, cuts_one, "rmse"))
-            d["nll_rgb"] = float(np.float32(psums[3] / (n * c)))
-            d["avg_var"] = float(np.float32(psums[2] / n))
-            d["mse_mean"] = float(np.float32(psums[0] / n))
-            d.update(_auce_from_hist(hist, float(psums[4]) * c, float(n * c), zh))
+            for et in ("mae", "mse", "rmse"):
+                o, v, a = tails[et]
+                d[f"err_{et}"], d[f"err_var_{et}"], d[f"ause_{et}"] = o[i], v[i], a[i]
+            d["nll_rgb"] = float(nll[i])
+            d["avg_var"] = float(avg_var[i])
+            d["mse_mean"] = float(mse_mean[i])
+            d.update(auce_rows[i])
             results.append(d)
         return results
 

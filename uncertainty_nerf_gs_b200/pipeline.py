@@ -19,6 +19,13 @@ from .models import outputs as mo
 Tensor = torch.Tensor
 
 RAY_KEYS = ("density", "deltas", "starts", "ends", "rgb", "beta")
+# Member outputs that are per *sample*, not per pixel.  The reference's ensemble loop averages them too
+# (ensemble_pipeline.py:160-162 runs over every key), but the scorer never reads them
+# (eval_uncertainty.py:316-322, 427-428) and SURVEY.md section 8(d) config 2 lists only the image keys, so
+# the evaluation driver leaves them out of the member reduce: averaging the [H, W, 48] density pass-through
+# alone would move 4.6x the bytes of all nine image keys together.  ``models.outputs.ensemble_reduce`` itself
+# (the drop-in for the pipeline method) still reduces whatever keys it is given.
+PER_SAMPLE_KEYS = ("density",)
 
 # layout of the per-view float64 record that crosses GPUs
 CURVE_KEYS_100 = ("err_mae", "err_mse", "err_rmse", "err_var_mae", "err_var_mse", "err_var_rmse")
@@ -30,10 +37,11 @@ RECORD_LEN = 100 * len(CURVE_KEYS_100) + 99 * len(CURVE_KEYS_99) + len(SCALAR_KE
 
 
 def render_members(members: Sequence[Dict[str, Tensor]], height: int, width: int, rays_per_chunk: int,
-                   timers: Optional[List[Tuple[torch.cuda.Event, torch.cuda.Event]]] = None
-                   ) -> List[Dict[str, Tensor]]:
+                   timers: Optional[List[Tuple[torch.cuda.Event, torch.cuda.Event]]] = None,
+                   keep_per_sample: bool = False) -> List[Dict[str, Tensor]]:
     """Composite every member's ray samples (active-nerfacto ``get_outputs`` per eval chunk) and view the
-    per-ray outputs as ``[H, W, C]`` like ``get_outputs_for_camera`` does."""
+    per-ray outputs as ``[H, W, C]`` like ``get_outputs_for_camera`` does.  Per-sample pass-through keys
+    (``PER_SAMPLE_KEYS``) are dropped unless ``keep_per_sample``."""
     outs = []
     for m in members:
         if timers is not None:
@@ -44,7 +52,8 @@ def render_members(members: Sequence[Dict[str, Tensor]], height: int, width: int
         if timers is not None:
             t1.record()
             timers.append((t0, t1))
-        outs.append({k: v.view(height, width, -1) for k, v in o.items()})
+        outs.append({k: v.view(height, width, -1) for k, v in o.items()
+                     if keep_per_sample or k not in PER_SAMPLE_KEYS})
     return outs
 
 
@@ -118,7 +127,7 @@ class HostViewEvaluator:
             main.wait_event(ev)
             o = mo.active_nerfacto_outputs(slot["density"], slot["deltas"], slot["starts"], slot["ends"], slot["rgb"],
                                            slot["beta"], rays_per_chunk=rays_per_chunk)
-            outs.append({k: v.view(self.h, self.w, -1) for k, v in o.items()})
+            outs.append({k: v.view(self.h, self.w, -1) for k, v in o.items() if k not in PER_SAMPLE_KEYS})
         red = mo.ensemble_reduce(outs) if len(outs) > 1 else outs[0]
         main.wait_stream(self.copy_stream)
         d = metrics.score_rgb_batch(red["rgb"], self.gt_dev, red["rgb_std"])[0]
