@@ -341,6 +341,22 @@ int ub_splat_depth_residual(const float* xys, const float* depths, const float* 
                             float* out_sq_residual, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (f1) Backward of ub_composite_tiles_planes, for training through the fused pass (the reference's losses,
+ * activesplatfacto_model.py:369-441, read outputs["rgb"] and outputs["uncertainty"]; gsplat supplies this
+ * gradient inside rasterize_gaussians' autograd function).
+ * Inputs as the forward call, plus v_outs_host[p] = dL/d(out plane p) [H,W,ch_p] (NULL: zero) and
+ * v_alpha = dL/d(alpha) [H,W] (NULL: zero).  Outputs (zeroed here, then accumulated with float32 atomics):
+ * v_xys [G,2], v_conics [G,3], v_opacities [G], v_planes_host[p] [G,ch_p] (NULL: not wanted).
+ * ---------------------------------------------------------------------------------------- */
+int ub_composite_tiles_planes_backward(const float* xys, const float* conics, const float* opacities,
+                                       const float* const* planes_host, const int32_t* plane_channels_host,
+                                       int32_t num_planes, const int32_t* gaussian_ids, const int32_t* tile_bins,
+                                       int32_t img_height, int32_t img_width, const float* background_host,
+                                       const float* const* v_outs_host, const float* v_alpha,
+                                       int64_t num_gaussians, float* v_xys, float* v_conics, float* v_opacities,
+                                       float* const* v_planes_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * (f2) Tile binning of projected Gaussians (setup step; the compositing above takes its outputs).
  * Replaces what gsplat does inside every rasterize_gaussians call of activesplatfacto_model.py:260-355
  * (tile rectangle = centre +- radius in tile units, (tile << 32 | depth) keys, stable sort, tile ranges).

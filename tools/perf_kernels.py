@@ -93,6 +93,12 @@ def splat():
     planes = [sc["rgbs"], sc["betas"], sc["depths"][:, None].contiguous()]
     ms5 = timeit(lambda i: ops.composite_tiles_planes(sc["xys"], sc["conics"], sc["opacities"], planes, ids, bins, H, W), iters=10)
     ms3 = timeit(lambda i: ops.composite_tiles(sc["xys"], sc["conics"], sc["opacities"], sc["rgbs"], ids, bins, H, W), iters=10)
+    v_rgb = torch.randn(H, W, 3, device=dev); v_beta = torch.randn(H, W, 1, device=dev)
+    msbw = timeit(lambda i: ops.composite_tiles_planes_backward(sc["xys"], sc["conics"], sc["opacities"],
+                                                                [sc["rgbs"], sc["betas"]], ids, bins, H, W, [0.1, 0.2, 0.3, 0.0],
+                                                                [v_rgb, v_beta], None), iters=5)
+    ms4 = timeit(lambda i: ops.composite_tiles_planes(sc["xys"], sc["conics"], sc["opacities"], [sc["rgbs"], sc["betas"]], ids, bins, H, W), iters=10)
+    print(json.dumps({"kernel": "composite_tiles backward (rgb+beta planes, 4 ch)", "ms_backward": msbw, "ms_forward_4ch": ms4}))
     bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
     bgl = [0.1, 0.2, 0.3]
     class _BG:  # avoid the device->host sync of background.tolist() inside the timed loop

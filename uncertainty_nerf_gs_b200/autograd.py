@@ -77,3 +77,37 @@ def composite_rays_train(density: Tensor, deltas: Tensor, starts: Tensor, ends: 
             "expected_depth": out["expected_depth"], "density": density, "rgb_var": out["rgb_var"],
             "rgb_std": out["rgb_std"], "depth_var": out["depth_var"], "depth_std": out["depth_std"],
             "weights": out["weights"]}
+
+
+class _CompositeTilesFn(torch.autograd.Function):
+    """``ub_composite_tiles_planes`` / ``..._backward`` as one differentiable op.  ``args`` = the colour planes."""
+
+    @staticmethod
+    def forward(ctx, xys, conics, opacities, gaussian_ids, tile_bins, height, width, background, *planes):
+        outs, alpha, _ = ops.composite_tiles_planes(xys, conics, opacities, planes, gaussian_ids, tile_bins,
+                                                    height, width, background)
+        ctx.height, ctx.width, ctx.background = height, width, background
+        ctx.save_for_backward(xys, conics, opacities, gaussian_ids, tile_bins, *planes)
+        return (*outs, alpha)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        xys, conics, opacities, gaussian_ids, tile_bins, *planes = ctx.saved_tensors
+        v_outs, v_alpha = grads[:-1], grads[-1]
+        want = list(ctx.needs_input_grad[8:])
+        v_xys, v_conics, v_opac, v_pl = ops.composite_tiles_planes_backward(
+            xys, conics, opacities, planes, gaussian_ids, tile_bins, ctx.height, ctx.width, ctx.background,
+            v_outs, v_alpha, want)
+        v_pl = [None if v is None else v.view_as(p) for v, p in zip(v_pl, planes)]
+        return (v_xys, v_conics, v_opac.view_as(opacities), None, None, None, None, None, *v_pl)
+
+
+def composite_tiles_train(xys: Tensor, conics: Tensor, opacities: Tensor, planes: Sequence[Tensor],
+                          gaussian_ids: Tensor, tile_bins: Tensor, height: int, width: int,
+                          background: Optional[Sequence[float]] = None):
+    """Differentiable fused tile compositing: ``([H, W, c_p] per colour plane, alpha [H, W, 1])`` with gradients
+    to ``xys``, ``conics``, ``opacities`` and every plane -- the role gsplat's ``rasterize_gaussians`` autograd
+    function plays in the reference (activesplatfacto_model.py:260-301), all planes in one pass each way."""
+    res = _CompositeTilesFn.apply(xys, conics, opacities, gaussian_ids, tile_bins, height, width,
+                                  None if background is None else [float(v) for v in background], *planes)
+    return list(res[:-1]), res[-1]

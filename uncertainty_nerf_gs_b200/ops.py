@@ -496,6 +496,42 @@ def composite_tiles_planes(xys: Tensor, conics: Tensor, opacities: Tensor, plane
     return outs, alpha, keys
 
 
+def composite_tiles_planes_backward(xys: Tensor, conics: Tensor, opacities: Tensor, planes: Sequence[Tensor],
+                                    gaussian_ids: Tensor, tile_bins: Tensor, height: int, width: int,
+                                    background: Optional[Sequence[float]], v_outs: Sequence[Optional[Tensor]],
+                                    v_alpha: Optional[Tensor], want_plane_grads: Optional[Sequence[bool]] = None
+                                    ) -> Tuple[Tensor, Tensor, Tensor, List[Optional[Tensor]]]:
+    """Gradients of ``composite_tiles_planes`` -> ``(v_xys [G,2], v_conics [G,3], v_opacities [G], [v_plane_p])``."""
+    lib = _lib.load()
+    xys, conics = _dev_f32(xys, "xys"), _dev_f32(conics, "conics")
+    opacities = _dev_f32(opacities.reshape(-1), "opacities")
+    g = xys.shape[0]
+    dev = xys.device
+    pls = [_dev_f32(p.reshape(g, -1), f"planes[{i}]") for i, p in enumerate(planes)]
+    chs = [int(p.shape[1]) for p in pls]
+    total = sum(chs)
+    vos = [None if v is None else _dev_f32(v.reshape(height, width, c), f"v_outs[{i}]")
+           for i, (v, c) in enumerate(zip(v_outs, chs))]
+    va = None if v_alpha is None else _dev_f32(v_alpha.reshape(height, width), "v_alpha")
+    want = [True] * len(pls) if want_plane_grads is None else list(want_plane_grads)
+    v_xys = torch.empty(g, 2, device=dev)
+    v_conics = torch.empty(g, 3, device=dev)
+    v_opac = torch.empty(g, device=dev)
+    v_pl = [torch.empty(g, c, device=dev) if w else None for c, w in zip(chs, want)]
+    bg = (C.c_float * total)(*([0.0] * total if background is None else [float(v) for v in background]))
+    pp = (C.c_void_p * len(pls))(*[p.data_ptr() for p in pls])
+    pc = (C.c_int32 * len(pls))(*chs)
+    pv = (C.c_void_p * len(pls))(*[_ptr(v) for v in vos])
+    pg = (C.c_void_p * len(pls))(*[_ptr(v) for v in v_pl])
+    with torch.cuda.device(dev):
+        _lib.check(lib.ub_composite_tiles_planes_backward(
+            xys.data_ptr(), conics.data_ptr(), opacities.data_ptr(), pp, pc, len(pls),
+            _ptr(gaussian_ids.contiguous()), tile_bins.contiguous().data_ptr(), height, width, bg, pv, _ptr(va), g,
+            v_xys.data_ptr(), v_conics.data_ptr(), v_opac.data_ptr(), pg, _stream()))
+    _count(1)
+    return v_xys, v_conics, v_opac, v_pl
+
+
 def splat_normalize_(image: Tensor, alpha: Optional[Tensor] = None, max_key: Optional[Tensor] = None,
                      clamp_max_one: bool = False) -> Tensor:
     """In place: ``min(image, 1)`` and / or ``alpha > 0 ? image / alpha : max`` (activesplatfacto_model.py:275,319)."""
