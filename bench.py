@@ -244,11 +244,14 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def finish(pending):
-        rec = pipeline.pack_record(view_id, pending.finish())[None, :]
+        return pipeline.pack_record(view_id, pending.finish())[None, :]
+
+    def gather(local_records):      # the path's one exchange: fixed-size records of all ranks' views, once
+        rec = np.concatenate(local_records, axis=0)
         return pipeline.gather_records(rec, dev) if world > 1 else rec
 
     def step(timers=None):          # synchronous form (warm-up)
-        return finish(pipeline.evaluate_view_async(members, gt, h, w, CHUNK, timers=timers))
+        return gather([finish(pipeline.evaluate_view_async(members, gt, h, w, CHUNK, timers=timers))])
 
     for _ in range(warmup):
         step()
@@ -259,15 +262,16 @@ def run_ours(args, rank, world, local_rank):
     with ClockSampler(local_rank) as clocks:
         torch.cuda.profiler.start()  # no-op unless run under `ncu --profile-from-start off`
         ev0.record()
-        # stream of views: view i+1 is enqueued before view i's record is read back (K views in, K records
-        # out inside the timed region; the last record is collected before the closing barrier)
-        pending = None
+        # stream of views: view i+1 is enqueued before view i's record is read back; the K records of every
+        # rank are exchanged by ONE all_gather at the end of the stream, inside the timed region
+        pending, local = None, []
         for _ in range(steps):
             nxt = pipeline.evaluate_view_async(members, gt, h, w, CHUNK, timers=timers)
             if pending is not None:
-                records = finish(pending)
+                local.append(finish(pending))
             pending = nxt
-        records = finish(pending)
+        local.append(finish(pending))
+        records = gather(local)
         ev1.record()
         barrier()
         torch.cuda.profiler.stop()
@@ -296,6 +300,29 @@ def run_ours(args, rank, world, local_rank):
     s1.record()
     torch.cuda.synchronize()
     score_ms = s0.elapsed_time(s1) / score_steps
+    # the same, streamed like the step above (image i+1 enqueued before image i's record is read back) ...
+    s0.record()
+    pend = None
+    for _ in range(score_steps):
+        nxt = metrics.score_rgb_batch_async(pred_img["rgb"], gt, pred_img["rgb_std"])
+        if pend is not None:
+            pend.finish()
+        pend = nxt
+    pend.finish()
+    s1.record()
+    torch.cuda.synchronize()
+    score_stream_ms = s0.elapsed_time(s1) / score_steps
+    # ... and with 8 views per call (one set of segmented launches)
+    b8 = 8
+    p8, g8, s8 = (t[None].expand(b8, *t.shape).contiguous() for t in (pred_img["rgb"], gt, pred_img["rgb_std"]))
+    metrics.score_rgb_batch(p8, g8, s8)
+    s0.record()
+    for _ in range(max(3, score_steps // 4)):
+        metrics.score_rgb_batch(p8, g8, s8)
+    s1.record()
+    torch.cuda.synchronize()
+    score_b8_ms = s0.elapsed_time(s1) / max(3, score_steps // 4) / b8
+    del p8, g8, s8
 
     # ---- end to end: pinned host inputs -> H2D -> pipeline -> D2H record ----
     e2e = None
@@ -344,8 +371,11 @@ def run_ours(args, rank, world, local_rank):
                    "views_per_step": world, "l2": f"inputs {m * R * 1536 / 1e9:.1f} GB per step >> 126 MB L2, no flush needed",
                    "parallelism": f"view-sharded x{world}, all_gather of {pipeline.RECORD_LEN * 8} B records"},
         "images_per_s": world / (ms_per_step * 1e-3),
-        "ause_auce_images_per_s": world / (score_ms * 1e-3),
-        "ause_auce_ms_per_image": score_ms,
+        "ause_auce_images_per_s": world / (score_stream_ms * 1e-3),
+        "ause_auce_ms_per_image": score_stream_ms,
+        "ause_auce_detail": {"streamed_one_view_per_call_ms": score_stream_ms, "synchronous_one_view_per_call_ms": score_ms,
+                             "eight_views_per_call_ms_per_image": score_b8_ms,
+                             "images_per_s_eight_views_per_call": world / (score_b8_ms * 1e-3)},
         "roofline": {"kernel": "ub_composite_rays (memset + composite_rays_tma<48> + composite_finalize)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
