@@ -357,6 +357,25 @@ int ub_composite_tiles_planes_backward(const float* xys, const float* conics, co
                                        float* const* v_planes_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (f2) Producers of the splat path: EWA projection and view-dependent colours.  Replace gsplat's
+ * project_gaussians (activesplatfacto_model.py:221-234) and spherical_harmonics (:242-249), forward only (eval).
+ *   means3d [G,3], scales [G,3] (already exp'ed), quats [G,4] (w,x,y,z; normalised inside),
+ *   viewmat: DEVICE pointer to the [3,4] row-major world->camera matrix, clip_thresh: near plane (gsplat: 0.01).
+ *   Outputs: xys [G,2], depths [G], radii [G] int32, conics [G,3]; optional (may be NULL): compensation [G],
+ *   num_tiles_hit [G] int32, cov3d [G,6].  Culled Gaussians (behind the near plane, zero determinant, no tile)
+ *   get radius 0 and zeros.
+ *   ub_spherical_harmonics: degree in [0,3] gives the coefficient layout coeffs [G,(degree+1)^2,3]; the first
+ *   (degrees_to_use+1)^2 bases are evaluated at viewdirs [G,3] (normalised inside) -> out_colors [G,3].
+ * ---------------------------------------------------------------------------------------- */
+int ub_project_gaussians(const float* means3d, const float* scales, float glob_scale, const float* quats,
+                         const float* viewmat, float fx, float fy, float cx, float cy, int32_t img_height,
+                         int32_t img_width, float clip_thresh, int64_t num_gaussians, float* out_xys,
+                         float* out_depths, int32_t* out_radii, float* out_conics, float* out_compensation,
+                         int32_t* out_num_tiles_hit, float* out_cov3d, void* stream);
+int ub_spherical_harmonics(int32_t degree, int32_t degrees_to_use, const float* viewdirs, const float* coeffs,
+                           int64_t num_gaussians, float* out_colors, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * (f2) Tile binning of projected Gaussians (setup step; the compositing above takes its outputs).
  * Replaces what gsplat does inside every rasterize_gaussians call of activesplatfacto_model.py:260-355
  * (tile rectangle = centre +- radius in tile units, (tile << 32 | depth) keys, stable sort, tile ranges).

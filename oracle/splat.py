@@ -59,6 +59,98 @@ def bin_gaussians(xys: Tensor, depths: Tensor, radii: Tensor, height: int, width
 
 
 
+def project_gaussians(means3d: Tensor, scales: Tensor, glob_scale: float, quats: Tensor, viewmat: Tensor, fx: float,
+                      fy: float, cx: float, cy: float, height: int, width: int, clip_thresh: float = 0.01
+                      ) -> Dict[str, Tensor]:
+    """gsplat 0.1.11 ``project_gaussians`` (published algorithm; call site activesplatfacto_model.py:221-234):
+    ``xys, depths, radii, conics, compensation, num_tiles_hit, cov3d`` plus ``radius_real`` (the value before
+    ``ceil``, for tests that must tolerate a one-ulp difference at an integer boundary).  ``viewmat [3,4]``."""
+    f32 = torch.float32
+    means3d, scales, quats, viewmat = (t.to(f32) for t in (means3d, scales, quats, viewmat))
+    g = means3d.shape[0]
+    Wm, tvec = viewmat[:3, :3], viewmat[:3, 3]
+    p_view = means3d @ Wm.T + tvec
+    keep = ~(p_view[:, 2] <= clip_thresh)
+    q = quats / quats.norm(dim=-1, keepdim=True)
+    w, x, y, z = q.unbind(-1)
+    R = torch.stack([
+        torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], -1),
+        torch.stack([2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)], -1),
+        torch.stack([2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], -1)], -2)
+    M = R * (glob_scale * scales)[:, None, :]
+    V = M @ M.transpose(1, 2)
+    cov3d = torch.stack([V[:, 0, 0], V[:, 0, 1], V[:, 0, 2], V[:, 1, 1], V[:, 1, 2], V[:, 2, 2]], -1)
+    lim_x, lim_y = 1.3 * (0.5 * width / fx), 1.3 * (0.5 * height / fy)
+    tz = p_view[:, 2]
+    tx = tz * torch.clamp(p_view[:, 0] / tz, -lim_x, lim_x)
+    ty = tz * torch.clamp(p_view[:, 1] / tz, -lim_y, lim_y)
+    rz = 1.0 / tz
+    zero = torch.zeros_like(tz)
+    J = torch.stack([torch.stack([fx * rz, zero, -fx * tx * rz * rz], -1),
+                     torch.stack([zero, fy * rz, -fy * ty * rz * rz], -1)], -2)          # [G, 2, 3]
+    T = J @ Wm
+    cov = T @ V @ T.transpose(1, 2)
+    c00, c01, c11 = cov[:, 0, 0], cov[:, 0, 1], cov[:, 1, 1]
+    det_orig = c00 * c11 - c01 * c01
+    a, b, c = c00 + 0.3, c01, c11 + 0.3
+    det = a * c - b * b
+    comp = torch.sqrt(torch.clamp(det_orig / det, min=0.0))
+    has_conic = keep & (det != 0)
+    inv_det = 1.0 / det
+    conics = torch.stack([c * inv_det, -b * inv_det, a * inv_det], -1)
+    mid = 0.5 * (a + c)
+    disc = torch.sqrt(torch.clamp(mid * mid - det, min=0.1))
+    radius_real = 3.0 * torch.sqrt(torch.maximum(mid + disc, mid - disc))
+    radius = torch.ceil(radius_real)
+    rw = 1.0 / (p_view[:, 2] + 1e-6)
+    xys = torch.stack([p_view[:, 0] * rw * fx + cx, p_view[:, 1] * rw * fy + cy], -1)
+    tiles_x, tiles_y = tile_grid(height, width)
+    tc, tr = xys / TILE, radius / TILE
+    x0 = torch.clamp(torch.trunc(tc[:, 0] - tr).long(), 0, tiles_x)
+    x1 = torch.clamp(torch.trunc(tc[:, 0] + tr + 1).long(), 0, tiles_x)
+    y0 = torch.clamp(torch.trunc(tc[:, 1] - tr).long(), 0, tiles_y)
+    y1 = torch.clamp(torch.trunc(tc[:, 1] + tr + 1).long(), 0, tiles_y)
+    area = torch.nan_to_num((x1 - x0) * (y1 - y0))
+    vis = has_conic & (area > 0)
+    z1 = lambda t, m: torch.where(m if t.dim() == 1 else m[:, None], t, torch.zeros_like(t))
+    return {"xys": z1(xys, vis), "depths": z1(p_view[:, 2], vis), "radii": z1(radius, vis).to(torch.int32),
+            "conics": z1(conics, has_conic), "compensation": z1(comp, vis),
+            "num_tiles_hit": z1(area.to(f32), vis).to(torch.int32), "cov3d": z1(cov3d, keep),
+            "radius_real": z1(radius_real, vis)}
+
+
+_SH_C0 = 0.28209479177387814
+_SH_C1 = 0.4886025119029199
+_SH_C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+_SH_C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435)
+
+
+def spherical_harmonics(degrees_to_use: int, viewdirs: Tensor, coeffs: Tensor) -> Tensor:
+    """gsplat 0.1.11 ``spherical_harmonics`` (3DGS real SH basis; call site activesplatfacto_model.py:245):
+    ``coeffs [G, K, 3]`` -> colours ``[G, 3]`` from the first ``(degrees_to_use + 1)^2`` bases; the direction is
+    normalised inside."""
+    cf = coeffs.to(torch.float32)
+    col = _SH_C0 * cf[:, 0]
+    if degrees_to_use < 1:
+        return col
+    d = viewdirs.to(torch.float32)
+    d = d / torch.sqrt((d * d).sum(-1, keepdim=True))
+    x, y, z = (d[:, i:i + 1] for i in range(3))
+    col = col + _SH_C1 * (-y * cf[:, 1] + z * cf[:, 2] - x * cf[:, 3])
+    if degrees_to_use < 2:
+        return col
+    xx, xy, xz, yy, yz, zz = x * x, x * y, x * z, y * y, y * z, z * z
+    col = col + (_SH_C2[0] * xy * cf[:, 4] + _SH_C2[1] * yz * cf[:, 5] + _SH_C2[2] * (2 * zz - xx - yy) * cf[:, 6]
+                 + _SH_C2[3] * xz * cf[:, 7] + _SH_C2[4] * (xx - yy) * cf[:, 8])
+    if degrees_to_use < 3:
+        return col
+    return col + (_SH_C3[0] * y * (3 * xx - yy) * cf[:, 9] + _SH_C3[1] * xy * z * cf[:, 10]
+                  + _SH_C3[2] * y * (4 * zz - xx - yy) * cf[:, 11] + _SH_C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * cf[:, 12]
+                  + _SH_C3[4] * x * (4 * zz - xx - yy) * cf[:, 13] + _SH_C3[5] * z * (xx - yy) * cf[:, 14]
+                  + _SH_C3[6] * x * (xx - 3 * yy) * cf[:, 15])
+
+
 def rasterize(xys: Tensor, conics: Tensor, opacities: Tensor, colors: Tensor, gaussian_ids: Tensor,
               tile_bins: Tensor, height: int, width: int, background: Tensor) -> Tuple[Tensor, Tensor]:
     """``out [H, W, C] = sum_i c_i alpha_i T_i + T_final * background``, ``alpha [H, W] = 1 - T_final``.

@@ -154,3 +154,61 @@ def test_laplace_tensor_core_path_large_magnitudes(built_library):
     out = ops.laplace_ll_moments(x.cuda(), theta.cuda(), 3, "sigmoid", want_mean2=True)
     torch.testing.assert_close(out["mean"].cpu(), mu, rtol=2e-5, atol=2e-6)
     torch.testing.assert_close(out["mean2"].cpu(), mu2, rtol=2e-5, atol=2e-6)
+
+
+# ---- producers of the splat path: projection + spherical harmonics (row f2) ----
+@pytest.mark.parametrize("n,hw", [(5000, (120, 160)), (257, (33, 47))])
+def test_project_gaussians_matches_oracle(built_library, n, hw):
+    h, w = hw
+    sc = synthetic.gaussians_3d(n, h, w, seed=n)
+    ref = osp.project_gaussians(sc["means"], sc["scales"], 1.0, sc["quats"], sc["viewmat"], sc["fx"], sc["fy"],
+                                sc["cx"], sc["cy"], h, w)
+    xys, depths, radii, conics, comp, tiles, cov3d = binning.project_gaussians(
+        sc["means"].cuda(), sc["scales"].cuda(), 1, sc["quats"].cuda(), sc["viewmat"].cuda(), sc["fx"], sc["fy"],
+        sc["cx"], sc["cy"], h, w, 16)
+    # integer outputs: identical unless 3 sqrt(lambda_max) sits within float32 rounding of an integer
+    frac = ref["radius_real"] - torch.floor(ref["radius_real"])
+    sure = (frac > 1e-3) & (frac < 1 - 1e-3) | (ref["radii"] == 0)
+    visible = ref["radii"] > 0
+    assert int(visible.sum()) > n // 10 and int((~visible).sum()) > 0            # both populations are exercised
+    assert torch.equal(radii.cpu()[sure], ref["radii"][sure])
+    assert torch.equal(tiles.cpu()[sure], ref["num_tiles_hit"][sure])
+    same = radii.cpu() == ref["radii"]
+    for name, got, want in (("xys", xys, ref["xys"]), ("depths", depths, ref["depths"]),
+                            ("compensation", comp, ref["compensation"])):
+        torch.testing.assert_close(got.cpu()[same], want[same], rtol=2e-4, atol=2e-4, msg=lambda m: f"{name}: {m}")
+    torch.testing.assert_close(conics.cpu(), ref["conics"], rtol=5e-4, atol=1e-6)
+    # off-diagonal covariance entries are sums with cancellation: absolute tolerance relative to the matrix scale
+    torch.testing.assert_close(cov3d.cpu(), ref["cov3d"], rtol=1e-4, atol=1e-6 * float(ref["cov3d"].abs().max()))
+
+
+@pytest.mark.parametrize("use", [0, 1, 2, 3])
+def test_spherical_harmonics_matches_oracle(built_library, use):
+    sc = synthetic.gaussians_3d(3001, 64, 64, seed=use)
+    dirs = sc["means"] - sc["camera_position"]
+    ref = osp.spherical_harmonics(use, dirs, sc["sh_coeffs"])
+    got = binning.spherical_harmonics(use, dirs.cuda(), sc["sh_coeffs"].cuda())
+    torch.testing.assert_close(got.cpu(), ref, rtol=1e-5, atol=2e-6)
+    with pytest.raises(Exception):
+        binning.spherical_harmonics(4, dirs.cuda(), sc["sh_coeffs"].cuda())      # more degrees than coefficients
+
+
+def test_projection_to_image_chain(built_library):
+    """3-D scene -> project -> SH colours -> bin -> fused active-splatfacto outputs, against the oracle chain."""
+    from uncertainty_nerf_gs_b200.models.outputs import active_splatfacto_outputs
+
+    h, w, n = 48, 64, 600
+    sc = synthetic.gaussians_3d(n, h, w, seed=11)
+    cu = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in sc.items()}
+    xys, depths, radii, conics, comp, tiles, _ = binning.project_gaussians(
+        cu["means"], cu["scales"], 1, cu["quats"], cu["viewmat"], sc["fx"], sc["fy"], sc["cx"], sc["cy"], h, w, 16)
+    rgbs = torch.clamp(binning.spherical_harmonics(3, cu["means"] - cu["camera_position"], cu["sh_coeffs"]) + 0.5, min=0.0)
+    ids, bins = binning.bin_gaussians(xys, depths, radii, h, w)
+    assert int(tiles.sum()) == ids.numel()                                       # num_tiles_hit is the binning's count
+    bg = torch.tensor([0.2, 0.3, 0.4])
+    out = active_splatfacto_outputs(xys, depths, conics, cu["opacities"], rgbs, cu["betas"], ids, bins, h, w, bg.cuda())
+    # oracle chain on the GPU's projected quantities (the projection itself is compared above)
+    ref = osp.active_splatfacto_outputs(xys.cpu(), depths.cpu(), conics.cpu(), sc["opacities"], rgbs.cpu(), sc["betas"],
+                                        ids.cpu(), bins.cpu(), h, w, bg)
+    for k in ("rgb", "depth", "accumulation", "uncertainty", "depth_var"):
+        torch.testing.assert_close(out[k].cpu(), ref[k], rtol=2e-4, atol=2e-5, equal_nan=True, msg=lambda m: f"{k}: {m}")

@@ -8,6 +8,7 @@ for the CUDA path and the oracle), ``"cuda"`` for the full-size benchmark.
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -136,5 +137,33 @@ def splat_scene(num_gaussians: int, height: int, width: int, seed: int = 0, devi
         "opacities": torch.sigmoid(1.5 * torch.randn(G, 1, **kw)),
         "depths": torch.rand(G, **kw) * 9.9 + 0.1,
         "rgbs": torch.rand(G, 3, **kw),
+        "betas": torch.nn.functional.softplus(torch.randn(G, 1, **kw)) + 0.01,
+    }
+
+
+def gaussians_3d(num_gaussians: int, height: int, width: int, seed: int = 0, device="cpu", sh_degree: int = 3
+                 ) -> Dict[str, Tensor]:
+    """A 3-D Gaussian scene in front of (and partly behind / beside) a pinhole camera, with the inputs the
+    reference hands to ``project_gaussians`` / ``spherical_harmonics`` (activesplatfacto_model.py:205-249):
+    ``means, scales`` (already exp'ed), ``quats`` (unnormalised), ``viewmat [3,4]``, intrinsics, SH coefficients."""
+    g = _gen(seed, device)
+    kw = dict(generator=g, device=device, dtype=torch.float32)
+    G = num_gaussians
+    means = torch.stack([torch.rand(G, **kw) * 8 - 4, torch.rand(G, **kw) * 6 - 3, torch.rand(G, **kw) * 9 - 1], -1)
+    scales = torch.exp(torch.randn(G, 3, **kw) * 0.6 - 3.0)
+    quats = torch.randn(G, 4, **kw)
+    # camera: small rotation about y and x, translated back along z
+    ay, ax = 0.15, -0.08
+    ry = torch.tensor([[math.cos(ay), 0, math.sin(ay)], [0, 1, 0], [-math.sin(ay), 0, math.cos(ay)]])
+    rx = torch.tensor([[1, 0, 0], [0, math.cos(ax), -math.sin(ax)], [0, math.sin(ax), math.cos(ax)]])
+    rot = (rx @ ry).to(torch.float32)
+    viewmat = torch.cat([rot, torch.tensor([[0.1], [-0.2], [1.5]])], dim=1).to(device)
+    k = (sh_degree + 1) ** 2
+    return {
+        "means": means, "scales": scales, "quats": quats, "viewmat": viewmat,
+        "fx": 0.9 * width, "fy": 0.95 * width, "cx": width / 2 + 0.3, "cy": height / 2 - 0.4,
+        "sh_coeffs": 0.5 * torch.randn(G, k, 3, **kw),
+        "camera_position": -(rot.T @ torch.tensor([0.1, -0.2, 1.5])).to(device),
+        "opacities": torch.sigmoid(1.5 * torch.randn(G, 1, **kw)),
         "betas": torch.nn.functional.softplus(torch.randn(G, 1, **kw)) + 0.01,
     }
