@@ -222,6 +222,7 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa_bound = pipeline.bind_host_thread_to_gpu(local_rank) if world > 1 else False
     h, w, m = args.height, args.width, args.members
     R = h * w
     steps, warmup = max(1, args.steps), max(3, args.warmup)
@@ -369,7 +370,8 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(h, w, m), "rays_per_view": R, "samples_per_ray": S, "members": m,
                    "views_per_step": world, "l2": f"inputs {m * R * 1536 / 1e9:.1f} GB per step >> 126 MB L2, no flush needed",
-                   "parallelism": f"view-sharded x{world}, all_gather of {pipeline.RECORD_LEN * 8} B records"},
+                   "parallelism": f"view-sharded x{world}, all_gather of {pipeline.RECORD_LEN * 8} B records",
+                   "host_threads_bound_to_gpu_numa_node": bool(numa_bound)},
         "images_per_s": world / (ms_per_step * 1e-3),
         "ause_auce_images_per_s": world / (score_stream_ms * 1e-3),
         "ause_auce_ms_per_image": score_stream_ms,

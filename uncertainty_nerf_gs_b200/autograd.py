@@ -60,7 +60,7 @@ class _CompositeRaysFn(torch.autograd.Function):
         gc = torch.empty_like(keep[4]) if need[4] else None
         gb = torch.empty_like(keep[5]) if need[5] else None
         a.out_g_density, a.out_g_rgb, a.out_g_beta = ops._ptr(gd), ops._ptr(gc), ops._ptr(gb)
-        with torch.cuda.device(dev):
+        with ops._guard(dev):
             _lib.check(lib.ub_composite_rays_backward(C.byref(a), ops._stream()))
         ops._count(1)
         return gd, None, None, None, gc, gb, None, None

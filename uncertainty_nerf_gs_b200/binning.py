@@ -45,7 +45,7 @@ def project_gaussians(means3d: Tensor, scales: Tensor, glob_scale: float, quats:
     conics, comp = torch.empty(g, 3, device=dev), torch.empty(g, device=dev)
     tiles = torch.empty(g, dtype=torch.int32, device=dev)
     cov3d = torch.empty(g, 6, device=dev)
-    with torch.cuda.device(dev):
+    with ops._guard(dev):
         _lib.check(lib.ub_project_gaussians(means3d.data_ptr(), scales.data_ptr(), float(glob_scale), quats.data_ptr(),
                                             vm.data_ptr(), float(fx), float(fy), float(cx), float(cy), img_height,
                                             img_width, float(clip_thresh), g, xys.data_ptr(), depths.data_ptr(),
@@ -65,7 +65,7 @@ def spherical_harmonics(degrees_to_use: int, viewdirs: Tensor, coeffs: Tensor) -
     if degree is None or coeffs.shape[2] != 3:
         raise ValueError("coeffs must be [G, (degree+1)^2, 3] with degree <= 3")
     out = torch.empty(g, 3, device=coeffs.device)
-    with torch.cuda.device(coeffs.device):
+    with ops._guard(coeffs.device):
         _lib.check(lib.ub_spherical_harmonics(degree, int(degrees_to_use), viewdirs.data_ptr(), coeffs.data_ptr(), g,
                                               out.data_ptr(), ops._stream()))
     ops._count(1)
@@ -86,7 +86,7 @@ def bin_gaussians(xys: Tensor, depths: Tensor, radii: Tensor, height: int, width
     offsets = torch.empty(g + 1, dtype=torch.int64, device=dev)
     total = torch.empty(1, dtype=torch.int64, device=dev)
     ws = ops._workspace(lib.ub_bin_count_workspace_bytes(g), dev)
-    with torch.cuda.device(dev):
+    with ops._guard(dev):
         _lib.check(lib.ub_bin_count(xys.data_ptr(), radii.data_ptr(), g, height, width, offsets.data_ptr(),
                                     total.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream()))
         n = int(total.item())          # the one host synchronisation of binning: the output size

@@ -5,6 +5,7 @@ Every function requires CUDA float32 tensors and raises otherwise -- there is no
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -39,8 +40,24 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_NO_GUARD = contextlib.nullcontext()
+
+
 def _stream() -> int:
+    """Raw ``cudaStream_t`` of torch's current stream on the current device (the fast private accessor when this
+    torch has it: ``torch.cuda.current_stream()`` costs ~20 us of Python per call)."""
+    if _RAW_STREAM is not None:
+        return _RAW_STREAM(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
+
+
+def _guard(device):
+    """``torch.cuda.device(device)`` only when the current device differs (the context manager itself costs ~10 us)."""
+    idx = device.index if isinstance(device, torch.device) else int(device)
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(idx)
 
 
 def _workspace(nbytes: int, device) -> Tensor:
@@ -127,7 +144,7 @@ def composite_rays(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor
     if torch.cuda.current_device() == dev.index:
         _lib.check(lib.ub_composite_rays(C.byref(args), ws_ptr, ws_bytes, _stream()))
     else:
-        with torch.cuda.device(dev):
+        with _guard(dev):
             _lib.check(lib.ub_composite_rays(C.byref(args), ws_ptr, ws_bytes, _stream()))
     _count(2 if R > 0 else 0)
     return out
@@ -158,7 +175,7 @@ def render_weights(weights: Tensor, starts: Tensor, ends: Tensor, *, rays_per_ch
         out[k] = torch.empty(R, 1, device=dev)
         setattr(args, fields[k], out[k].data_ptr())
     ws = _workspace(lib.ub_render_weights_workspace_bytes(R, args.rays_per_chunk), dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _lib.check(lib.ub_render_weights(C.byref(args), ws.data_ptr(), ws.numel(), _stream()))
     _count((2 if "expected_depth" in out else 1) if R > 0 else 0)
     return out
@@ -181,7 +198,7 @@ def average_sampled_weights(density: Tensor, density_var: Tensor, deltas: Tensor
         if noise.shape[0] != num_draws:
             raise ValueError("noise must be [num_draws, R, S]")
     out = torch.empty(R, S, 1, device=density.device)
-    with torch.cuda.device(density.device):
+    with _guard(density.device):
         _lib.check(lib.ub_average_sampled_weights(density.data_ptr(), density_var.data_ptr(), deltas.data_ptr(),
                                                   _ptr(noise), R, S, int(num_draws), int(seed), out.data_ptr(),
                                                   _stream()))
@@ -222,7 +239,7 @@ def reduce_many(jobs: Sequence[Tuple[Sequence[Tensor], Optional[str]]]) -> List[
         prepared.append((ms, c, n, spread, mean, spr))
     dev = prepared[0][0][0].device
     results = []
-    with torch.cuda.device(dev):
+    with _guard(dev):
         for lo in range(0, len(prepared), _lib.UB_MAX_REDUCE_JOBS):
             chunk = prepared[lo:lo + _lib.UB_MAX_REDUCE_JOBS]
             arr = (_lib.ReduceJob * len(chunk))()
@@ -336,7 +353,7 @@ def score_prologue(pred: Tensor, target: Tensor, std: Tensor, seg_lengths: Seque
     args.out_var = _ptr(out.get("var"))
     args.out_sums, args.out_hist = out["sums"].data_ptr(), out["hist"].data_ptr()
     ws = _workspace(lib.ub_score_prologue_workspace_bytes(nseg, seg.max_len, nz), dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _lib.check(lib.ub_score_prologue(C.byref(args), ws.data_ptr(), ws.numel(), _stream()))
     _count(2)
     return out
@@ -357,7 +374,7 @@ def segmented_sort(keys: Tensor, seg_lengths: Sequence[int], want_perm: bool = T
     perm = torch.empty(total, dtype=torch.int32, device=dev) if want_perm else None
     nseg, max_len = seg.num, seg.max_len
     ws = _workspace(lib.ub_segmented_sort_workspace_bytes(nseg, total, max_len, 1 if want_perm else 0), dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _lib.check(lib.ub_segmented_sort(keys.data_ptr(), nseg, seg.offsets.data_ptr(), total, max_len,
                                          _ptr(sorted_keys), _ptr(perm), ws.data_ptr(), ws.numel(), _stream()))
     _count(12 if total > 0 else 0)
@@ -389,7 +406,7 @@ def cut_prefix_sums(values: Sequence[Tensor], perms: Union[None, Tensor, Sequenc
     ptrs = (C.c_void_p * len(vals))(*[v.data_ptr() for v in vals])
     pptrs = (C.c_void_p * len(vals))(*[_ptr(pm) for pm in perms])
     ws = _workspace(lib.ub_cut_prefix_sums_workspace_bytes(nseg, seg.max_len, len(vals), ncuts), dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _lib.check(lib.ub_cut_prefix_sums(ptrs, pptrs, len(vals), nseg, seg.offsets.data_ptr(), seg.max_len,
                                           cuts_dev.data_ptr(), ncuts, out.data_ptr(), ws.data_ptr(), ws.numel(),
                                           _stream()))
@@ -419,7 +436,7 @@ def laplace_ll_moments(x: Tensor, sampled_params: Tensor, out_dim: int, activati
     out = {"mean": torch.empty(p, out_dim, device=dev), "sigma2": torch.empty(p, out_dim, device=dev)}
     if want_mean2:
         out["mean2"] = torch.empty(p, out_dim, device=dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _lib.check(lib.ub_laplace_ll_moments(x.data_ptr(), p, h, out_dim, sampled_params.data_ptr(),
                                              sampled_params.shape[0],
                                              _ACTS[activation] | (0 if tensor_cores else 0x100), out["mean"].data_ptr(),
@@ -450,7 +467,7 @@ def composite_tiles(xys: Tensor, conics: Tensor, opacities: Tensor, colors: Tens
     out = torch.empty(height, width, ch, device=dev)
     alpha = torch.empty(height, width, 1, device=dev)
     bg = (C.c_float * ch)(*([0.0] * ch if background is None else [float(v) for v in background]))
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _lib.check(lib.ub_composite_tiles(xys.data_ptr(), conics.data_ptr(), opacities.data_ptr(), colors.data_ptr(),
                                           ch, gaussian_ids.data_ptr(), tile_bins.data_ptr(), height, width, bg,
                                           out.data_ptr(), alpha.data_ptr(), _stream()))
@@ -488,7 +505,7 @@ def composite_tiles_planes(xys: Tensor, conics: Tensor, opacities: Tensor, plane
     pp = (C.c_void_p * len(pls))(*[p.data_ptr() for p in pls])
     pc = (C.c_int32 * len(pls))(*chs)
     po = (C.c_void_p * len(pls))(*[o.data_ptr() for o in outs])
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _lib.check(lib.ub_composite_tiles_planes(xys.data_ptr(), conics.data_ptr(), opacities.data_ptr(), pp, pc,
                                                  len(pls), gaussian_ids.data_ptr(), tile_bins.data_ptr(), height,
                                                  width, bg, po, alpha.data_ptr(), _ptr(keys), _stream()))
@@ -523,7 +540,7 @@ def composite_tiles_planes_backward(xys: Tensor, conics: Tensor, opacities: Tens
     pc = (C.c_int32 * len(pls))(*chs)
     pv = (C.c_void_p * len(pls))(*[_ptr(v) for v in vos])
     pg = (C.c_void_p * len(pls))(*[_ptr(v) for v in v_pl])
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _lib.check(lib.ub_composite_tiles_planes_backward(
             xys.data_ptr(), conics.data_ptr(), opacities.data_ptr(), pp, pc, len(pls),
             _ptr(gaussian_ids.contiguous()), tile_bins.contiguous().data_ptr(), height, width, bg, pv, _ptr(va), g,
@@ -538,7 +555,7 @@ def splat_normalize_(image: Tensor, alpha: Optional[Tensor] = None, max_key: Opt
     lib = _lib.load()
     ch = int(image.shape[-1])
     n = image.numel() // ch
-    with torch.cuda.device(image.device):
+    with _guard(image.device):
         _lib.check(lib.ub_splat_normalize(image.data_ptr(), ch, _ptr(alpha), n, 1 if clamp_max_one else 0,
                                           1 if alpha is not None else 0, _ptr(max_key), _stream()))
     _count(1)
@@ -552,7 +569,7 @@ def splat_depth_residual(xys: Tensor, depths: Tensor, depth_image: Tensor) -> Te
     depth_image = _dev_f32(depth_image, "depth_image")
     h, w = int(depth_image.shape[0]), int(depth_image.shape[1])
     out = torch.empty(depths.numel(), 1, device=xys.device)
-    with torch.cuda.device(xys.device):
+    with _guard(xys.device):
         _lib.check(lib.ub_splat_depth_residual(xys.data_ptr(), depths.data_ptr(), depth_image.data_ptr(), h, w,
                                                depths.numel(), out.data_ptr(), _stream()))
     _count(1)

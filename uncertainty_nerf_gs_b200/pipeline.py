@@ -160,6 +160,29 @@ def unpack_record(rec: np.ndarray) -> Tuple[int, Dict[str, object]]:
     return int(rec[o]), d
 
 
+def bind_host_thread_to_gpu(local_rank: int) -> bool:
+    """Pin the calling process to the CPU cores NVML reports as closest to GPU ``local_rank`` (one process per
+    GPU: keeps every rank's launch thread on its GPU's NUMA node instead of migrating across sockets).  Returns
+    False when NVML or the affinity call is unavailable -- purely an optimisation."""
+    try:
+        import os
+
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * i + b for i, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def gather_records(local: np.ndarray, device=None) -> np.ndarray:
     """All-gather the ``[views_per_rank, RECORD_LEN]`` float64 records of every rank (the only collective on
     the path; NCCL all_gather_into_tensor over NVLink when ``device`` is CUDA, gloo on CPU) and return them
