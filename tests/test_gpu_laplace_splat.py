@@ -212,3 +212,41 @@ def test_projection_to_image_chain(built_library):
                                         ids.cpu(), bins.cpu(), h, w, bg)
     for k in ("rgb", "depth", "accumulation", "uncertainty", "depth_var"):
         torch.testing.assert_close(out[k].cpu(), ref[k], rtol=2e-4, atol=2e-5, equal_nan=True, msg=lambda m: f"{k}: {m}")
+
+
+_CULL_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, {root!r})
+from oracle import splat as osp
+from uncertainty_nerf_gs_b200 import ops, synthetic
+h, w = 70, 100
+sc = synthetic.splat_scene(3000, h, w, seed=21, mean_scale_px=5.0)
+sc["opacities"][::11] = 0.003          # below 1/255: can never contribute
+sc["opacities"][5::13] = 0.9995        # clamped alpha
+sc["opacities"][7::301] = float("nan")
+sc["conics"][3::97, 1] = 5.0           # indefinite conic (sigma < 0 somewhere): no cull allowed
+sc["conics"][9::211] = float("nan")
+ids, bins = osp.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], h, w)
+cu = {{k: v.cuda() for k, v in sc.items()}}
+outs, alpha, _ = ops.composite_tiles_planes(cu["xys"], cu["conics"], cu["opacities"], [cu["rgbs"], cu["betas"], cu["depths"][:, None].contiguous()],
+                                            ids.cuda(), bins.cuda(), h, w, [0.1, 0.2, 0.3, 0.0, 0.0])
+torch.save([o.cpu() for o in outs] + [alpha.cpu()], {out!r})
+"""
+
+
+def test_warp_row_cull_changes_nothing(built_library, tmp_path):
+    """The warp-level row cull of the tile compositor must be invisible: same bits with UB_TILES_NO_CULL=1."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    results = []
+    for flag in ("0", "1"):
+        out = str(tmp_path / f"tiles_{flag}.pt")
+        env = dict(os.environ, UB_TILES_NO_CULL=flag)
+        subprocess.run([sys.executable, "-c", _CULL_SCRIPT.format(root=root, out=out)], check=True, env=env, timeout=300)
+        results.append(torch.load(out))
+    for a, b in zip(*results):
+        assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+    assert float(torch.nan_to_num(results[0][-1]).max()) > 0.5

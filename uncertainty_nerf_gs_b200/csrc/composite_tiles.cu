@@ -21,6 +21,8 @@
 // "planes" (rgb [G,3], beta [G,1], depth [G,1]) and go to one image per plane, so no concatenated colour
 // tensor and no strided channel views exist on the host side.  The per-channel maxima the reference's
 // post-processing needs (`depth_im.max()`) are accumulated with one atomicMax per tile.
+#include <cstdlib>
+
 #include "ub_common.cuh"
 
 namespace ub {
@@ -43,6 +45,7 @@ struct TileParams {
   float* out[kMaxPlanes];
   float* out_alpha;
   unsigned* channel_max_keys;  // [channels] order keys, or NULL
+  int no_cull;                 // debugging aid (UB_TILES_NO_CULL=1): evaluate every (pixel, splat) pair
 };
 
 template <int CH>
@@ -50,15 +53,22 @@ __global__ void __launch_bounds__(kTileThreads) composite_tiles_kernel(const Til
   constexpr int NCOLV = (CH + 2 + 3) / 4;  // float4 records after the first: {cb, cc, c0, c1}, {c2..c5}, ...
   __shared__ float4 s_geo[kTileThreads];
   __shared__ float4 s_rec[NCOLV][kTileThreads];
+  __shared__ float4 s_box[kTileThreads];
+  __shared__ unsigned char s_list[kTileThreads / 32][kTileThreads];  // per warp: staged splats that can touch its block
   __shared__ float s_max[kTileThreads / 32][CH];
 
   const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
-  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;  // row / column inside the tile
+  int ti, tj;  // row / column inside the tile
+  tile_pixel_of_thread(threadIdx.x, ti, tj);
   const int i = blockIdx.y * UB_TILE + ti, j = blockIdx.x * UB_TILE + tj;
   const float px = (float)j + 0.5f, py = (float)i + 0.5f;
   const bool inside = i < p.height && j < p.width;
   bool done = !inside;
   const int lo = p.tile_bins[2 * tile + 0], hi = p.tile_bins[2 * tile + 1];
+  // pixel-centre rows of this warp (two rows of the tile) and columns of the tile
+  // pixel-centre box of this warp's 8 x 4 block
+  const float blk_x_lo = (float)(blockIdx.x * UB_TILE + 8 * ((threadIdx.x >> 5) & 1)) + 0.5f, blk_x_hi = blk_x_lo + 7.0f;
+  const float blk_y_lo = (float)(blockIdx.y * UB_TILE + 4 * (threadIdx.x >> 6)) + 0.5f, blk_y_hi = blk_y_lo + 3.0f;
 
   float T = 1.0f;
   float acc[CH];
@@ -86,15 +96,37 @@ __global__ void __launch_bounds__(kTileThreads) composite_tiles_kernel(const Til
           }
         }
       }
-      s_geo[threadIdx.x] = make_float4(xy.x, xy.y, p.opacities[g], ca);
+      const float opac = p.opacities[g];
+      s_geo[threadIdx.x] = make_float4(xy.x, xy.y, opac, ca);
       s_rec[0][threadIdx.x] = make_float4(cb, cc, col[0], col[1]);
 #pragma unroll
       for (int v = 1; v < NCOLV; ++v)
         s_rec[v][threadIdx.x] = make_float4(col[4 * v - 2], col[4 * v - 1], col[4 * v], col[4 * v + 1]);
+      s_box[threadIdx.x] = p.no_cull ? make_float4(-INFINITY, INFINITY, -INFINITY, INFINITY)
+                                     : splat_reach_box(xy.x, xy.y, opac, ca, cb, cc);
     }
     __syncthreads();
     const int n = min(kTileThreads, hi - batch);
-    for (int t = 0; t < n && !done; ++t) {
+    // warp-level cull: compact, in order, the staged splats whose reach box meets this warp's 8 x 4 block; the
+    // per-pixel loop below then never sees the others (about half of a tile's list for a typical scene)
+    if (__all_sync(FULL_MASK, done)) continue;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kTileThreads / 32; ++k) {
+      const int t = k * 32 + lane;
+      bool keep = false;
+      if (t < n) {
+        const float4 box = s_box[t];
+        keep = !(box.x > blk_x_hi || box.y < blk_x_lo || box.z > blk_y_hi || box.w < blk_y_lo);
+      }
+      const unsigned m = __ballot_sync(FULL_MASK, keep);
+      if (keep) s_list[warp][cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned char)t;
+      cnt += __popc(m);
+    }
+    __syncwarp();
+    for (int q = 0; q < cnt && !done; ++q) {
+      const int t = s_list[warp][q];
       const float4 ga = s_geo[t];
       const float4 gb = s_rec[0][t];
       const float dx = ga.x - px, dy = ga.y - py;
@@ -156,7 +188,9 @@ __global__ void __launch_bounds__(kTileThreads) composite_tiles_kernel(const Til
   }
 }
 
-static int launch_tiles(const TileParams& p, int channels, int img_height, cudaStream_t stream) {
+static int launch_tiles(TileParams p, int channels, int img_height, cudaStream_t stream) {
+  static const bool no_cull = [] { const char* e = getenv("UB_TILES_NO_CULL"); return e && e[0] == '1'; }();
+  p.no_cull = no_cull ? 1 : 0;
   dim3 grid((unsigned)p.tiles_x, (unsigned)((img_height + UB_TILE - 1) / UB_TILE));
   switch (channels) {
     case 1: composite_tiles_kernel<1><<<grid, kTileThreads, 0, stream>>>(p); break;

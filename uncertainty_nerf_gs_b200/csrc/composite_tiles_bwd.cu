@@ -53,17 +53,23 @@ __global__ void __launch_bounds__(kBwdThreads) composite_tiles_bwd_kernel(const 
   __shared__ float4 s_geo[kBwdThreads];
   __shared__ float4 s_rec[NCOLV][kBwdThreads];
   __shared__ int s_gid[kBwdThreads];
+  __shared__ float4 s_box[kBwdThreads];  // warp-level cull, see splat_reach_box (ub_common.cuh)
+  __shared__ unsigned char s_list[kBwdThreads / 32][kBwdThreads];  // per warp: staged splats that can touch its block
   __shared__ float s_acc[kBwdThreads][NV + 1];
   __shared__ int s_end;
 
   const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
-  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  int ti, tj;
+  tile_pixel_of_thread(threadIdx.x, ti, tj);
   const int i = blockIdx.y * UB_TILE + ti, j = blockIdx.x * UB_TILE + tj;
   const float px = (float)j + 0.5f, py = (float)i + 0.5f;
   const bool inside = i < p.height && j < p.width;
   const int lo = p.tile_bins[2 * tile + 0], hi = p.tile_bins[2 * tile + 1];
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (hi <= lo) return;
+  // pixel-centre box of this warp's 8 x 4 block
+  const float blk_x_lo = (float)(blockIdx.x * UB_TILE + 8 * ((threadIdx.x >> 5) & 1)) + 0.5f, blk_x_hi = blk_x_lo + 7.0f;
+  const float blk_y_lo = (float)(blockIdx.y * UB_TILE + 4 * (threadIdx.x >> 6)) + 0.5f, blk_y_hi = blk_y_lo + 3.0f;
 
   auto stage = [&](int batch, int limit) {
     const int idx = batch + threadIdx.x;
@@ -86,12 +92,33 @@ __global__ void __launch_bounds__(kBwdThreads) composite_tiles_bwd_kernel(const 
         }
       }
       s_gid[threadIdx.x] = g;
-      s_geo[threadIdx.x] = make_float4(xy.x, xy.y, p.opacities[g], ca);
+      const float opac = p.opacities[g];
+      s_box[threadIdx.x] = splat_reach_box(xy.x, xy.y, opac, ca, cb, cc);
+      s_geo[threadIdx.x] = make_float4(xy.x, xy.y, opac, ca);
       s_rec[0][threadIdx.x] = make_float4(cb, cc, col[0], col[1]);
 #pragma unroll
       for (int v = 1; v < NCOLV; ++v)
         s_rec[v][threadIdx.x] = make_float4(col[4 * v - 2], col[4 * v - 1], col[4 * v], col[4 * v + 1]);
     }
+  };
+
+  // in-order list of the staged splats (first n entries) whose reach box meets this warp's 8 x 4 pixel block
+  auto build_list = [&](int n) {
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kBwdThreads / 32; ++k) {
+      const int t = k * 32 + lane;
+      bool keep = false;
+      if (t < n) {
+        const float4 box = s_box[t];
+        keep = !(box.x > blk_x_hi || box.y < blk_x_lo || box.z > blk_y_hi || box.w < blk_y_lo);
+      }
+      const unsigned m = __ballot_sync(FULL_MASK, keep);
+      if (keep) s_list[warp][cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned char)t;
+      cnt += __popc(m);
+    }
+    __syncwarp();
+    return cnt;
   };
 
   // ---- phase 1: final transmittance and end of the contributing range of every pixel ----
@@ -104,7 +131,10 @@ __global__ void __launch_bounds__(kBwdThreads) composite_tiles_bwd_kernel(const 
       stage(batch, hi);
       __syncthreads();
       const int n = min(kBwdThreads, hi - batch);
-      for (int t = 0; t < n && !done; ++t) {
+      if (__all_sync(FULL_MASK, done)) continue;
+      const int cnt = build_list(n);
+      for (int q = 0; q < cnt && !done; ++q) {
+        const int t = s_list[warp][q];
         const float4 ga = s_geo[t];
         const float4 gb = s_rec[0][t];
         const float dx = ga.x - px, dy = ga.y - py;
@@ -166,7 +196,10 @@ __global__ void __launch_bounds__(kBwdThreads) composite_tiles_bwd_kernel(const 
     stage(batch, end);
     __syncthreads();
     const int n = min(kBwdThreads, end - batch);
-    for (int t = n - 1; t >= 0; --t) {
+    // a warp none of whose pixels reached this batch has nothing to do in it
+    const int cnt = __any_sync(FULL_MASK, inside && last > batch) ? build_list(n) : 0;
+    for (int q = cnt - 1; q >= 0; --q) {
+      const int t = s_list[warp][q];
       const int idx = batch + t;
       bool valid = inside && idx < last;
       float g[NV];

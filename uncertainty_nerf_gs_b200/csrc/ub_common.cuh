@@ -139,4 +139,31 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
+// Pixel-centre box {x_lo, x_hi, y_lo, y_hi} outside which a splat cannot reach alpha >= 1/255, for warp-level
+// culling in the tile kernels: a warp covers an 8 x 4 pixel block of the tile, and a splat whose box misses the
+// block cannot change any of its pixels, so the warp skips it with one uniform test instead of 32 per-pixel
+// evaluations.  alpha >= 1/255 needs sigma <= L = ln(255 o); the ellipse {0.5 d^T Q d <= L} (Q = conic) spans
+// |dx| <= sqrt(2 L C / det Q), |dy| <= sqrt(2 L A / det Q).  Slack (1e-3 on L, 1e-4 relative + 1e-3 px on the
+// extents) keeps the test conservative under float32 rounding; a conic that is not positive definite or a NaN
+// disables the cull; o < 1/255 makes the box empty.  Results are unchanged bit for bit.
+__device__ __forceinline__ float4 splat_reach_box(float x, float y, float opac, float ca, float cb, float cc) {
+  const float4 everywhere = make_float4(-INFINITY, INFINITY, -INFINITY, INFINITY);
+  const float det = ca * cc - cb * cb;
+  const float L = logf(255.0f * opac) + 1e-3f;
+  if (!(det > 0.0f) || !(ca > 0.0f) || !(cc > 0.0f) || !(L == L) || !(x == x) || !(y == y)) return everywhere;
+  if (L <= 0.0f) return make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+  const float k = 2.0f * L / det;
+  const float hy = sqrtf(k * ca) * (1.0f + 1e-4f) + 1e-3f;
+  const float hx = sqrtf(k * cc) * (1.0f + 1e-4f) + 1e-3f;
+  if (!(hy == hy) || !(hx == hx)) return everywhere;
+  return make_float4(x - hx, x + hx, y - hy, y + hy);
+}
+
+// thread -> pixel of a 16 x 16 tile: warp w owns the 8 x 4 block at column 8 (w & 1), row 4 (w >> 1)
+__device__ __forceinline__ void tile_pixel_of_thread(int tid, int& ti, int& tj) {
+  const int w = tid >> 5, l = tid & 31;
+  tj = 8 * (w & 1) + (l & 7);
+  ti = 4 * (w >> 1) + (l >> 3);
+}
+
 }  // namespace ub
