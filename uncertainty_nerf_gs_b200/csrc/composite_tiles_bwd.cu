@@ -46,6 +46,34 @@ struct TileBwdParams {
   float* v_plane[kBwdPlanes];      // [G, ch_p] or NULL
 };
 
+// Sum P (8 or 16) per-lane values over the warp with the value-halving butterfly: at every step a lane keeps half
+// of its values and hands the other half to its partner, so P + 1 shuffles replace 5 P.  Afterwards the lanes
+// (l, l ^ 1) both hold the warp total of value index(l); returns that total and sets `index`.
+template <int P>
+__device__ __forceinline__ float warp_sum_scatter(float (&v)[P], int lane, int& index) {
+  static_assert(P == 8 || P == 16, "padded value count");
+  constexpr int kFirst = P == 16 ? 16 : 8;  // lane bit used by the first halving step
+  int idx = 0;
+#pragma unroll
+  for (int half = P / 2, bit = kFirst; half >= 1; half >>= 1, bit >>= 1) {
+    const bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(FULL_MASK, send, bit);
+    }
+    idx += upper ? half : 0;
+  }
+  // the remaining lane bits (1 for P = 16; 1, 2 for P = 8... folded below) hold partial sums of the same value
+  float r = v[0];
+#pragma unroll
+  for (int bit = (P == 16 ? 1 : 1); bit >= 1; bit >>= 1) r += __shfl_xor_sync(FULL_MASK, r, bit);
+  if (P == 8) r += __shfl_xor_sync(FULL_MASK, r, 16);
+  index = idx;
+  return r;
+}
+
 template <int CH>
 __global__ void __launch_bounds__(kBwdThreads) composite_tiles_bwd_kernel(const TileBwdParams p) {
   constexpr int NCOLV = (CH + 2 + 3) / 4;
@@ -248,17 +276,15 @@ __global__ void __launch_bounds__(kBwdThreads) composite_tiles_bwd_kernel(const 
         }
       }
       if (!__any_sync(FULL_MASK, valid)) continue;
+      constexpr int P = NV <= 8 ? 8 : 16;
+      float gp[P];
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        float v = g[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
-        g[k] = v;
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) atomicAdd(&s_acc[t][k], g[k]);
-      }
+      for (int k = 0; k < P; ++k) gp[k] = k < NV ? g[k] : 0.f;
+      int which;
+      const float total = warp_sum_scatter<P>(gp, lane, which);
+      // one lane per value index adds the warp total to the batch entry's accumulator
+      const bool owner = P == 16 ? (lane & 1) == 0 : (lane & 17) == 0;
+      if (owner && which < NV && total != 0.f) atomicAdd(&s_acc[t][which], total);
     }
     __syncthreads();
     // flush this batch: thread t owns entry t
