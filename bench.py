@@ -266,10 +266,15 @@ def run_ours(args, rank, world, local_rank):
         # stream of views: view i+1 is enqueued before view i's record is read back; the K records of every
         # rank are exchanged by ONE all_gather at the end of the stream, inside the timed region
         pending, local = None, []
+        host_enqueue_s = host_finish_s = 0.0
         for _ in range(steps):
+            t_a = time.perf_counter()
             nxt = pipeline.evaluate_view_async(members, gt, h, w, CHUNK, timers=timers)
+            t_b = time.perf_counter()
             if pending is not None:
                 local.append(finish(pending))
+            host_enqueue_s += t_b - t_a
+            host_finish_s += time.perf_counter() - t_b
             pending = nxt
         local.append(finish(pending))
         records = gather(local)
@@ -385,6 +390,7 @@ def run_ours(args, rank, world, local_rank):
                      "launches_timed": len(comp_ms), "share_of_step": comp_avg_ms * m / ms_per_step,
                      "traffic": ncu_traffic()},
         "gpu_launches": launches,
+        "host_ms_per_step": {"enqueue": host_enqueue_s / steps * 1e3, "wait_and_tail": host_finish_s / steps * 1e3},
         "clocks": clocks.summary(),
         "check": {"rgb_ause_rmse": agg["rgb_ause_rmse"], "rgb_nll": agg["rgb_nll"], "views_aggregated": int(records.shape[0])},
     }
