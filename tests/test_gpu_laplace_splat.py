@@ -250,3 +250,33 @@ def test_warp_row_cull_changes_nothing(built_library, tmp_path):
     for a, b in zip(*results):
         assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
     assert float(torch.nan_to_num(results[0][-1]).max()) > 0.5
+
+
+def test_splat_producers_edge_cases(built_library):
+    """Empty scenes, everything behind the camera, degree-0 colours, and a backward pass with no intersections."""
+    from uncertainty_nerf_gs_b200 import ops
+    from uncertainty_nerf_gs_b200.autograd import composite_tiles_train
+
+    dev = "cuda"
+    vm = torch.eye(4, device=dev)[:3]
+    empty = binning.project_gaussians(torch.zeros(0, 3, device=dev), torch.zeros(0, 3, device=dev), 1,
+                                      torch.zeros(0, 4, device=dev), vm, 50.0, 50.0, 16.0, 16.0, 32, 32, 16)
+    assert all(t.shape[0] == 0 for t in empty)
+    sc = synthetic.gaussians_3d(64, 32, 32, seed=3)
+    behind = sc["means"].clone()
+    behind[:, 2] = -5.0                                                   # camera looks down +z with this view matrix
+    xys, depths, radii, conics, comp, tiles, cov3d = binning.project_gaussians(
+        behind.cuda(), sc["scales"].cuda(), 1, sc["quats"].cuda(), vm, 50.0, 50.0, 16.0, 16.0, 32, 32, 16)
+    assert int(radii.abs().sum()) == 0 and int(tiles.sum()) == 0 and float(cov3d.abs().sum()) == 0.0
+    ids, bins = binning.bin_gaussians(xys, depths, radii, 32, 32)
+    assert ids.numel() == 0
+    col0 = binning.spherical_harmonics(0, sc["means"].cuda(), sc["sh_coeffs"][:, :1].contiguous().cuda())
+    torch.testing.assert_close(col0.cpu(), 0.28209479177387814 * sc["sh_coeffs"][:, 0], rtol=1e-6, atol=1e-7)
+    # nothing intersects: the image is the background, alpha 0, and every gradient is exactly zero
+    rgbs = torch.rand(64, 3, device=dev, requires_grad=True)
+    x = xys.clone().requires_grad_(True)
+    (img,), a = composite_tiles_train(x, conics + 1.0, torch.full((64,), 0.5, device=dev), [rgbs], ids, bins, 32, 32,
+                                      [0.25, 0.5, 0.75])
+    assert float(a.detach().abs().max()) == 0.0 and torch.equal(img.detach()[0, 0].cpu(), torch.tensor([0.25, 0.5, 0.75]))
+    (img.sum() + a.sum()).backward()
+    assert float(rgbs.grad.abs().max()) == 0.0 and float(x.grad.abs().max()) == 0.0

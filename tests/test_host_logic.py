@@ -1,6 +1,8 @@
 """CPU: host-side logic of the product package (no kernels): cut counts, z table, the numpy tails of
 ause / auce fed with exact intermediate results, argument validation, binning, and the failure mode when
 no CUDA device / library is present (the product path must fail loudly, never fall back)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -145,3 +147,12 @@ def test_batched_host_tails_equal_per_image_numpy():
         assert np.array_equal(rows[i]["coverage_values"], cov)
         assert rows[i]["auc_abs_error_values"] == np.trapz(y=np.abs(err), x=alphas)
         assert rows[i]["auc_length_values"] == np.trapz(y=list(2.0 * z * (ss[i] / n[i])), x=alphas)
+
+
+def test_numa_binding_helper_is_harmless_without_nvml():
+    from uncertainty_nerf_gs_b200 import pipeline
+
+    before = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    assert pipeline.bind_host_thread_to_gpu(0) in (True, False)       # no GPU here: False, and nothing changes
+    if before is not None and not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
