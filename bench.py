@@ -65,7 +65,7 @@ class ClockSampler:
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, device_index: int, period_s: float = 0.01):
+    def __init__(self, device_index: int, period_s: float = float(os.environ.get("UB_CLOCK_PERIOD_MS", "10")) * 1e-3):
         self.samples, self.reasons, self.power = [], set(), []
         self.period = period_s
         self._stop = threading.Event()

@@ -32,3 +32,23 @@ res["torch.empty"] = bench(lambda: torch.empty(100, device=dev))
 res["event_record"] = bench(lambda: torch.cuda.Event().record())
 res["_stream"] = bench(lambda: ops._stream())
 print(json.dumps({k: round(v, 1) for k, v in res.items()}))
+
+# ---- whole-view enqueue cost with and without the scoring side stream (tiny device work) ----
+hh, ww = 64, 64
+members = [synthetic.ray_samples(hh * ww, 48, seed=i, device=dev) for i in range(5)]
+for overlap in (False, True):
+    pend = []
+    def run():
+        pend.append(pipeline.evaluate_view_async(members, gt, hh, ww, 1 << 15, overlap_scoring=overlap))
+        if len(pend) > 1:
+            pend.pop(0).finish()
+    us = bench(run, n=100)
+    print(json.dumps({"evaluate_view_async+finish host us": round(us, 1), "overlap_scoring": overlap}))
+    for p_ in pend: p_.finish()
+    pend.clear()
+side = torch.cuda.Stream()
+def sw():
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        pass
+print(json.dumps({"stream switch us": round(bench(sw), 1)}))

@@ -355,7 +355,7 @@ def score_prologue(pred: Tensor, target: Tensor, std: Tensor, seg_lengths: Seque
     ws = _workspace(lib.ub_score_prologue_workspace_bytes(nseg, seg.max_len, nz), dev)
     with _guard(dev):
         _lib.check(lib.ub_score_prologue(C.byref(args), ws.data_ptr(), ws.numel(), _stream()))
-    _count(2)
+    _count(3)  # ratio table, prologue, finalize
     return out
 
 

@@ -81,14 +81,40 @@ class PendingView:
         return d
 
 
+_SCORE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _score_stream(device) -> "torch.cuda.Stream":
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _SCORE_STREAMS.get(idx)
+    if st is None:
+        st = _SCORE_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return st
+
+
 def evaluate_view_async(members: Sequence[Dict[str, Tensor]], rgb_gt: Tensor, height: int, width: int,
                         rays_per_chunk: int = 1 << 15, min_rgb_std_for_nll: float = 3e-2,
-                        timers: Optional[list] = None) -> PendingView:
+                        timers: Optional[list] = None, overlap_scoring: bool = True) -> PendingView:
     """``evaluate_view`` without the final host synchronisation: a driver streaming over a test set enqueues
-    view i+1 before reading view i's record back, so the device never waits for the numpy tail."""
+    view i+1 before reading view i's record back, so the device never waits for the numpy tail.
+
+    With ``overlap_scoring`` the scoring of this view is enqueued on a second stream behind an event: its ~20
+    small, latency-bound launches (radix passes over one image, cut sums, ...) then run underneath the next
+    view's persistent compositing kernels (which leave 55 KB of shared memory and half the registers of every
+    SM free) instead of serialising with them.  The reduced images stay referenced by the returned object until
+    ``finish()``, so the caching allocator cannot hand their memory to the other stream early."""
     outs = render_members(members, height, width, rays_per_chunk, timers)
     red = mo.ensemble_reduce(outs) if len(outs) > 1 else outs[0]
-    return PendingView(metrics.score_rgb_batch_async(red["rgb"], rgb_gt, red["rgb_std"], min_rgb_std_for_nll))
+    rgb, std = red["rgb"], red["rgb_std"]
+    if not overlap_scoring:
+        return PendingView(metrics.score_rgb_batch_async(rgb, rgb_gt, std, min_rgb_std_for_nll))
+    main = torch.cuda.current_stream(rgb.device)
+    side = _score_stream(rgb.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        pending = metrics.score_rgb_batch_async(rgb, rgb_gt, std, min_rgb_std_for_nll)
+    pending.keep_alive = (rgb, std, rgb_gt)
+    return PendingView(pending)
 
 
 class HostViewEvaluator:
