@@ -22,12 +22,14 @@ STD_KEYS = ("rgb", "depth", "expected_depth")
 def active_nerfacto_outputs(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor, rgb: Tensor,
                             beta: Tensor, *, background="last_sample", rays_per_chunk: Optional[int] = None,
                             eval_mode: bool = True, proposal_levels: Sequence[Level] = (),
-                            return_weights: bool = False) -> Dict[str, Tensor]:
+                            return_weights: bool = False, image_hw: Optional[Tuple[int, int]] = None
+                            ) -> Dict[str, Tensor]:
     """``ActiveNerfactoModel.get_outputs`` downstream of ``field.forward``
-    (reference activenerfacto_model.py:94-127, 150-151).  Inputs ``[R, S, C]``; outputs ``[R, C]``."""
+    (reference activenerfacto_model.py:94-127, 150-151).  Inputs ``[R, S, C]``; outputs ``[R, C]``, or
+    ``[H, W, C]`` with ``image_hw`` (the per-camera view the chunk loop of ``get_outputs_for_camera`` builds)."""
     o = ops.composite_rays(density, deltas, starts, ends, rgb, beta, background=background,
                            beta_mode="nan_guard", rays_per_chunk=rays_per_chunk, eval_mode=eval_mode,
-                           return_weights=return_weights)
+                           return_weights=return_weights, image_hw=image_hw)
     out = {
         "rgb": o["rgb"],
         "accumulation": o["accumulation"],
@@ -117,7 +119,8 @@ def ensemble_reduce(outputs_list: Sequence[Dict[str, Tensor]]) -> Dict[str, Tens
         out[k] = mean
         if has_pred_std and k in ("rgb", "depth"):
             alea = res[k + "_var"][0]                      # mean over members of the predicted variance
-            out[k + "_var_alea"] = alea.mean(dim=-1).unsqueeze(-1)
+            # .mean(dim=-1, keepdim) of a one-channel image is the image itself (x / 1): skip the launch
+            out[k + "_var_alea"] = alea if alea.shape[-1] == 1 else alea.mean(dim=-1).unsqueeze(-1)
             out[k + "_var_epi"] = spread
             out[k + "_var"] = out[k + "_var_epi"] + out[k + "_var_alea"]
             out[k + "_std"] = out[k + "_var"].sqrt()

@@ -76,34 +76,48 @@ _BG_MODES = {"last_sample": _lib.UB_BG_LAST_SAMPLE, "random": _lib.UB_BG_NONE, "
 _BETA_MODES = {"raw": _lib.UB_BETA_RAW, "nan_guard": _lib.UB_BETA_NAN_GUARD}
 
 
+def _ray_stream(t: Tensor, name: str, R: int, S: int, C_: int = 1) -> Tensor:
+    """A ``[R, S]`` / ``[R, S, 1]`` (``C_ == 1``) or ``[R, S, C_]`` float32 CUDA stream, contiguous; only the
+    pointer is used afterwards, so no reshaped view is created (each costs microseconds on this latency-bound path)."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device: the ub200 path has no CPU implementation")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    shp = t.shape
+    ok = (len(shp) == 3 and shp[0] == R and shp[1] == S and shp[2] == C_) or \
+         (C_ == 1 and len(shp) == 2 and shp[0] == R and shp[1] == S)
+    if not ok:
+        want = f"{(R, S, C_)}" if C_ != 1 else f"{(R, S)} or {(R, S, 1)}"
+        raise ValueError(f"{name}: shape {tuple(shp)} != {want}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
 def composite_rays(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor, rgb: Tensor,
                    beta: Optional[Tensor] = None, *, background: Union[str, Sequence[float], Tensor] = "last_sample",
                    beta_mode: str = "nan_guard", rays_per_chunk: Optional[int] = None,
-                   eval_mode: bool = True, return_weights: bool = False) -> Dict[str, Tensor]:
+                   eval_mode: bool = True, return_weights: bool = False,
+                   image_hw: Optional[Tuple[int, int]] = None) -> Dict[str, Tensor]:
     """One fused pass over ``[R, S]`` ray samples -> rgb, accumulation, median depth, expected depth,
     ``rgb_var = sum w^2 beta``, depth variance (+ std of both).  Outputs are ``[R, C]`` like the
-    reference's per-chunk ``get_outputs`` (activenerfacto_model.py:94-127)."""
+    reference's per-chunk ``get_outputs`` (activenerfacto_model.py:94-127), or ``[H, W, C]`` when
+    ``image_hw = (H, W)`` with ``H * W == R`` (what ``get_outputs_for_camera`` makes of them)."""
     lib = _lib.load()
-    density = _dev_f32(_squeeze_last(density, "density", 2), "density")
-    R, S = density.shape
-    tensors = {"deltas": deltas, "starts": starts, "ends": ends}
-    flat = {}
-    for name, t in tensors.items():
-        t = _dev_f32(_squeeze_last(t, name, 2), name)
-        if t.shape != (R, S):
-            raise ValueError(f"{name}: shape {tuple(t.shape)} != {(R, S)}")
-        flat[name] = t
-    rgb = _dev_f32(rgb, "rgb")
-    if rgb.shape != (R, S, 3):
-        raise ValueError(f"rgb: shape {tuple(rgb.shape)} != {(R, S, 3)}")
+    if not isinstance(density, torch.Tensor) or density.dim() not in (2, 3):
+        raise ValueError("density: expected [R, S] or [R, S, 1]")
+    R, S = int(density.shape[0]), int(density.shape[1])
+    density = _ray_stream(density, "density", R, S)
+    deltas = _ray_stream(deltas, "deltas", R, S)
+    starts = _ray_stream(starts, "starts", R, S)
+    ends = _ray_stream(ends, "ends", R, S)
+    rgb = _ray_stream(rgb, "rgb", R, S, 3)
     if beta is not None:
-        beta = _dev_f32(_squeeze_last(beta, "beta", 2), "beta")
-        if beta.shape != (R, S):
-            raise ValueError(f"beta: shape {tuple(beta.shape)} != {(R, S)}")
+        beta = _ray_stream(beta, "beta", R, S)
     dev = density.device
     args = _lib.CompositeRaysArgs()
-    args.density, args.deltas = density.data_ptr(), flat["deltas"].data_ptr()
-    args.starts, args.ends = flat["starts"].data_ptr(), flat["ends"].data_ptr()
+    args.density, args.deltas = density.data_ptr(), deltas.data_ptr()
+    args.starts, args.ends = starts.data_ptr(), ends.data_ptr()
     args.rgb, args.beta = rgb.data_ptr(), _ptr(beta)
     args.num_rays, args.num_samples = R, S
     if isinstance(background, str):
@@ -122,17 +136,24 @@ def composite_rays(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor
     # one allocation for all per-ray outputs (rows of a [10, R] buffer + the chunk workspace behind it):
     # the wrapper, not the kernel, bounds the latency of small (training-sized) batches
     ws_bytes = lib.ub_composite_rays_workspace_bytes(R, args.rays_per_chunk)
-    buf = torch.empty(10 * R + (ws_bytes + 3) // 4 + 4, device=dev)
+    ws_floats = (ws_bytes + 3) // 4
+    buf = torch.empty(10 * R + ws_floats + 4, device=dev)
     base = buf.data_ptr()
-    row = lambda i, c: buf[i * R:(i + c) * R].view(R, c)
-    out = {"rgb": row(0, 3), "accumulation": row(3, 1), "depth": row(4, 1), "expected_depth": row(5, 1),
-           "depth_var": row(8, 1), "depth_std": row(9, 1)}
+    if image_hw is not None:
+        if image_hw[0] * image_hw[1] != R:
+            raise ValueError(f"image_hw {tuple(image_hw)} does not hold {R} rays")
+        lead = (int(image_hw[0]), int(image_hw[1]))
+    else:
+        lead = (R,)
+    rows = buf[3 * R:10 * R].view(7, *lead, 1).unbind(0)     # accumulation, depth, expected, var, std, dvar, dstd
+    out = {"rgb": buf[:3 * R].view(*lead, 3), "accumulation": rows[0], "depth": rows[1], "expected_depth": rows[2],
+           "depth_var": rows[5], "depth_std": rows[6]}
     f = 4 * R
     args.out_rgb, args.out_accumulation = base, base + 3 * f
     args.out_depth, args.out_expected_depth = base + 4 * f, base + 5 * f
     args.out_depth_var, args.out_depth_std = base + 8 * f, base + 9 * f
     if beta is not None:
-        out["rgb_var"], out["rgb_std"] = row(6, 1), row(7, 1)
+        out["rgb_var"], out["rgb_std"] = rows[3], rows[4]
         args.out_rgb_var, args.out_rgb_std = base + 6 * f, base + 7 * f
     if return_weights:
         out["weights"] = torch.empty(R, S, 1, device=dev)
@@ -140,12 +161,9 @@ def composite_rays(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor
     ws_ptr = base + 10 * f
     ws_ptr += (-ws_ptr) % 16
     ws_off = (ws_ptr - base) // 4
-    out["_workspace"] = buf[ws_off:ws_off + (ws_bytes + 3) // 4]   # chunk clip bounds (used by the backward)
-    if torch.cuda.current_device() == dev.index:
+    out["_workspace"] = buf[ws_off:ws_off + ws_floats]   # chunk clip bounds (used by the backward)
+    with _guard(dev):
         _lib.check(lib.ub_composite_rays(C.byref(args), ws_ptr, ws_bytes, _stream()))
-    else:
-        with _guard(dev):
-            _lib.check(lib.ub_composite_rays(C.byref(args), ws_ptr, ws_bytes, _stream()))
     _count(2 if R > 0 else 0)
     return out
 

@@ -48,12 +48,16 @@ def render_members(members: Sequence[Dict[str, Tensor]], height: int, width: int
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record()
         o = mo.active_nerfacto_outputs(m["density"], m["deltas"], m["starts"], m["ends"], m["rgb"], m["beta"],
-                                       rays_per_chunk=rays_per_chunk)
+                                       rays_per_chunk=rays_per_chunk, image_hw=(height, width))
         if timers is not None:
             t1.record()
             timers.append((t0, t1))
-        outs.append({k: v.view(height, width, -1) for k, v in o.items()
-                     if keep_per_sample or k not in PER_SAMPLE_KEYS})
+        if keep_per_sample:
+            o["density"] = o["density"].view(height, width, -1)
+        else:
+            for k in PER_SAMPLE_KEYS:
+                o.pop(k, None)
+        outs.append(o)
     return outs
 
 
@@ -152,8 +156,10 @@ class HostViewEvaluator:
         for slot, ev in zip(self.slots, events):
             main.wait_event(ev)
             o = mo.active_nerfacto_outputs(slot["density"], slot["deltas"], slot["starts"], slot["ends"], slot["rgb"],
-                                           slot["beta"], rays_per_chunk=rays_per_chunk)
-            outs.append({k: v.view(self.h, self.w, -1) for k, v in o.items() if k not in PER_SAMPLE_KEYS})
+                                           slot["beta"], rays_per_chunk=rays_per_chunk, image_hw=(self.h, self.w))
+            for k in PER_SAMPLE_KEYS:
+                o.pop(k, None)
+            outs.append(o)
         red = mo.ensemble_reduce(outs) if len(outs) > 1 else outs[0]
         main.wait_stream(self.copy_stream)
         d = metrics.score_rgb_batch(red["rgb"], self.gt_dev, red["rgb_std"])[0]
