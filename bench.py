@@ -294,6 +294,15 @@ def run_ours(args, rank, world, local_rank):
     # ---- scoring-only throughput (AUSE + AUCE images/s), separate timed loop ----
     from uncertainty_nerf_gs_b200 import metrics
 
+    # ---- the dominant kernel alone: the same compositing calls with nothing else on the device (in the timed
+    # region above, the previous view's scoring runs underneath them on a second stream) ----
+    solo_timers = []
+    for _ in range(2):
+        pipeline.render_members(members, h, w, CHUNK, solo_timers)
+    torch.cuda.synchronize()
+    solo_ms = [a.elapsed_time(b) for a, b in solo_timers[m:]]
+    comp_solo_ms = sum(solo_ms) / len(solo_ms)
+
     pred_img = pipeline.render_members(members[:1], h, w, CHUNK)[0]
     torch.cuda.synchronize()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -388,7 +397,12 @@ def run_ours(args, rank, world, local_rank):
                      "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
                      "bytes_per_ray": BYTES_PER_RAY, "rays_per_launch": R, "ms_per_launch": comp_avg_ms,
                      "launches_timed": len(comp_ms), "share_of_step": comp_avg_ms * m / ms_per_step,
-                     "traffic": ncu_traffic()},
+                     "traffic": ncu_traffic(),
+                     "note": "timed inside the step, where the previous view's scoring kernels share the SMs and HBM "
+                             "(second stream); `standalone` = the same call with the device otherwise idle",
+                     "standalone": {"ms_per_launch": comp_solo_ms,
+                                    "achieved": BYTES_PER_RAY * R / (comp_solo_ms * 1e-3) / 1e9,
+                                    "frac": BYTES_PER_RAY * R / (comp_solo_ms * 1e-3) / 1e9 / peak}},
         "gpu_launches": launches,
         "host_ms_per_step": {"enqueue": host_enqueue_s / steps * 1e3, "wait_and_tail": host_finish_s / steps * 1e3},
         "clocks": clocks.summary(),
