@@ -88,3 +88,17 @@ def test_full_view_linearity(built_library):
     ref = torch.stack(ms[:5]).double()
     torch.testing.assert_close(mean.double(), ref.mean(0), rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(std.double(), ref.std(0).mean(-1, keepdim=True), rtol=1e-5, atol=1e-7)
+
+
+def test_ensemble_branch_a_when_the_combined_entries_survive(built_library):
+    """If a member dict lists rgb_var / rgb_std *before* rgb, the reference's loop overwrites nothing and the
+    epistemic + aleatoric sum survives: the skipped-dead-work shortcut must not change that."""
+    from uncertainty_nerf_gs_b200.models.outputs import ensemble_reduce
+
+    outs = synthetic.member_renders(4, 23, 31, seed=11, with_pred_std=True)
+    order = ["rgb_var", "rgb_std", "rgb", "accumulation", "depth", "expected_depth", "depth_var", "depth_std"]
+    outs = [{k: o[k] for k in order if k in o} | {k: v for k, v in o.items() if k not in order} for o in outs]
+    ref = orc.ensemble_reduce(outs)
+    out = ensemble_reduce(_cuda_list(outs))
+    _compare(out, ref)
+    torch.testing.assert_close(out["rgb_var"].cpu(), (ref["rgb_var_epi"] + ref["rgb_var_alea"]), rtol=RTOL, atol=1e-8)

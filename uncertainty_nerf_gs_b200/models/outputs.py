@@ -114,6 +114,7 @@ def ensemble_reduce(outputs_list: Sequence[Dict[str, Tensor]]) -> Dict[str, Tens
         jobs.append(([o[k] for o in outputs_list], spread))
     res = dict(zip(keys, ops.reduce_many(jobs)))
     out: Dict[str, Tensor] = {}
+    pos = {k: i for i, k in enumerate(keys)}
     for k in keys:
         mean, spread = res[k]
         out[k] = mean
@@ -122,8 +123,15 @@ def ensemble_reduce(outputs_list: Sequence[Dict[str, Tensor]]) -> Dict[str, Tens
             # .mean(dim=-1, keepdim) of a one-channel image is the image itself (x / 1): skip the launch
             out[k + "_var_alea"] = alea if alea.shape[-1] == 1 else alea.mean(dim=-1).unsqueeze(-1)
             out[k + "_var_epi"] = spread
-            out[k + "_var"] = out[k + "_var_epi"] + out[k + "_var_alea"]
-            out[k + "_std"] = out[k + "_var"].sqrt()
+            # The reference goes on to store epi + alea and its square root under k_var / k_std -- and overwrites
+            # both with the plain member means when its loop reaches those keys (the order quirk).  Entries that
+            # a later key overwrites are not computed at all; the returned dict is the same.
+            var_survives = pos.get(k + "_var", -1) < pos[k]
+            std_survives = pos.get(k + "_std", -1) < pos[k]
+            total = out[k + "_var_epi"] + out[k + "_var_alea"] if (var_survives or std_survives) else None
+            # (an overwritten entry is inserted here with its final value, so the key order stays the reference's)
+            out[k + "_var"] = total if var_survives else res[k + "_var"][0]
+            out[k + "_std"] = total.sqrt() if std_survives else res[k + "_std"][0]
         elif not has_pred_std and k in STD_KEYS:
             out[k + "_std"] = spread
     return out
