@@ -110,7 +110,42 @@ def splat():
                       "GBs_5ch": (48 * I + 24 * R) / ms5 / 1e6, "Mpix_s": R / ms5 / 1e3}))
 
 
+def cpu():
+    """The CPU restatement of every kernel family on the host of this box (all threads), beside the GPU numbers
+    above: bounded samples, best of 3.  The oracle is imported here only as the thing being *compared against*."""
+    import time
+    from oracle import compositing as oc, laplace as ol, metrics as om, reduce as orc, splat as osp
+    torch.set_num_threads(os.cpu_count())
+    def best(fn, n=3):
+        fn()
+        ts = []
+        for _ in range(n):
+            t = time.perf_counter(); fn(); ts.append(time.perf_counter() - t)
+        return min(ts)
+    info = {"cpu_threads": torch.get_num_threads(), "torch": torch.__version__}
+    m = synthetic.ray_samples(32768, S, seed=0)
+    t = best(lambda: oc.active_nerfacto_outputs(**m))
+    print(json.dumps({"cpu": "composite (oracle torch, one 32768-ray chunk)", "s": t, "Mrays_s": 32768 / t / 1e6, **info}))
+    outs = synthetic.member_renders(5, H, W, seed=0, with_pred_std=True)
+    t = best(lambda: orc.ensemble_reduce(outs), n=2)
+    print(json.dumps({"cpu": "ensemble_reduce K=5 (oracle torch, 1297x840 image keys)", "s": t, "views_s": 1 / t, **info}))
+    p_, s_, g_ = synthetic.scoring_image(800, 800, seed=0)
+    t = best(lambda: om.unc_metrics_rgb(p_, g_, s_, stable=False), n=2)
+    print(json.dumps({"cpu": "3x ause + auce + nll (reference's literal calls, 800x800)", "s": t, "images_s": 1 / t, **info}))
+    lap = synthetic.laplace_head(32768, 64, 3, 100, seed=0)
+    theta = ol.posterior_samples(lap["mu_q"], lap["ggn"], lap["eps_draws"])
+    t = best(lambda: ol.sample_laplace(lap["x"], theta, 3, torch.sigmoid))
+    print(json.dumps({"cpu": "laplace rgb head moments (oracle torch loop of 100 linears, 32768 points)", "s": t,
+                      "Mpoints_s": 32768 / t / 1e6, **info}))
+    sc = synthetic.splat_scene(2000, 96, 128, seed=0, mean_scale_px=4.0)
+    ids, bins = osp.bin_gaussians(sc["xys"], sc["depths"], sc["radii"], 96, 128)
+    t = best(lambda: osp.rasterize(sc["xys"], sc["conics"], sc["opacities"], sc["rgbs"], ids, bins, 96, 128, torch.zeros(3)), n=1)
+    print(json.dumps({"cpu": "tile rasterise 128x96, 2000 splats (oracle: python loop over tiles x splats; the reference itself "
+                             "runs gsplat's CUDA kernel here, so this is not a reference timing)", "s": t,
+                      "Mpix_s": 96 * 128 / t / 1e6, **info}))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["composite", "reduce", "score", "laplace", "splat"]
+    which = sys.argv[1:] or ["composite", "reduce", "score", "laplace", "splat", "cpu"]
     for name in which:
         globals()[name]()
