@@ -212,3 +212,39 @@ def test_prologue_vectors_match_torch(built_library):
     assert torch.equal(out["var"].cpu(), ref["var"])
     nll = om.negative_gaussian_loglikelihood(p.reshape(-1, 3), g.reshape(-1, 3), s, eps=3e-2)
     torch.testing.assert_close(out["sums"][0, 3].cpu(), nll.double().sum(), rtol=1e-6, atol=0)
+
+
+def test_auce_counts_exact_at_interval_boundaries(built_library):
+    """Adversarial inputs for the three-tier coverage count (csrc/score_prologue.cu): targets placed on, and one
+    float32 ulp either side of, the float64 interval ends m -+ z_k sigma for every threshold k; tiny and huge
+    sigma relative to |m| (forces the general path); zero / NaN / negative sigma.  Counts must equal numpy's."""
+    from scipy.stats import norm
+
+    from uncertainty_nerf_gs_b200.metrics import auce
+
+    rng = np.random.default_rng(7)
+    alphas = np.arange(start=0.01, stop=1.0, step=0.01)
+    z = norm.ppf(1 - alphas / 2)
+    rows = []
+    for k in range(len(z)):
+        for rep in range(24):
+            m = np.float32(rng.uniform(-3, 3) if rep % 3 else rng.uniform(-1e3, 1e3))
+            scale = [1.0, 1e-3, 1e-7, 30.0][rep % 4]
+            s = np.float32(abs(rng.normal()) * scale + 1e-9)
+            for sign in (-1.0, 1.0):
+                edge = np.float64(m) + sign * (np.float64(z[k]) * np.float64(s))   # numpy >= 2: float64 arithmetic
+                t0 = np.float32(edge)
+                for t in (t0, np.nextafter(t0, np.float32(np.inf)), np.nextafter(t0, np.float32(-np.inf))):
+                    rows.append((m, s, t))
+    rows += [(np.float32(1.0), np.float32(0.0), np.float32(1.0)), (np.float32(1.0), np.float32(0.0), np.float32(1.5)),
+             (np.float32(0.5), np.float32(-0.2), np.float32(0.5)), (np.float32(0.5), np.float32(np.nan), np.float32(0.5)),
+             (np.float32(np.nan), np.float32(0.1), np.float32(0.5)), (np.float32(0.5), np.float32(0.1), np.float32(np.nan)),
+             (np.float32(0.0), np.float32(1e-38), np.float32(1e-39)), (np.float32(1e30), np.float32(1e25), np.float32(1.00001e30)),
+             (np.float32(0.3), np.float32(np.inf), np.float32(0.9))]
+    arr = np.array(rows, dtype=np.float32)
+    m, s, t = arr[:, 0:1].copy(), arr[:, 1:2].copy(), arr[:, 2:3].copy()
+    with np.errstate(invalid="ignore", over="ignore"):
+        ref = om.auce(m, s, t)
+    out = auce(m, s, t)
+    n = float(m.size)
+    assert np.array_equal(np.rint(np.asarray(out["coverage_values"]) * n), np.rint(np.asarray(ref["coverage_values"]) * n))
