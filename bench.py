@@ -327,16 +327,22 @@ def run_ours(args, rank, world, local_rank):
     s1.record()
     torch.cuda.synchronize()
     score_stream_ms = s0.elapsed_time(s1) / score_steps
-    # ... and with 8 views per call (one set of segmented launches)
+    # ... and with 8 views per call (one set of segmented launches), streamed the same way
     b8 = 8
     p8, g8, s8 = (t[None].expand(b8, *t.shape).contiguous() for t in (pred_img["rgb"], gt, pred_img["rgb_std"]))
     metrics.score_rgb_batch(p8, g8, s8)
+    n8 = max(3, score_steps // 4)
     s0.record()
-    for _ in range(max(3, score_steps // 4)):
-        metrics.score_rgb_batch(p8, g8, s8)
+    pend = None
+    for _ in range(n8):
+        nxt = metrics.score_rgb_batch_async(p8, g8, s8)
+        if pend is not None:
+            pend.finish()
+        pend = nxt
+    pend.finish()
     s1.record()
     torch.cuda.synchronize()
-    score_b8_ms = s0.elapsed_time(s1) / max(3, score_steps // 4) / b8
+    score_b8_ms = s0.elapsed_time(s1) / n8 / b8
     del p8, g8, s8
 
     # ---- end to end: pinned host inputs -> H2D -> pipeline -> D2H record ----
@@ -387,11 +393,13 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": f"view-sharded x{world}, all_gather of {pipeline.RECORD_LEN * 8} B records",
                    "host_threads_bound_to_gpu_numa_node": bool(numa_bound)},
         "images_per_s": world / (ms_per_step * 1e-3),
-        "ause_auce_images_per_s": world / (score_stream_ms * 1e-3),
-        "ause_auce_ms_per_image": score_stream_ms,
-        "ause_auce_detail": {"streamed_one_view_per_call_ms": score_stream_ms, "synchronous_one_view_per_call_ms": score_ms,
+        "ause_auce_images_per_s": world / (score_b8_ms * 1e-3),
+        "ause_auce_ms_per_image": score_b8_ms,
+        "ause_auce_detail": {"mode_of_headline": "8 views of the workload's size per call (segmented launches), calls streamed",
                              "eight_views_per_call_ms_per_image": score_b8_ms,
-                             "images_per_s_eight_views_per_call": world / (score_b8_ms * 1e-3)},
+                             "streamed_one_view_per_call_ms": score_stream_ms,
+                             "synchronous_one_view_per_call_ms": score_ms,
+                             "images_per_s_one_view_per_call_streamed": world / (score_stream_ms * 1e-3)},
         "roofline": {"kernel": "ub_composite_rays (memset + composite_rays_tma<48> + composite_finalize)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,

@@ -58,13 +58,21 @@ def score():
         imgs = [synthetic.scoring_image(h, w, seed=i, device=dev) for i in range(b)]
         pred = torch.stack([i[0] for i in imgs]); std = torch.stack([i[1] for i in imgs]); gt = torch.stack([i[2] for i in imgs])
         ms = timeit(lambda i: metrics.score_rgb_batch(pred, gt, std), iters=10)
+        pend = []
+        def streamed(i):          # call i+1 is enqueued before call i's record is read back
+            pend.append(metrics.score_rgb_batch_async(pred, gt, std))
+            if len(pend) > 1:
+                pend.pop(0).finish()
+        ms_stream = timeit(streamed, iters=12)
+        for q in pend:
+            q.finish()
         n = h * w
         z = metrics._z_table(dev)
         tp = timeit(lambda i: ops.score_prologue(pred.reshape(-1, 3), gt.reshape(-1, 3), std.reshape(-1), [n] * b, z, 0.03))
         var = (std ** 2).reshape(-1)
         ts = timeit(lambda i: ops.segmented_sort(var, [n] * b, want_perm=True, want_keys=False))
         tk = timeit(lambda i: ops.segmented_sort(var, [n] * b, want_perm=False, want_keys=True))
-        print(json.dumps({"kernel": f"score {w}x{h} x{b}", "ms_total": ms, "images_s": b / ms * 1e3, "ms_prologue": tp,
+        print(json.dumps({"kernel": f"score {w}x{h} x{b}", "ms_total": ms, "images_s": b / ms * 1e3, "ms_streamed": ms_stream, "images_s_streamed": b / ms_stream * 1e3, "ms_prologue": tp,
                           "prologue_GBs": 40 * n * b / tp / 1e6, "ms_sort_pairs": ts, "ms_sort_keys": tk,
                           "sort_pairs_Mkeys_s": n * b / ts / 1e3}))
 
