@@ -41,6 +41,23 @@ def composite():
         print(json.dumps({"kernel": f"composite_rays[{r}]", "ms": ms, "GBs": 1576 * r / ms / 1e6}))
 
 
+def backward():
+    from uncertainty_nerf_gs_b200.autograd import composite_rays_train
+    for r in (4096, R):
+        m = synthetic.ray_samples(r, S, seed=1, device=dev)
+        leaves = {k: m[k].clone().requires_grad_(True) for k in ("density", "rgb", "beta")}
+        def run(i):
+            out = composite_rays_train(leaves["density"], m["deltas"], m["starts"], m["ends"], leaves["rgb"], leaves["beta"])
+            (out["rgb"].sum() + out["rgb_var"].sum() + out["accumulation"].sum()).backward()
+            for v in leaves.values():
+                v.grad = None
+        ms = timeit(run, iters=10)
+        fwd = timeit(lambda i: ops.composite_rays(m["density"], m["deltas"], m["starts"], m["ends"], m["rgb"], m["beta"],
+                                                  eval_mode=False, return_weights=True), iters=10)
+        print(json.dumps({"kernel": f"composite_rays train fwd+bwd [{r} rays]", "ms_fwd_bwd_with_torch_loss": ms, "ms_fwd_only": fwd,
+                          "Mrays_s": r / ms / 1e3}))
+
+
 def reduce():
     for K in (5, 10):
         ms_ = [torch.rand(R, 3, device=dev) for _ in range(K)]
@@ -154,6 +171,6 @@ def cpu():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["composite", "reduce", "score", "laplace", "splat", "cpu"]
+    which = sys.argv[1:] or ["composite", "backward", "reduce", "score", "laplace", "splat", "cpu"]
     for name in which:
         globals()[name]()
