@@ -10,6 +10,8 @@
 // through ONE launch: blockIdx.y selects the key ("job").  The spread uses shifted sums in float64
 // (shift = first member), which is exact for identical members and has no mean^2/var
 // cancellation; torch's CPU kernel (Welford with float64 accumulators) agrees to float32 rounding.
+#include <algorithm>
+
 #include "ub_common.cuh"
 
 namespace ub {
@@ -31,54 +33,69 @@ struct ReduceBatch {
   int num_members;
 };
 
-template <int C>
+// KMAX > 0: all members (K <= KMAX) are loaded before the first use -- up to KMAX * 48 bytes in flight per thread,
+// which is what hides the DRAM latency at the 2 CTAs / SM the float64 arithmetic allows -- and the two float64
+// sums of an element live only while that element is reduced.  KMAX == 0: any K, one member at a time.
+// The order of the float64 additions (members ascending) is the same in both, so the results are identical.
+template <int C, int KMAX>
 __device__ __forceinline__ void reduce_pixels(const float* const* member, int K, const ReduceJob& jb,
                                               long long pix0, int npix, bool vec) {
   constexpr int E = 4 * C;  // elements per thread
-  float x0[E];
-  double s1[E], s2[E];
   const long long e0 = pix0 * C;
   const int ne = npix * C;
-  if (vec) {
-    const float4* src = reinterpret_cast<const float4*>(member[0] + e0);
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-      float4 v = src[j];
-      x0[4 * j + 0] = v.x;
-      x0[4 * j + 1] = v.y;
-      x0[4 * j + 2] = v.z;
-      x0[4 * j + 3] = v.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < E; ++i) x0[i] = i < ne ? member[0][e0 + i] : 0.f;
-  }
-#pragma unroll
-  for (int i = 0; i < E; ++i) {
-    s1[i] = 0.0;
-    s2[i] = 0.0;
-  }
-  for (int k = 1; k < K; ++k) {
-    float x[E];
+  auto load = [&](const float* m, float (&dst)[E]) {
     if (vec) {
-      const float4* src = reinterpret_cast<const float4*>(member[k] + e0);
+      const float4* src = reinterpret_cast<const float4*>(m + e0);
 #pragma unroll
       for (int j = 0; j < C; ++j) {
-        float4 v = src[j];
-        x[4 * j + 0] = v.x;
-        x[4 * j + 1] = v.y;
-        x[4 * j + 2] = v.z;
-        x[4 * j + 3] = v.w;
+        const float4 v = __ldcs(src + j);
+        dst[4 * j + 0] = v.x;
+        dst[4 * j + 1] = v.y;
+        dst[4 * j + 2] = v.z;
+        dst[4 * j + 3] = v.w;
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < E; ++i) x[i] = i < ne ? member[k][e0 + i] : 0.f;
+      for (int i = 0; i < E; ++i) dst[i] = i < ne ? m[e0 + i] : 0.f;
     }
+  };
+  float x0[E];
+  double s1[E], s2[E];
+  if constexpr (KMAX > 0) {
+    float x[KMAX][E];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) load(member[k < K ? k : 0], x[k]);
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-      const double d = (double)x[i] - (double)x0[i];
-      s1[i] += d;
-      s2[i] += d * d;
+      x0[i] = x[0][i];
+      double a = 0.0, b2 = 0.0;
+#pragma unroll
+      for (int k = 1; k < KMAX; ++k) {
+        if (k < K) {
+          const double d = (double)x[k][i] - (double)x0[i];
+          a += d;
+          b2 += d * d;
+        }
+      }
+      s1[i] = a;
+      s2[i] = b2;
+    }
+  } else {
+    load(member[0], x0);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      s1[i] = 0.0;
+      s2[i] = 0.0;
+    }
+    for (int k = 1; k < K; ++k) {
+      float x[E];
+      load(member[k], x);
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const double d = (double)x[i] - (double)x0[i];
+        s1[i] += d;
+        s2[i] += d * d;
+      }
     }
   }
   const double inv_k = 1.0 / (double)K;
@@ -185,13 +202,19 @@ __device__ __forceinline__ void reduce_pixel_any_c(const float* const* member, i
   if (jb.spread_mode != UB_SPREAD_NONE && jb.out_spread) jb.out_spread[px] = C == 1 ? acc : acc / (float)C;
 }
 
-__global__ void __launch_bounds__(256) reduce_members_batched_kernel(const __grid_constant__ ReduceBatch b) {
+// Two instantiations share the launch: FLAT = true carries only the mean-only float32 stream path (about 40
+// registers, full occupancy: most of a view's bytes go through it), FLAT = false the float64 spread paths (128
+// registers, 2 CTAs per SM).  One kernel for both left the streaming jobs at a quarter of the occupancy they need.
+template <bool FLAT>
+__global__ void __launch_bounds__(256, FLAT ? 6 : 2) reduce_members_batched_kernel(const __grid_constant__ ReduceBatch b) {
   const ReduceJob& jb = b.job[blockIdx.y];
   const float* const* member = b.member[blockIdx.y];
   const int K = b.num_members;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (jb.spread_mode == UB_SPREAD_NONE && jb.vec_ok && jb.out_mean) {
+  const bool is_flat = jb.spread_mode == UB_SPREAD_NONE && jb.vec_ok && jb.out_mean;
+  if (is_flat != FLAT) return;
+  if (FLAT) {
     const long long n = jb.num_pixels * jb.channels;
     const long long groups = n / 8;
     for (long long g = tid; g < groups; g += stride) reduce_flat_mean8(member, K, jb.out_mean, g * 8);
@@ -204,19 +227,24 @@ __global__ void __launch_bounds__(256) reduce_members_batched_kernel(const __gri
     }
     return;
   }
+  if constexpr (!FLAT) {
   if (jb.channels == 1 || jb.channels == 3) {
     const long long groups = (jb.num_pixels + 3) / 4;
     for (long long g = tid; g < groups; g += stride) {
       const long long pix0 = g * 4;
       const int npix = (int)min(4LL, jb.num_pixels - pix0);
       const bool vec = jb.vec_ok && npix == 4;
-      if (jb.channels == 1)
-        reduce_pixels<1>(member, K, jb, pix0, npix, vec);
-      else
-        reduce_pixels<3>(member, K, jb, pix0, npix, vec);
+      if (jb.channels == 1) {
+        if (K <= 8) reduce_pixels<1, 8>(member, K, jb, pix0, npix, vec);
+        else reduce_pixels<1, 0>(member, K, jb, pix0, npix, vec);
+      } else {
+        if (K <= 5) reduce_pixels<3, 5>(member, K, jb, pix0, npix, vec);
+        else reduce_pixels<3, 0>(member, K, jb, pix0, npix, vec);
+      }
     }
   } else {
     for (long long px = tid; px < jb.num_pixels; px += stride) reduce_pixel_any_c(member, K, jb, px);
+  }
   }
 }
 
@@ -234,9 +262,11 @@ int ub_reduce_members_batched(const ub_reduce_job* jobs_host, int32_t num_jobs, 
   UB_REQUIRE(num_members >= 1 && num_members <= kMaxBatchMembers, UB_ERR_UNSUPPORTED,
              "reduce_members: num_members %d outside [1, %d]", num_members, kMaxBatchMembers);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  ReduceBatch b{};
-  b.num_members = num_members;
-  long long max_threads = 0;
+  // two compacted job lists, one per kernel instantiation (a block of the wrong kind would only launch and exit)
+  ReduceBatch flat{}, spread{};
+  flat.num_members = spread.num_members = num_members;
+  int n_flat = 0, n_spread = 0;
+  long long flat_threads = 0, spread_threads = 0;
   for (int j = 0; j < num_jobs; ++j) {
     const ub_reduce_job& in = jobs_host[j];
     UB_REQUIRE(in.members_host != nullptr, UB_ERR_BAD_ARG, "reduce_members: job %d members_host is NULL", j);
@@ -250,26 +280,36 @@ int ub_reduce_members_batched(const ub_reduce_job* jobs_host, int32_t num_jobs, 
     for (int k = 0; k < num_members; ++k) {
       UB_REQUIRE(in.members_host[k] != nullptr || in.num_pixels == 0, UB_ERR_BAD_ARG,
                  "reduce_members: job %d member %d is NULL", j, k);
-      b.member[j][k] = in.members_host[k];
       vec_ok = vec_ok && al16(in.members_host[k]);
     }
-    b.job[j].num_pixels = in.num_pixels;
-    b.job[j].channels = in.channels;
-    b.job[j].spread_mode = in.out_spread ? in.spread_mode : UB_SPREAD_NONE;
-    b.job[j].out_mean = in.out_mean;
-    b.job[j].out_spread = in.out_spread;
-    b.job[j].vec_ok = vec_ok ? 1 : 0;
-    long long threads = (in.channels == 1 || in.channels == 3) ? (in.num_pixels + 3) / 4 : in.num_pixels;
-    if (b.job[j].spread_mode == UB_SPREAD_NONE && vec_ok) threads = (in.num_pixels * in.channels + 7) / 8;
-    if (threads > max_threads) max_threads = threads;
+    const int mode = in.out_spread ? in.spread_mode : UB_SPREAD_NONE;
+    const bool is_flat = mode == UB_SPREAD_NONE && vec_ok && in.out_mean != nullptr;
+    ReduceBatch& b = is_flat ? flat : spread;
+    const int slot = is_flat ? n_flat++ : n_spread++;
+    for (int k = 0; k < num_members; ++k) b.member[slot][k] = in.members_host[k];
+    b.job[slot].num_pixels = in.num_pixels;
+    b.job[slot].channels = in.channels;
+    b.job[slot].spread_mode = mode;
+    b.job[slot].out_mean = in.out_mean;
+    b.job[slot].out_spread = in.out_spread;
+    b.job[slot].vec_ok = vec_ok ? 1 : 0;
+    if (is_flat) {
+      flat_threads = std::max(flat_threads, (long long)((in.num_pixels * in.channels + 7) / 8));
+    } else {
+      const long long t = (in.channels == 1 || in.channels == 3) ? (in.num_pixels + 3) / 4 : in.num_pixels;
+      spread_threads = std::max(spread_threads, t);
+    }
   }
-  if (max_threads == 0) return UB_OK;
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  long long blocks = (max_threads + 255) / 256;
   const long long cap = (long long)sms * 8;
-  if (blocks > cap) blocks = cap;
-  dim3 grid((unsigned)blocks, (unsigned)num_jobs);
-  reduce_members_batched_kernel<<<grid, 256, 0, stream>>>(b);
+  if (n_flat > 0 && flat_threads > 0) {
+    dim3 grid((unsigned)std::min(cap, (flat_threads + 255) / 256), (unsigned)n_flat);
+    reduce_members_batched_kernel<true><<<grid, 256, 0, stream>>>(flat);
+  }
+  if (n_spread > 0 && spread_threads > 0) {
+    dim3 grid((unsigned)std::min(cap, (spread_threads + 255) / 256), (unsigned)n_spread);
+    reduce_members_batched_kernel<false><<<grid, 256, 0, stream>>>(spread);
+  }
   return check_launch("reduce_members");
 }
 

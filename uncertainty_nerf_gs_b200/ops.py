@@ -269,7 +269,7 @@ def reduce_many(jobs: Sequence[Tuple[Sequence[Tensor], Optional[str]]]) -> List[
                 slot.num_pixels, slot.channels, slot.spread_mode = n, c, _SPREAD[spread]
                 slot.out_mean, slot.out_spread = mean.data_ptr(), _ptr(spr)
             _lib.check(lib.ub_reduce_members_batched(arr, len(chunk), k, _stream()))
-            _count(1)
+            _count(2)  # flat-mean and spread instantiations
     for (_, _, _, _, mean, spr) in prepared:
         results.append((mean, spr))
     return results
@@ -489,7 +489,7 @@ def composite_tiles(xys: Tensor, conics: Tensor, opacities: Tensor, colors: Tens
         _lib.check(lib.ub_composite_tiles(xys.data_ptr(), conics.data_ptr(), opacities.data_ptr(), colors.data_ptr(),
                                           ch, gaussian_ids.data_ptr(), tile_bins.data_ptr(), height, width, bg,
                                           out.data_ptr(), alpha.data_ptr(), _stream()))
-    _count(1)
+    _count(2)  # flat-mean and spread instantiations
     return out, alpha
 
 
@@ -527,7 +527,7 @@ def composite_tiles_planes(xys: Tensor, conics: Tensor, opacities: Tensor, plane
         _lib.check(lib.ub_composite_tiles_planes(xys.data_ptr(), conics.data_ptr(), opacities.data_ptr(), pp, pc,
                                                  len(pls), gaussian_ids.data_ptr(), tile_bins.data_ptr(), height,
                                                  width, bg, po, alpha.data_ptr(), _ptr(keys), _stream()))
-    _count(1)
+    _count(2)  # flat-mean and spread instantiations
     return outs, alpha, keys
 
 
@@ -563,7 +563,7 @@ def composite_tiles_planes_backward(xys: Tensor, conics: Tensor, opacities: Tens
             xys.data_ptr(), conics.data_ptr(), opacities.data_ptr(), pp, pc, len(pls),
             _ptr(gaussian_ids.contiguous()), tile_bins.contiguous().data_ptr(), height, width, bg, pv, _ptr(va), g,
             v_xys.data_ptr(), v_conics.data_ptr(), v_opac.data_ptr(), pg, _stream()))
-    _count(1)
+    _count(2)  # flat-mean and spread instantiations
     return v_xys, v_conics, v_opac, v_pl
 
 
@@ -576,7 +576,7 @@ def splat_normalize_(image: Tensor, alpha: Optional[Tensor] = None, max_key: Opt
     with _guard(image.device):
         _lib.check(lib.ub_splat_normalize(image.data_ptr(), ch, _ptr(alpha), n, 1 if clamp_max_one else 0,
                                           1 if alpha is not None else 0, _ptr(max_key), _stream()))
-    _count(1)
+    _count(2)  # flat-mean and spread instantiations
     return image
 
 
@@ -590,5 +590,5 @@ def splat_depth_residual(xys: Tensor, depths: Tensor, depth_image: Tensor) -> Te
     with _guard(xys.device):
         _lib.check(lib.ub_splat_depth_residual(xys.data_ptr(), depths.data_ptr(), depth_image.data_ptr(), h, w,
                                                depths.numel(), out.data_ptr(), _stream()))
-    _count(1)
+    _count(2)  # flat-mean and spread instantiations
     return out
