@@ -37,6 +37,20 @@ struct ReduceBatch {
 // which is what hides the DRAM latency at the 2 CTAs / SM the float64 arithmetic allows -- and the two float64
 // sums of an element live only while that element is reduced.  KMAX == 0: any K, one member at a time.
 // The order of the float64 additions (members ascending) is the same in both, so the results are identical.
+// (float)sqrt(v) for a float64 v without the ~35-instruction DSQRT: float32 rsqrt estimate, one float64 Newton step
+// (relative error ~1e-14, far below the float32 rounding of the result); zero, subnormal-as-float, huge and NaN
+// arguments take the library sqrt.
+__device__ __forceinline__ float sqrt_to_float(double v) {
+  const float vf = (float)v;
+  if (vf > 1e-30f && vf < 1e30f) {
+    const double y = (double)rsqrtf(vf);
+    double s = v * y;
+    s = fma(0.5 * y, fma(-s, s, v), s);
+    return (float)s;
+  }
+  return (float)sqrt(v);
+}
+
 template <int C, int KMAX>
 __device__ __forceinline__ void reduce_pixels(const float* const* member, int K, const ReduceJob& jb,
                                               long long pix0, int npix, bool vec) {
@@ -99,6 +113,7 @@ __device__ __forceinline__ void reduce_pixels(const float* const* member, int K,
     }
   }
   const double inv_k = 1.0 / (double)K;
+  const double inv_km1 = 1.0 / (double)(K - 1);
   float mean[E];
 #pragma unroll
   for (int i = 0; i < E; ++i) mean[i] = (float)((double)x0[i] + s1[i] * inv_k);
@@ -122,9 +137,10 @@ __device__ __forceinline__ void reduce_pixels(const float* const* member, int K,
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const int i = px * C + c;
-        double var = (s2[i] - s1[i] * s1[i] * inv_k) / (double)(K - 1);  // K == 1 -> NaN like torch
+        // * 1/(K-1) instead of a float64 division (<= 1 ulp of a double apart); K == 1 -> 0 * inf = NaN like torch
+        double var = (s2[i] - s1[i] * s1[i] * inv_k) * inv_km1;
         if (var < 0.0) var = 0.0;
-        const float v = jb.spread_mode == UB_SPREAD_STD ? (float)sqrt(var) : (float)var;
+        const float v = jb.spread_mode == UB_SPREAD_STD ? sqrt_to_float(var) : (float)var;
         acc = c == 0 ? v : acc + v;
       }
       spread[px] = C == 1 ? acc : acc / (float)C;
