@@ -283,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.profiler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ops.LAUNCH_COUNT - launches0
-    comp_ms = [a.elapsed_time(b) for a, b in timers]
+    comp_ms = [a.elapsed_time(b) / cnt for a, b, cnt in timers for _ in range(cnt)]   # per compositing launch
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -300,7 +300,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(2):
         pipeline.render_members(members, h, w, CHUNK, solo_timers)
     torch.cuda.synchronize()
-    solo_ms = [a.elapsed_time(b) for a, b in solo_timers[m:]]
+    solo_ms = [a.elapsed_time(b) / cnt for a, b, cnt in solo_timers[1:]]
     comp_solo_ms = sum(solo_ms) / len(solo_ms)
 
     pred_img = pipeline.render_members(members[:1], h, w, CHUNK)[0]
@@ -400,7 +400,8 @@ def run_ours(args, rank, world, local_rank):
                              "streamed_one_view_per_call_ms": score_stream_ms,
                              "synchronous_one_view_per_call_ms": score_ms,
                              "images_per_s_one_view_per_call_streamed": world / (score_stream_ms * 1e-3)},
-        "roofline": {"kernel": "ub_composite_rays (memset + composite_rays_tma<48> + composite_finalize)",
+        "roofline": {"kernel": "composite_rays_tma<48,7,14> inside ub_composite_rays_batch (per launch = the batched call of "
+                               "M members incl. its one memset and one finalize launch, divided by M)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
                      "bytes_per_ray": BYTES_PER_RAY, "rays_per_launch": R, "ms_per_launch": comp_avg_ms,

@@ -99,6 +99,15 @@ size_t ub_composite_rays_workspace_bytes(int64_t num_rays, int64_t rays_per_chun
 int ub_composite_rays(const ub_composite_rays_args* args, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* The same for up to UB_MAX_COMPOSITE_BATCH independent ray batches (the M members of one view:
+ * ensemble_pipeline.py:150-157 renders them one after the other): one workspace memset, the compositing kernels
+ * back to back, one finalize launch for all batches.  The workspace is one 16-byte aligned region of
+ * ub_composite_rays_batch_workspace_bytes(args, n) bytes. */
+#define UB_MAX_COMPOSITE_BATCH 8
+size_t ub_composite_rays_batch_workspace_bytes(const ub_composite_rays_args* args, int32_t num_batches);
+int ub_composite_rays_batch(const ub_composite_rays_args* args, int32_t num_batches, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* Backward of ub_composite_rays in training mode (eval_mode 0, beta used as is) w.r.t. density, sample
  * colours and beta: what `ns-train` needs to run active-nerfacto through the fused compositor (losses:
  * models/activenerfacto/activenerfacto_model.py:155-191; the interlevel / distortion losses consume the

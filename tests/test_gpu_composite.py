@@ -224,3 +224,33 @@ def test_full_view_properties(built_library):
     b = ops.composite_rays(*[inp[k][half:] for k in ("density", "deltas", "starts", "ends", "rgb", "beta")])
     for k in ("rgb", "accumulation", "depth", "rgb_var", "depth_var"):
         assert torch.equal(torch.cat([a[k], b[k]]), o[k]), k
+
+
+@pytest.mark.parametrize("num_samples,chunk", [(48, 64), (20, 0), (64, 128)])
+def test_batched_members_equal_individual_calls(built_library, num_samples, chunk):
+    """ub_composite_rays_batch (one memset, M kernels, one finalize launch) must return, bit for bit, what M
+    separate ub_composite_rays calls return -- including the per-chunk clip bounds of every member and the
+    inf-beta redo in chunks that held a NaN."""
+    from uncertainty_nerf_gs_b200 import ops
+
+    R = 333
+    members = []
+    for i in range(5):
+        m = synthetic.ray_samples(R, num_samples, seed=40 + i, device="cuda")
+        if i == 2:
+            m["beta"][7, 3] = float("nan")
+            m["beta"][9, 1] = float("inf")
+            m["starts"][:40] += 3.0
+            m["ends"][:40] += 3.0
+        members.append(m)
+    keys = ("density", "deltas", "starts", "ends", "rgb", "beta")
+    many = ops.composite_rays_many([[m[k] for k in keys] for m in members], rays_per_chunk=chunk or None,
+                                   background=(0.1, 0.5, 0.9))
+    for m, got in zip(members, many):
+        one = ops.composite_rays(*[m[k] for k in keys], rays_per_chunk=chunk or None, background=(0.1, 0.5, 0.9))
+        for k, v in got.items():
+            assert torch.equal(torch.nan_to_num(v, nan=-5.0), torch.nan_to_num(one[k], nan=-5.0)), k
+    img = ops.composite_rays_many([[m[k] for k in keys] for m in members[:2]], image_hw=(9, 37))
+    assert img[1]["rgb"].shape == (9, 37, 3) and img[0]["depth_std"].shape == (9, 37, 1)
+    nine = ops.composite_rays_many([[members[i % 5][k] for k in keys] for i in range(9)])   # more than one C batch
+    assert len(nine) == 9 and torch.equal(nine[8]["rgb"], nine[3]["rgb"])

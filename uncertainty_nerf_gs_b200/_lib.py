@@ -21,6 +21,7 @@ UB_ACT_IDENTITY, UB_ACT_SIGMOID, UB_ACT_EXP = 0, 1, 2
 UB_PROLOGUE_NSUMS = 5
 UB_MAX_MEMBERS = 32
 UB_MAX_REDUCE_JOBS = 16
+UB_MAX_COMPOSITE_BATCH = 8
 UB_TILE = 16
 
 fp = C.c_void_p  # device pointers travel as void*
@@ -84,6 +85,8 @@ SIGNATURES = {
     "ub_composite_rays_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "ub_composite_rays": (C.c_int, [C.POINTER(CompositeRaysArgs), fp, C.c_size_t, fp]),
     "ub_composite_rays_backward": (C.c_int, [C.POINTER(CompositeRaysBwdArgs), fp]),
+    "ub_composite_rays_batch_workspace_bytes": (C.c_size_t, [fp, C.c_int32]),
+    "ub_composite_rays_batch": (C.c_int, [fp, C.c_int32, fp, C.c_size_t, fp]),
     "ub_render_weights_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "ub_render_weights": (C.c_int, [C.POINTER(RenderWeightsArgs), fp, C.c_size_t, fp]),
     "ub_average_sampled_weights": (C.c_int, [fp, fp, fp, fp, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, fp, fp]),

@@ -588,9 +588,7 @@ __global__ void __launch_bounds__(256) composite_rays_generic(const CompositePar
 // Finalize: clip the expected depth to the chunk's [min(steps), max(steps)] (torch.clip keeps a
 // NaN input); and, in chunks whose beta contained a NaN, redo rgb_var for the (rare) rays whose
 // beta also holds +-inf, because the reference then applied nan_to_num to the whole chunk.
-__global__ void __launch_bounds__(256) composite_finalize(const CompositeParams p) {
-  const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ray >= p.num_rays) return;
+__device__ __forceinline__ void finalize_ray(const CompositeParams& p, long long ray) {
   const long long chunk = p.rays_per_chunk > 0 ? ray / p.rays_per_chunk : 0;
   const unsigned* ws = p.chunk_ws + chunk * 4;
   if (p.o_exp) {
@@ -617,6 +615,21 @@ __global__ void __launch_bounds__(256) composite_finalize(const CompositeParams 
       if (p.o_rgb_std) p.o_rgb_std[ray] = sqrtf(var);
     }
   }
+}
+
+__global__ void __launch_bounds__(256) composite_finalize(const CompositeParams p) {
+  const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray < p.num_rays) finalize_ray(p, ray);
+}
+
+// the finalize passes of up to UB_MAX_COMPOSITE_BATCH independent ray batches in one launch (blockIdx.y = batch)
+struct FinalizeBatch {
+  CompositeParams p[UB_MAX_COMPOSITE_BATCH];
+};
+__global__ void __launch_bounds__(256) composite_finalize_batch(const __grid_constant__ FinalizeBatch b) {
+  const CompositeParams& p = b.p[blockIdx.y];
+  const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray < p.num_rays) finalize_ray(p, ray);
 }
 
 static size_t chunk_ws_bytes(long long num_rays, long long rays_per_chunk) {
@@ -663,8 +676,9 @@ size_t ub_render_weights_workspace_bytes(int64_t num_rays, int64_t rays_per_chun
   return ub::chunk_ws_bytes(num_rays, rays_per_chunk);
 }
 
-int ub_composite_rays(const ub_composite_rays_args* a, void* workspace, size_t workspace_bytes,
-                      void* stream_v) {
+// validation + parameter block of one ray batch (no launches)
+static int composite_prepare(const ub_composite_rays_args* a, void* workspace, size_t workspace_bytes,
+                             ub::CompositeParams& p) {
   using namespace ub;
   UB_REQUIRE(a != nullptr, UB_ERR_BAD_ARG, "composite_rays: args is NULL");
   UB_REQUIRE(a->num_rays >= 0 && a->num_samples >= 1, UB_ERR_BAD_ARG,
@@ -681,9 +695,7 @@ int ub_composite_rays(const ub_composite_rays_args* a, void* workspace, size_t w
   const size_t need = chunk_ws_bytes(a->num_rays, a->rays_per_chunk);
   UB_REQUIRE(workspace != nullptr && workspace_bytes >= need, UB_ERR_WORKSPACE,
              "composite_rays: workspace %zu B < required %zu B", workspace_bytes, need);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-
-  CompositeParams p{};
+  p = CompositeParams{};
   p.density = a->density;
   p.deltas = a->deltas;
   p.starts = a->starts;
@@ -710,12 +722,15 @@ int ub_composite_rays(const ub_composite_rays_args* a, void* workspace, size_t w
   p.o_dstd = a->out_depth_std;
   p.o_w = a->out_weights;
   p.chunk_ws = static_cast<unsigned*>(workspace);
+  p.tiles_per_chunk = a->rays_per_chunk > 0 ? (int)(a->rays_per_chunk / kRaysPerTile) : 0;
+  return UB_OK;
+}
 
-  if (cudaMemsetAsync(workspace, 0, need, stream) != cudaSuccess) return check_launch("composite_rays memset");
-
+// the compositing kernel of one prepared batch (the chunk workspace must already be zero)
+static int composite_launch_main(const ub_composite_rays_args* a, const ub::CompositeParams& p, cudaStream_t stream) {
+  using namespace ub;
   const bool chunk_ok = (a->rays_per_chunk <= 0 || a->rays_per_chunk % kRaysPerTile == 0) &&
                         a->num_rays < (1LL << 31) - 64;
-  p.tiles_per_chunk = a->rays_per_chunk > 0 ? (int)(a->rays_per_chunk / kRaysPerTile) : 0;
   const bool align_ok = aligned16(a->density) && aligned16(a->deltas) && aligned16(a->starts) &&
                         aligned16(a->ends) && aligned16(a->rgb) &&
                         (a->beta == nullptr || aligned16(a->beta)) &&
@@ -749,10 +764,74 @@ int ub_composite_rays(const ub_composite_rays_args* a, void* workspace, size_t w
     composite_rays_generic<false><<<(unsigned)blocks, 256, 0, stream>>>(p);
     rc = check_launch("composite_rays_generic");
   }
+  return rc;
+}
+
+int ub_composite_rays(const ub_composite_rays_args* a, void* workspace, size_t workspace_bytes,
+                      void* stream_v) {
+  using namespace ub;
+  CompositeParams p{};
+  int rc = composite_prepare(a, workspace, workspace_bytes, p);
+  if (rc != UB_OK || a->num_rays == 0) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const size_t need = chunk_ws_bytes(a->num_rays, a->rays_per_chunk);
+  if (cudaMemsetAsync(workspace, 0, need, stream) != cudaSuccess) return check_launch("composite_rays memset");
+  rc = composite_launch_main(a, p, stream);
   if (rc != UB_OK) return rc;
   const unsigned fblocks = (unsigned)((a->num_rays + 255) / 256);
   composite_finalize<<<fblocks, 256, 0, stream>>>(p);
   return check_launch("composite_finalize");
+}
+
+static size_t batch_ws_slice(const ub_composite_rays_args& a) {
+  return ub::align_up(ub::chunk_ws_bytes(a.num_rays, a.rays_per_chunk), 16);
+}
+
+size_t ub_composite_rays_batch_workspace_bytes(const ub_composite_rays_args* args, int32_t num_batches) {
+  size_t total = 0;
+  if (args == nullptr) return 16;
+  for (int i = 0; i < num_batches; ++i) total += batch_ws_slice(args[i]);
+  return total > 0 ? total : 16;
+}
+
+int ub_composite_rays_batch(const ub_composite_rays_args* args, int32_t num_batches, void* workspace,
+                            size_t workspace_bytes, void* stream_v) {
+  using namespace ub;
+  UB_REQUIRE(args != nullptr && num_batches >= 1 && num_batches <= UB_MAX_COMPOSITE_BATCH, UB_ERR_BAD_ARG,
+             "composite_rays_batch: between 1 and %d batches", UB_MAX_COMPOSITE_BATCH);
+  const size_t need = ub_composite_rays_batch_workspace_bytes(args, num_batches);
+  UB_REQUIRE(workspace != nullptr && workspace_bytes >= need, UB_ERR_WORKSPACE,
+             "composite_rays_batch: workspace %zu B < required %zu B", workspace_bytes, need);
+  UB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, UB_ERR_BAD_ARG,
+             "composite_rays_batch: workspace must be 16-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  FinalizeBatch fb{};
+  char* ws = static_cast<char*>(workspace);
+  long long max_rays = 0;
+  int live = 0;
+  const ub_composite_rays_args* live_args[UB_MAX_COMPOSITE_BATCH];
+  for (int i = 0; i < num_batches; ++i) {
+    const size_t slice = batch_ws_slice(args[i]);
+    CompositeParams p{};
+    int rc = composite_prepare(&args[i], ws, slice, p);
+    ws += slice;
+    if (rc != UB_OK) return rc;
+    if (args[i].num_rays == 0) continue;
+    fb.p[live] = p;
+    live_args[live] = &args[i];
+    ++live;
+    if (args[i].num_rays > max_rays) max_rays = args[i].num_rays;
+  }
+  if (live == 0) return UB_OK;
+  // one memset, the compositing kernels back to back, one finalize launch for all batches
+  if (cudaMemsetAsync(workspace, 0, need, stream) != cudaSuccess) return check_launch("composite_rays_batch memset");
+  for (int i = 0; i < live; ++i) {
+    int rc = composite_launch_main(live_args[i], fb.p[i], stream);
+    if (rc != UB_OK) return rc;
+  }
+  dim3 grid((unsigned)((max_rays + 255) / 256), (unsigned)live);
+  composite_finalize_batch<<<grid, 256, 0, stream>>>(fb);
+  return check_launch("composite_finalize_batch");
 }
 
 int ub_render_weights(const ub_render_weights_args* a, void* workspace, size_t workspace_bytes,

@@ -48,6 +48,21 @@ def active_nerfacto_outputs(density: Tensor, deltas: Tensor, starts: Tensor, end
     return out
 
 
+def active_nerfacto_outputs_many(members: Sequence[Dict[str, Tensor]], *, background="last_sample",
+                                 rays_per_chunk: Optional[int] = None, image_hw: Optional[Tuple[int, int]] = None
+                                 ) -> List[Dict[str, Tensor]]:
+    """``active_nerfacto_outputs`` (eval mode) for the M members of one view in one batched call
+    (``ub_composite_rays_batch``).  ``members[i]`` holds ``density, deltas, starts, ends, rgb, beta``; every
+    returned dict has the reference's keys in the reference's order."""
+    res = ops.composite_rays_many([(m["density"], m["deltas"], m["starts"], m["ends"], m["rgb"], m["beta"])
+                                   for m in members], background=background, beta_mode="nan_guard",
+                                  rays_per_chunk=rays_per_chunk, eval_mode=True, image_hw=image_hw)
+    return [{"rgb": o["rgb"], "accumulation": o["accumulation"], "depth": o["depth"],
+             "expected_depth": o["expected_depth"], "density": m["density"], "rgb_var": o["rgb_var"],
+             "rgb_std": o["rgb_std"], "depth_var": o["depth_var"], "depth_std": o["depth_std"]}
+            for o, m in zip(res, members)]
+
+
 def laplace_outputs_unc(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor, rgb: Tensor,
                         rgb_var: Tensor, *, averaged_weights: Optional[Tensor] = None,
                         density_var: Optional[Tensor] = None, density_noise: Optional[Tensor] = None,

@@ -168,6 +168,88 @@ def composite_rays(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor
     return out
 
 
+def composite_rays_many(batches: Sequence[Sequence[Tensor]], *, background: Union[str, Sequence[float]] = "last_sample",
+                        beta_mode: str = "nan_guard", rays_per_chunk: Optional[int] = None, eval_mode: bool = True,
+                        image_hw: Optional[Tuple[int, int]] = None) -> List[Dict[str, Tensor]]:
+    """``composite_rays`` for several independent ray batches of one shape -- the M members of a view -- through
+    ``ub_composite_rays_batch``: one workspace memset, the compositing kernels back to back, one finalize launch,
+    one host call.  ``batches[i] = (density, deltas, starts, ends, rgb, beta)``; returns one output dict per batch."""
+    lib = _lib.load()
+    n = len(batches)
+    if n < 1:
+        return []
+    if n > _lib.UB_MAX_COMPOSITE_BATCH:
+        out: List[Dict[str, Tensor]] = []
+        for lo in range(0, n, _lib.UB_MAX_COMPOSITE_BATCH):
+            out += composite_rays_many(batches[lo:lo + _lib.UB_MAX_COMPOSITE_BATCH], background=background,
+                                       beta_mode=beta_mode, rays_per_chunk=rays_per_chunk, eval_mode=eval_mode,
+                                       image_hw=image_hw)
+        return out
+    first = batches[0][0]
+    if not isinstance(first, torch.Tensor) or first.dim() not in (2, 3):
+        raise ValueError("density: expected [R, S] or [R, S, 1]")
+    R, S = int(first.shape[0]), int(first.shape[1])
+    dev = first.device
+    if isinstance(background, str):
+        if background not in _BG_MODES:
+            raise ValueError(f"unsupported background {background!r}")
+        bg_mode, bg = _BG_MODES[background], None
+    else:
+        bg = [float(v) for v in background]
+        if len(bg) != 3:
+            raise ValueError("fixed background must have 3 components")
+        bg_mode = _lib.UB_BG_FIXED
+    if image_hw is not None:
+        if image_hw[0] * image_hw[1] != R:
+            raise ValueError(f"image_hw {tuple(image_hw)} does not hold {R} rays")
+        lead = (int(image_hw[0]), int(image_hw[1]))
+    else:
+        lead = (R,)
+    arr = (_lib.CompositeRaysArgs * n)()
+    keep = []
+    for a, batch in zip(arr, batches):
+        density, deltas, starts, ends, rgb, beta = batch
+        density = _ray_stream(density, "density", R, S)
+        deltas = _ray_stream(deltas, "deltas", R, S)
+        starts = _ray_stream(starts, "starts", R, S)
+        ends = _ray_stream(ends, "ends", R, S)
+        rgb = _ray_stream(rgb, "rgb", R, S, 3)
+        beta = _ray_stream(beta, "beta", R, S)
+        keep.append((density, deltas, starts, ends, rgb, beta))
+        a.density, a.deltas, a.starts, a.ends = density.data_ptr(), deltas.data_ptr(), starts.data_ptr(), ends.data_ptr()
+        a.rgb, a.beta = rgb.data_ptr(), beta.data_ptr()
+        a.num_rays, a.num_samples = R, S
+        a.background_mode = bg_mode
+        if bg is not None:
+            a.background_rgb = (C.c_float * 3)(*bg)
+        a.beta_mode = _BETA_MODES[beta_mode]
+        a.rays_per_chunk = int(rays_per_chunk) if rays_per_chunk else 0
+        a.eval_mode = 1 if eval_mode else 0
+    ws_bytes = lib.ub_composite_rays_batch_workspace_bytes(arr, n)
+    ws_floats = (ws_bytes + 3) // 4
+    per = 10 * R
+    buf = torch.empty(n * per + ws_floats + 4, device=dev)
+    base = buf.data_ptr()
+    f = 4 * R
+    outs = []
+    for i, a in enumerate(arr):
+        b0 = base + 4 * per * i
+        a.out_rgb, a.out_accumulation = b0, b0 + 3 * f
+        a.out_depth, a.out_expected_depth = b0 + 4 * f, b0 + 5 * f
+        a.out_rgb_var, a.out_rgb_std = b0 + 6 * f, b0 + 7 * f
+        a.out_depth_var, a.out_depth_std = b0 + 8 * f, b0 + 9 * f
+        rows = buf[per * i + 3 * R:per * (i + 1)].view(7, *lead, 1).unbind(0)
+        outs.append({"rgb": buf[per * i:per * i + 3 * R].view(*lead, 3), "accumulation": rows[0], "depth": rows[1],
+                     "expected_depth": rows[2], "rgb_var": rows[3], "rgb_std": rows[4], "depth_var": rows[5],
+                     "depth_std": rows[6]})
+    ws_ptr = base + 4 * per * n
+    ws_ptr += (-ws_ptr) % 16
+    with _guard(dev):
+        _lib.check(lib.ub_composite_rays_batch(arr, n, ws_ptr, ws_bytes, _stream()))
+    _count(n + 1 if R > 0 else 0)
+    return outs
+
+
 def render_weights(weights: Tensor, starts: Tensor, ends: Tensor, *, rays_per_chunk: Optional[int] = None,
                    want: Sequence[str] = ("depth",)) -> Dict[str, Tensor]:
     """Median depth / expected depth / accumulation / depth variance from given weights

@@ -40,24 +40,22 @@ def render_members(members: Sequence[Dict[str, Tensor]], height: int, width: int
                    timers: Optional[List[Tuple[torch.cuda.Event, torch.cuda.Event]]] = None,
                    keep_per_sample: bool = False) -> List[Dict[str, Tensor]]:
     """Composite every member's ray samples (active-nerfacto ``get_outputs`` per eval chunk) and view the
-    per-ray outputs as ``[H, W, C]`` like ``get_outputs_for_camera`` does.  Per-sample pass-through keys
-    (``PER_SAMPLE_KEYS``) are dropped unless ``keep_per_sample``."""
-    outs = []
-    for m in members:
-        if timers is not None:
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record()
-        o = mo.active_nerfacto_outputs(m["density"], m["deltas"], m["starts"], m["ends"], m["rgb"], m["beta"],
-                                       rays_per_chunk=rays_per_chunk, image_hw=(height, width))
-        if timers is not None:
-            t1.record()
-            timers.append((t0, t1))
+    per-ray outputs as ``[H, W, C]`` like ``get_outputs_for_camera`` does: one batched call for all members
+    (one workspace memset, M compositing kernels, one finalize launch).  Per-sample pass-through keys
+    (``PER_SAMPLE_KEYS``) are dropped unless ``keep_per_sample``.  ``timers`` receives ``(start, end, M)``."""
+    if timers is not None:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+    outs = mo.active_nerfacto_outputs_many(members, rays_per_chunk=rays_per_chunk, image_hw=(height, width))
+    if timers is not None:
+        t1.record()
+        timers.append((t0, t1, len(members)))     # one bracket around the batched call: elapsed / count per launch
+    for o in outs:
         if keep_per_sample:
             o["density"] = o["density"].view(height, width, -1)
         else:
             for k in PER_SAMPLE_KEYS:
                 o.pop(k, None)
-        outs.append(o)
     return outs
 
 
