@@ -350,6 +350,18 @@ int ub_splat_depth_residual(const float* xys, const float* depths, const float* 
                             float* out_sq_residual, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (a15) Inputs of the depth scorer.  Replaces the per-view torch lines of get_unc_metrics_depth
+ * (scripts/eval_uncertainty.py:461-462 scale, :511-513 clamp to [1e-3, max gt], :552-560 keep gt > 0).
+ * depth, depth_std, depth_gt [B, N] float32, scales [B] float32 (DEVICE).  Outputs: the kept pixels of all views
+ * in row-major order, view after view (capacity B*N each), and out_offsets [B+1] int64 (DEVICE): view b owns
+ * [out_offsets[b], out_offsets[b+1]) -- ragged segments for ub_score_prologue / ub_segmented_sort.
+ * ---------------------------------------------------------------------------------------- */
+size_t ub_depth_prepare_workspace_bytes(int32_t num_views, int64_t pixels_per_view);
+int ub_depth_prepare(const float* depth, const float* depth_std, const float* depth_gt, const float* scales,
+                     int32_t num_views, int64_t pixels_per_view, float* out_pred, float* out_std, float* out_gt,
+                     int64_t* out_offsets, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * (f1) Backward of ub_composite_tiles_planes, for training through the fused pass (the reference's losses,
  * activesplatfacto_model.py:369-441, read outputs["rgb"] and outputs["uncertainty"]; gsplat supplies this
  * gradient inside rasterize_gaussians' autograd function).

@@ -96,3 +96,37 @@ def test_philox_draws_are_statistically_sane(built_library):
     ref = torch.stack([oc.get_weights(s, inp["deltas"]) for s in sampled]).mean(0)
     assert float((out - ref).abs().mean()) < 2e-3
     assert abs(float(out.sum() - ref.sum())) / float(ref.sum()) < 5e-3
+
+
+def test_depth_prepare_is_the_reference_torch_lines(built_library):
+    """ub_depth_prepare against the reference's own per-view torch lines (scale, clamp, minimum, boolean mask),
+    bit for bit: ragged views, a view without any valid pixel, a NaN in a ground truth, sizes that are not a
+    multiple of the block, pixel order preserved."""
+    from uncertainty_nerf_gs_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    for n in (1, 1023, 1024, 5000):
+        b = 4
+        gt = torch.rand(b, n, generator=g) * 8 + 0.5
+        gt[torch.rand(b, n, generator=g) < 0.4] = 0.0
+        gt[1] = 0.0                                             # a view with nothing to score
+        if n > 10:
+            gt[2, 7] = float("nan")                             # torch: max() and minimum() propagate it
+            gt[3, 3] = -2.0
+        depth = torch.randn(b, n, generator=g) * 3
+        depth[0, 0] = float("nan")
+        depth[3, n // 2] = 1e6
+        std = torch.rand(b, n, generator=g)
+        scales = [2.5, 1.0, 0.7, 3.25]
+        pred, sd, gg, lens = ops.depth_prepare(depth.cuda(), std.cuda(), gt.cuda(), scales)
+        want_p, want_s, want_g, want_l = [], [], [], []
+        for i in range(b):
+            max_d = gt[i].max().float()
+            d = scales[i] * depth[i]
+            mask = gt[i] > 0
+            dm = torch.minimum(torch.clamp(d[mask], min=1e-3), max_d)
+            want_p.append(dm); want_s.append((scales[i] * std[i])[mask]); want_g.append(gt[i][mask]); want_l.append(int(mask.sum()))
+        assert lens == want_l
+        for got, want in ((pred, want_p), (sd, want_s), (gg, want_g)):
+            w = torch.cat(want)
+            assert torch.equal(torch.nan_to_num(got.cpu(), nan=-9.0), torch.nan_to_num(w, nan=-9.0))

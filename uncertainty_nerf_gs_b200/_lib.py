@@ -101,6 +101,8 @@ SIGNATURES = {
                                      fp, C.c_int32, fp, fp, C.c_size_t, fp]),
     "ub_laplace_ll_moments": (C.c_int, [fp, C.c_int64, C.c_int32, C.c_int32, fp, C.c_int32, C.c_int32,
                                         fp, fp, fp, fp]),
+    "ub_depth_prepare_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
+    "ub_depth_prepare": (C.c_int, [fp, fp, fp, fp, C.c_int32, C.c_int64, fp, fp, fp, fp, fp, C.c_size_t, fp]),
     "ub_project_gaussians": (C.c_int, [fp, fp, C.c_float, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                        C.c_int32, C.c_float, C.c_int64, fp, fp, fp, fp, fp, fp, fp, fp]),
     "ub_spherical_harmonics": (C.c_int, [C.c_int32, C.c_int32, fp, fp, C.c_int64, fp, fp]),

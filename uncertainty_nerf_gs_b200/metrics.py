@@ -337,30 +337,17 @@ def score_depth_batch(depth: Tensor, depth_std: Tensor, depth_gt: Tensor, scales
     ``scales[b]`` is the per-dataset scale ``a``.  Per view: scale, clamp to ``[1e-3, max gt]``, keep the
     pixels with ``gt > 0`` (a ragged segment per view), then the same kernels as the rgb path with one
     channel and sigma = std: prologue (se / ae / var, NLL with eps = ``min_depth_std_for_nll``, interval
-    histogram), one segmented sort over 3B ragged segments, cut-point prefix sums.  The cheap per-view
-    elementwise preparation uses torch ops (same fp32 semantics as the reference's own torch lines)."""
+    histogram), one segmented sort over 3B ragged segments, cut-point prefix sums.  The per-view preparation is
+    one stable stream compaction (``ub_depth_prepare``); the per-view lengths are the only value read back."""
     if depth.dim() == 4:
         depth, depth_std = depth[..., 0], depth_std[..., 0]
     if depth_gt.dim() == 4:
         depth_gt = depth_gt[..., 0]
     b = depth.shape[0]
     dev = depth.device
-    preds, stds, gts, lens = [], [], [], []
-    for i in range(b):
-        gt = depth_gt[i]
-        max_d = gt.max().float()
-        d = float(scales[i]) * depth[i]
-        s = float(scales[i]) * depth_std[i]
-        mask = gt > 0
-        dm = torch.clamp(d[mask], min=1e-3)
-        dm = torch.minimum(dm, max_d)
-        preds.append(dm)
-        stds.append(s[mask])
-        gts.append(gt[mask])
-        lens.append(int(dm.numel()))
-    pred = torch.cat(preds).reshape(-1, 1).contiguous()
-    std = torch.cat(stds).contiguous()
-    gt = torch.cat(gts).reshape(-1, 1).contiguous()
+    pred, std, gt, lens = ops.depth_prepare(depth.reshape(b, -1), depth_std.reshape(b, -1), depth_gt.reshape(b, -1),
+                                            scales)
+    pred, gt = pred.reshape(-1, 1), gt.reshape(-1, 1)
     total = pred.shape[0]
     z = _z_table(dev)
     pro = ops.score_prologue(pred, gt, std, lens, z, nll_min_std=min_depth_std_for_nll, sigma_from_var=False,

@@ -365,6 +365,36 @@ def reduce_members(members: Sequence[Tensor], spread: Optional[str] = None) -> T
     return reduce_many([(members, spread)])[0]
 
 
+def depth_prepare(depth: Tensor, depth_std: Tensor, depth_gt: Tensor, scales: Union[Sequence[float], Tensor]
+                  ) -> Tuple[Tensor, Tensor, Tensor, List[int]]:
+    """Scale, clamp and mask the depth-scoring inputs of a batch of views (eval_uncertainty.py:461-462, 511-513,
+    552-560): ``depth, depth_std, depth_gt [B, N]`` -> the kept pixels as flat ``pred, std, gt`` (views back to
+    back, row-major inside a view) and the per-view lengths.  Reading the lengths back is the one host
+    synchronisation of the depth path."""
+    lib = _lib.load()
+    depth, depth_std, depth_gt = _dev_f32(depth, "depth"), _dev_f32(depth_std, "depth_std"), _dev_f32(depth_gt, "depth_gt")
+    if depth.dim() != 2 or depth_std.shape != depth.shape or depth_gt.shape != depth.shape:
+        raise ValueError("depth, depth_std, depth_gt must share one [B, N] shape")
+    b, n = int(depth.shape[0]), int(depth.shape[1])
+    dev = depth.device
+    sc = scales if isinstance(scales, torch.Tensor) else torch.tensor([float(v) for v in scales], dtype=torch.float32)
+    sc = sc.to(device=dev, dtype=torch.float32).contiguous()
+    if sc.numel() != b:
+        raise ValueError("one scale per view")
+    pred, std, gt = (torch.empty(b * n, device=dev) for _ in range(3))
+    offsets = torch.empty(b + 1, dtype=torch.int64, device=dev)
+    ws = _workspace(lib.ub_depth_prepare_workspace_bytes(b, n), dev)
+    with _guard(dev):
+        _lib.check(lib.ub_depth_prepare(depth.data_ptr(), depth_std.data_ptr(), depth_gt.data_ptr(), sc.data_ptr(), b, n,
+                                        pred.data_ptr(), std.data_ptr(), gt.data_ptr(), offsets.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _stream()))
+    _count(4)
+    off = offsets.cpu().tolist()
+    total = off[-1]
+    lens = [off[i + 1] - off[i] for i in range(b)]
+    return pred[:total], std[:total], gt[:total], lens
+
+
 class Segments:
     """Segment table of a batch (device int64 offsets + the host-side scalars the C ABI wants).  Built once
     per distinct tuple of lengths and cached: the hot calls never copy host memory to the device (a copy
