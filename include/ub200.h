@@ -338,9 +338,12 @@ int ub_composite_tiles_planes(const float* xys, const float* conics, const float
 /* In-place post-processing of one output plane [num_pixels, channels]:
  *   clamp_max_one   : image = min(image, 1)                       activesplatfacto_model.py:275
  *   divide_by_alpha : image = alpha > 0 ? image / alpha : max     activesplatfacto_model.py:319, 356
- * max_key: DEVICE pointer to the plane's entry of channel_max_keys. */
+ * max_key: DEVICE pointer to the plane's entry of channel_max_keys.  Optional derived planes of the same shape,
+ * written from the post-processed image: out_square = image^2 (rgb_var = uncertainty ** 2, :364), out_sqrt =
+ * sqrt(image) (depth_std = depth_var.sqrt(), :367); NULL to skip. */
 int ub_splat_normalize(float* image, int32_t channels, const float* alpha, int64_t num_pixels,
-                       int32_t clamp_max_one, int32_t divide_by_alpha, const uint32_t* max_key, void* stream);
+                       int32_t clamp_max_one, int32_t divide_by_alpha, const uint32_t* max_key, float* out_square,
+                       float* out_sqrt, void* stream);
 
 /* out_sq_residual[g] = (depth_g - depth_image[floor(y_g), floor(x_g)])^2 when the centre pixel satisfies
  * 0 < x < W and 0 < y < H (strict, as the reference's mask), else depth_g^2: the colours of the

@@ -208,7 +208,7 @@ static int launch_tiles(TileParams p, int channels, int img_height, cudaStream_t
 // img[..., channel] = alpha > 0 ? img / alpha : max (reference :319, :356); rgb = min(rgb, 1) (:275)
 __global__ void __launch_bounds__(256)
 splat_normalize_kernel(float* img, int ch, const float* alpha, long long num_pixels, int clamp_max_one,
-                       int divide_by_alpha, const unsigned* max_key) {
+                       int divide_by_alpha, const unsigned* max_key, float* out_square, float* out_sqrt) {
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= num_pixels) return;
   if (clamp_max_one) {
@@ -221,6 +221,13 @@ splat_normalize_kernel(float* img, int ch, const float* alpha, long long num_pix
     const float a = alpha[pix];
     const float mx = order_key_inv(*max_key);
     for (int c = 0; c < ch; ++c) img[pix * ch + c] = a > 0.0f ? img[pix * ch + c] / a : mx;
+  }
+  if (out_square || out_sqrt) {  // rgb_var = uncertainty ** 2 (:364), depth_std = depth_var.sqrt() (:367)
+    for (int c = 0; c < ch; ++c) {
+      const float v = img[pix * ch + c];
+      if (out_square) out_square[pix * ch + c] = __fmul_rn(v, v);
+      if (out_sqrt) out_sqrt[pix * ch + c] = sqrtf(v);
+    }
   }
 }
 
@@ -302,7 +309,8 @@ int ub_composite_tiles(const float* xys, const float* conics, const float* opaci
 }
 
 int ub_splat_normalize(float* image, int32_t channels, const float* alpha, int64_t num_pixels,
-                       int32_t clamp_max_one, int32_t divide_by_alpha, const uint32_t* max_key, void* stream_v) {
+                       int32_t clamp_max_one, int32_t divide_by_alpha, const uint32_t* max_key, float* out_square,
+                       float* out_sqrt, void* stream_v) {
   using namespace ub;
   UB_REQUIRE(image != nullptr && channels >= 1 && num_pixels >= 0, UB_ERR_BAD_ARG, "splat_normalize: bad arguments");
   UB_REQUIRE(!divide_by_alpha || (alpha != nullptr && max_key != nullptr), UB_ERR_BAD_ARG,
@@ -310,7 +318,7 @@ int ub_splat_normalize(float* image, int32_t channels, const float* alpha, int64
   if (num_pixels == 0) return UB_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   splat_normalize_kernel<<<(unsigned)((num_pixels + 255) / 256), 256, 0, stream>>>(
-      image, channels, alpha, num_pixels, clamp_max_one, divide_by_alpha, max_key);
+      image, channels, alpha, num_pixels, clamp_max_one, divide_by_alpha, max_key, out_square, out_sqrt);
   return check_launch("splat_normalize");
 }
 

@@ -168,15 +168,16 @@ def active_splatfacto_outputs(xys: Tensor, depths: Tensor, conics: Tensor, opaci
     resid2 = ops.splat_depth_residual(xys, depths, depth_im)            # per-Gaussian squared residual    (:325-349)
     (depth_var,), _, vkeys = ops.composite_tiles_planes(xys, conics, opacities, [resid2], gaussian_ids, tile_bins,
                                                         height, width, [0.0], want_max=True)
-    ops.splat_normalize_(depth_var, alpha, vkeys[0:1])                  # / alpha, else max                (:356)
+    _, _, depth_std = ops.splat_normalize_(depth_var, alpha, vkeys[0:1], want_sqrt=True)   # / alpha, else max (:356); sqrt (:367)
+    _, rgb_var, _ = ops.splat_normalize_(uncertainty, want_square=True)                     # uncertainty ** 2  (:364)
     return {
         "rgb": rgb,
         "depth": depth_im,
         "accumulation": alpha,
         "background": background,
         "uncertainty": uncertainty,
-        "rgb_var": uncertainty ** 2,
+        "rgb_var": rgb_var,
         "rgb_std": uncertainty,
         "depth_var": depth_var,
-        "depth_std": depth_var.sqrt(),
+        "depth_std": depth_std,
     }

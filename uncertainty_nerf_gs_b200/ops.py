@@ -680,16 +680,20 @@ def composite_tiles_planes_backward(xys: Tensor, conics: Tensor, opacities: Tens
 
 
 def splat_normalize_(image: Tensor, alpha: Optional[Tensor] = None, max_key: Optional[Tensor] = None,
-                     clamp_max_one: bool = False) -> Tensor:
-    """In place: ``min(image, 1)`` and / or ``alpha > 0 ? image / alpha : max`` (activesplatfacto_model.py:275,319)."""
+                     clamp_max_one: bool = False, want_square: bool = False, want_sqrt: bool = False):
+    """In place: ``min(image, 1)`` and / or ``alpha > 0 ? image / alpha : max`` (activesplatfacto_model.py:275,319).
+    With ``want_square`` / ``want_sqrt`` also returns ``image ** 2`` / ``image.sqrt()`` of the processed image
+    (:364, :367) from the same pass: ``image`` alone, or ``(image, square, sqrt)`` with ``None`` for the unwanted."""
     lib = _lib.load()
     ch = int(image.shape[-1])
     n = image.numel() // ch
+    sq = torch.empty_like(image) if want_square else None
+    rt = torch.empty_like(image) if want_sqrt else None
     with _guard(image.device):
         _lib.check(lib.ub_splat_normalize(image.data_ptr(), ch, _ptr(alpha), n, 1 if clamp_max_one else 0,
-                                          1 if alpha is not None else 0, _ptr(max_key), _stream()))
-    _count(2)  # flat-mean and spread instantiations
-    return image
+                                          1 if alpha is not None else 0, _ptr(max_key), _ptr(sq), _ptr(rt), _stream()))
+    _count(1)
+    return (image, sq, rt) if (want_square or want_sqrt) else image
 
 
 def splat_depth_residual(xys: Tensor, depths: Tensor, depth_image: Tensor) -> Tensor:
