@@ -42,3 +42,28 @@ def test_driver_matches_reference_aggregation(built_library, tmp_path):
         assert isinstance(info["results"][k], float)
     eval_driver.save_curves(tmp_path / "plots", results)
     assert np.load(tmp_path / "plots" / "rgb_coverage_values.npy").shape == (99,)
+
+
+def test_view_stream_equals_per_view_evaluation(built_library):
+    """ViewStream (batched scoring on a second stream, delayed read-back) must return, in view order, exactly what
+    evaluating every view on its own returns."""
+    from uncertainty_nerf_gs_b200 import pipeline, synthetic
+
+    h, w, S, M = 24, 40, 48, 3
+    views = []
+    for v in range(7):
+        members = [synthetic.ray_samples(h * w, S, seed=100 * v + i, device="cuda") for i in range(M)]
+        _, _, gt = synthetic.scoring_image(h, w, seed=v, device="cuda")
+        views.append((members, gt))
+    want = [pipeline.evaluate_view(m, g, h, w, rays_per_chunk=256) for m, g in views]
+    vs = pipeline.ViewStream(h, w, rays_per_chunk=256, score_batch=3)
+    got = []
+    for m, g in views:
+        got += vs.push(m, g)
+    assert len(got) == 3                       # the first batch of three is read back when the second is enqueued
+    got += vs.flush()
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert list(a.keys()) == list(b.keys())
+        for k in b:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True), k

@@ -119,6 +119,69 @@ def evaluate_view_async(members: Sequence[Dict[str, Tensor]], rgb_gt: Tensor, he
     return PendingView(pending)
 
 
+class ViewStream:
+    """Streamed evaluation of a test set, the way ``eval_driver`` and ``bench.py`` drive the path.
+
+    ``push(members, rgb_gt)`` composites and reduces one view on the current stream and returns at once.  Every
+    ``score_batch`` views, the reduced images are stacked and scored by ONE set of segmented launches on a second
+    stream -- underneath the following views' persistent compositing kernels -- and the batch that was enqueued
+    before it is read back (its device work finished long ago, so the host does not stall).  ``push`` and
+    ``flush`` return the finished views' entries (the reference's per-image dict + ``metrics_dict`` scalars) in
+    view order.  Pays off on long streams (a test set): each batch allocates ~100 MB per view of scratch, and the
+    last batch is scored with nothing to hide under, so ``bench.py``'s 30-view timed region keeps the per-view
+    form (``evaluate_view_async``)."""
+
+    def __init__(self, height: int, width: int, rays_per_chunk: int = 1 << 15, score_batch: int = 8,
+                 min_rgb_std_for_nll: float = 3e-2, timers: Optional[list] = None):
+        self.h, self.w, self.chunk = height, width, rays_per_chunk
+        self.score_batch = max(1, int(score_batch))
+        self.min_std = min_rgb_std_for_nll
+        self.timers = timers
+        self._views: List[Tuple[Tensor, Tensor, Tensor]] = []   # reduced rgb, rgb_std, gt of the open batch
+        self._in_flight: List[object] = []                      # PendingScores of enqueued batches, oldest first
+
+    def _enqueue_batch(self) -> None:
+        views, self._views = self._views, []
+        dev = views[0][0].device
+        main = torch.cuda.current_stream(dev)
+        side = _score_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if len(views) == 1:
+                rgb, std, gt = (t[None] for t in views[0])
+            else:
+                rgb, std, gt = (torch.stack([v[i] for v in views]) for i in range(3))
+            pending = metrics.score_rgb_batch_async(rgb, gt, std, self.min_std)
+        pending.keep_alive = (views, rgb, std, gt)   # main-stream allocations read on the side stream
+        self._in_flight.append(pending)
+
+    @staticmethod
+    def _finish(pending) -> List[Dict[str, object]]:
+        out = pending.finish()
+        for d in out:
+            d.update(metrics.per_image_rgb_scalars(d))
+        return out
+
+    def push(self, members: Sequence[Dict[str, Tensor]], rgb_gt: Tensor) -> List[Dict[str, object]]:
+        outs = render_members(members, self.h, self.w, self.chunk, self.timers)
+        red = mo.ensemble_reduce(outs) if len(outs) > 1 else outs[0]
+        self._views.append((red["rgb"], red["rgb_std"], rgb_gt))
+        done: List[Dict[str, object]] = []
+        if len(self._views) >= self.score_batch:
+            self._enqueue_batch()
+            while len(self._in_flight) > 1:
+                done += self._finish(self._in_flight.pop(0))
+        return done
+
+    def flush(self) -> List[Dict[str, object]]:
+        if self._views:
+            self._enqueue_batch()
+        done: List[Dict[str, object]] = []
+        while self._in_flight:
+            done += self._finish(self._in_flight.pop(0))
+        return done
+
+
 class HostViewEvaluator:
     """End-to-end entry: the caller holds one view's member ray samples and ground truth in *pinned host*
     memory; every call copies them to the device on a copy stream (member m+1 uploads while member m
