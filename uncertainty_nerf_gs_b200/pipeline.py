@@ -115,6 +115,8 @@ def evaluate_view_async(members: Sequence[Dict[str, Tensor]], rgb_gt: Tensor, he
     side.wait_stream(main)
     with torch.cuda.stream(side):
         pending = metrics.score_rgb_batch_async(rgb, rgb_gt, std, min_rgb_std_for_nll)
+    for t in (rgb, std, rgb_gt):          # allocated on the main stream, read on the side stream: even if the
+        t.record_stream(side)             # caller drops the result unfinished, their memory is not reused early
     pending.keep_alive = (rgb, std, rgb_gt)
     return PendingView(pending)
 
@@ -152,7 +154,10 @@ class ViewStream:
             else:
                 rgb, std, gt = (torch.stack([v[i] for v in views]) for i in range(3))
             pending = metrics.score_rgb_batch_async(rgb, gt, std, self.min_std)
-        pending.keep_alive = (views, rgb, std, gt)   # main-stream allocations read on the side stream
+        for v in views:                              # main-stream allocations read on the side stream
+            for t in v:
+                t.record_stream(side)
+        pending.keep_alive = (views, rgb, std, gt)
         self._in_flight.append(pending)
 
     @staticmethod
