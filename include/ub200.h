@@ -283,6 +283,26 @@ int ub_cut_prefix_sums(const float* const* values_host, const int32_t* const* pe
                        int64_t max_segment_len, const int64_t* cuts, int32_t num_cuts, double* out_sums,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* AUSE cut-point sums without a full sort (multi-cut radix select).  Same result as ub_segmented_sort
+ * followed by ub_cut_prefix_sums -- the sums over the first cuts[s, c] elements of the stable ascending
+ * order of the keys (metrics/ause.py:10-20 with the error as its own key, :25-34 with the uncertainty as
+ * key and the errors as payload) -- when the permutation itself is not needed: keys are classified against
+ * the cut positions (adaptive 4096-bin histogram, tie groups resolved by element index, the few undecided
+ * keys around every cut sorted by the segmented radix sort), payloads summed per class in float64.
+ * Family f (<= 4) has keys keys_host[f] [total] and one or two payload arrays pay0_host[f], pay1_host[f]
+ * (HOST arrays of DEVICE pointers; pay1_host or its entries may be NULL; pay0 == keys is recognised).
+ * All families share seg_offsets (DEVICE int64 [num_views + 1], off[0] == 0) and cuts (DEVICE
+ * [num_views, num_cuts] int64, num_cuts <= 128, any order, clamped to the segment length).
+ * out_sums: DEVICE [num_views, V, num_cuts] float64, V = total number of payload arrays, rows in family
+ * order.  max_segment_len <= 2^24 (UB_ERR_UNSUPPORTED above: use the sort). */
+size_t ub_cut_select_sums_workspace_bytes(int32_t num_families, int32_t num_views, int64_t total,
+                                          int64_t max_segment_len, int32_t num_cuts);
+int ub_cut_select_sums(const float* const* keys_host, const float* const* pay0_host,
+                       const float* const* pay1_host, int32_t num_families, int32_t num_views,
+                       const int64_t* seg_offsets, int64_t total, int64_t max_segment_len, const int64_t* cuts,
+                       int32_t num_cuts, double* out_sums, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (A3) Last-layer diagonal-Laplace MC moments.
  * Replaces NerfactoLaplaceField.sample_laplace, models/laplace/laplace_field.py:528-568, for a

@@ -99,6 +99,9 @@ SIGNATURES = {
     "ub_cut_prefix_sums_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int32, C.c_int32]),
     "ub_cut_prefix_sums": (C.c_int, [C.POINTER(fp), C.POINTER(fp), C.c_int32, C.c_int32, fp, C.c_int64,
                                      fp, C.c_int32, fp, fp, C.c_size_t, fp]),
+    "ub_cut_select_sums_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32]),
+    "ub_cut_select_sums": (C.c_int, [C.POINTER(fp), C.POINTER(fp), C.POINTER(fp), C.c_int32, C.c_int32, fp,
+                                     C.c_int64, C.c_int64, fp, C.c_int32, fp, fp, C.c_size_t, fp]),
     "ub_laplace_ll_moments": (C.c_int, [fp, C.c_int64, C.c_int32, C.c_int32, fp, C.c_int32, C.c_int32,
                                         fp, fp, fp, fp]),
     "ub_depth_prepare_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),

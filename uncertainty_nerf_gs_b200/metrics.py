@@ -12,6 +12,7 @@ reproducible under ties).  AUCE contract: NumPy >= 2 promotion (float64 interval
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -142,6 +143,29 @@ def _ause_tail(oracle_f32: np.ndarray, by_unc_f32: np.ndarray):
     return _RATIOS, o[0], b[0], a[0]
 
 
+_SELECT_MAX_LEN = 1 << 24
+
+
+def _use_select(max_len: int) -> bool:
+    """The AUSE prefix sums come from the sort-free multi-cut select (``ub_cut_select_sums``) unless
+    ``UB_AUSE_SORT=1`` asks for the full segmented sort (same sums up to float64 summation order; the sort
+    remains the path that returns the permutation, ``ops.segmented_sort``)."""
+    return os.environ.get("UB_AUSE_SORT", "0") != "1" and max_len <= _SELECT_MAX_LEN
+
+
+def _ause_sums(vec: Tensor, lens, cuts: np.ndarray) -> Tensor:
+    """``[B, 4, ncuts]`` float64: payload sums under every cut for (abs err by var, sq err by var, abs err
+    ascending, sq err ascending) from the prologue's ``[3, total]`` buffer (var, abs err, sq err)."""
+    ae, se = vec[1], vec[2]
+    if _use_select(max(lens) if len(lens) else 0):
+        return ops.cut_select_sums([(vec[0], ae, se), (ae, ae, None), (se, se, None)], lens, cuts)
+    total = vec.shape[1]
+    sorted_all, perm_all = ops.segmented_sort(vec.reshape(-1), list(lens) * 3, want_perm=True, want_keys=True)
+    perm_var = perm_all[:total]
+    return ops.cut_prefix_sums([ae, se, sorted_all[total:2 * total], sorted_all[2 * total:]],
+                               [perm_var, perm_var, None, None], lens, cuts)
+
+
 def _check_err_type(err_type: str) -> None:
     if err_type not in ("rmse", "mse", "mae"):
         raise ValueError(f"err_type must be 'rmse', 'mse' or 'mae', got {err_type!r}")
@@ -156,9 +180,13 @@ def ause(unc_vec: Tensor, err_vec: Tensor, err_type: str = "rmse"
         raise ValueError("unc_vec and err_vec must be 1-D tensors of equal length")
     n = len(err_vec)
     cuts = ause_cut_counts(n)
-    both = torch.stack([unc_vec.reshape(-1), err_vec.reshape(-1)]).to(torch.float32)
-    sorted_all, perm_all = ops.segmented_sort(both.reshape(-1), [n, n], want_perm=True, want_keys=True)
-    sums = ops.cut_prefix_sums([sorted_all[n:], err_vec], [None, perm_all[:n]], [n], cuts[None, :])
+    if _use_select(n):
+        unc32, err32 = unc_vec.reshape(-1).to(torch.float32), err_vec.reshape(-1).to(torch.float32)
+        sums = ops.cut_select_sums([(err32, err32, None), (unc32, err32, None)], [n], cuts[None, :])
+    else:
+        both = torch.stack([unc_vec.reshape(-1), err_vec.reshape(-1)]).to(torch.float32)
+        sorted_all, perm_all = ops.segmented_sort(both.reshape(-1), [n, n], want_perm=True, want_keys=True)
+        sums = ops.cut_prefix_sums([sorted_all[n:], err_vec], [None, perm_all[:n]], [n], cuts[None, :])
     host = sums[0].cpu().numpy()
     return _ause_tail(_prefix_means(host[0], cuts, err_type), _prefix_means(host[1], cuts, err_type))
 
@@ -254,13 +282,9 @@ def score_rgb_batch_async(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min
     pro = ops.score_prologue(rgb_pred.reshape(-1, c), rgb_gt.reshape(-1, c), rgb_std.reshape(-1), lens, z,
                              nll_min_std=min_rgb_std_for_nll, sigma_from_var=True, want_vectors=True)
     vec = pro["vectors"]                                   # [3, total]: var, abs err, sq err
-    ae, se = vec[1], vec[2]
     cuts_one = ause_cut_counts(n)
     cuts = np.tile(cuts_one[None, :], (b, 1))
-    sorted_all, perm_all = ops.segmented_sort(vec.reshape(-1), lens * 3, want_perm=True, want_keys=True)
-    perm_var = perm_all[:total]
-    sums = ops.cut_prefix_sums([ae, se, sorted_all[total:2 * total], sorted_all[2 * total:]],
-                               [perm_var, perm_var, None, None], lens, cuts)          # [B, 4, 100]
+    sums = _ause_sums(vec, lens, cuts)                                                # [B, 4, 100]
     # one device->host transfer for everything the host tail needs (asynchronous into pinned memory)
     packed_dev = torch.cat([sums.reshape(b, -1), pro["sums"], pro["hist"].to(torch.float64)], dim=1)
     packed_host = torch.empty(packed_dev.shape, dtype=packed_dev.dtype, pin_memory=True)
@@ -353,12 +377,8 @@ def score_depth_batch(depth: Tensor, depth_std: Tensor, depth_gt: Tensor, scales
     pro = ops.score_prologue(pred, gt, std, lens, z, nll_min_std=min_depth_std_for_nll, sigma_from_var=False,
                              want_vectors=True)
     vec = pro["vectors"]
-    ae, se = vec[1], vec[2]
     cuts = np.stack([ause_cut_counts(n) for n in lens])
-    sorted_all, perm_all = ops.segmented_sort(vec.reshape(-1), lens * 3, want_perm=True, want_keys=True)
-    perm_var = perm_all[:total]
-    sums = ops.cut_prefix_sums([ae, se, sorted_all[total:2 * total], sorted_all[2 * total:]],
-                               [perm_var, perm_var, None, None], lens, cuts)
+    sums = _ause_sums(vec, lens, cuts)
     packed = torch.cat([sums.reshape(b, -1), pro["sums"], pro["hist"].to(torch.float64)], dim=1).cpu().numpy()
     zh = z_values_host()
     results = []

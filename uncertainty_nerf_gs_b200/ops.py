@@ -544,6 +544,42 @@ def cut_prefix_sums(values: Sequence[Tensor], perms: Union[None, Tensor, Sequenc
     return out
 
 
+def cut_select_sums(families: Sequence[Tuple[Tensor, Tensor, Optional[Tensor]]], seg_lengths: Sequence[int],
+                    cuts: np.ndarray) -> Tensor:
+    """float64 sums of the payloads over the first ``cuts[s, c]`` elements of the stable ascending order of
+    the keys, without sorting (``ub_cut_select_sums``): equal to ``segmented_sort`` + ``cut_prefix_sums`` up
+    to float64 summation order.  ``families``: ``(keys, payload0, payload1 or None)`` triples of ``[total]``
+    float32 tensors sharing the segmentation; ``payload0 is keys`` (same storage) sums the sorted keys.
+    Returns ``[nseg, V, ncuts]`` with one row per payload array in family order."""
+    lib = _lib.load()
+    fams = []
+    for i, (k, p0, p1) in enumerate(families):
+        k = _dev_f32(k.reshape(-1), f"keys[{i}]")
+        p0 = k if p0 is None or p0.data_ptr() == k.data_ptr() else _dev_f32(p0.reshape(-1), f"payload0[{i}]")
+        p1 = None if p1 is None else _dev_f32(p1.reshape(-1), f"payload1[{i}]")
+        fams.append((k, p0, p1))
+    dev = fams[0][0].device
+    seg = Segments.get(seg_lengths, dev)
+    total = seg.total
+    for k, p0, p1 in fams:
+        if k.numel() != total or p0.numel() != total or (p1 is not None and p1.numel() != total):
+            raise ValueError("every key / payload array must hold one entry per element")
+    cuts_dev = seg.cuts_device(cuts)
+    nseg, ncuts, nf = seg.num, cuts_dev.shape[1], len(fams)
+    nrows = sum(1 if p1 is None else 2 for _, _, p1 in fams)
+    out = torch.empty(nseg, nrows, ncuts, dtype=torch.float64, device=dev)
+    kp = (C.c_void_p * nf)(*[k.data_ptr() for k, _, _ in fams])
+    p0p = (C.c_void_p * nf)(*[p0.data_ptr() for _, p0, _ in fams])
+    p1p = (C.c_void_p * nf)(*[_ptr(p1) for _, _, p1 in fams])
+    ws = _workspace(lib.ub_cut_select_sums_workspace_bytes(nf, nseg, total, seg.max_len, ncuts), dev)
+    with _guard(dev):
+        _lib.check(lib.ub_cut_select_sums(kp, p0p, p1p, nf, nseg, seg.offsets.data_ptr(), total, seg.max_len,
+                                          cuts_dev.data_ptr(), ncuts, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          _stream()))
+    _count(8 + (12 if total > 0 else 0) + 2)
+    return out
+
+
 _ACTS = {"identity": _lib.UB_ACT_IDENTITY, "sigmoid": _lib.UB_ACT_SIGMOID, "exp": _lib.UB_ACT_EXP,
          "trunc_exp": _lib.UB_ACT_EXP}
 
