@@ -1,6 +1,9 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_select.py -x -q 2>&1 | tail -30 > gpurun_out/sel_tests.log
+timeout 900 python -m pytest tests/test_gpu_select.py -x -q 2>&1 | tail -30 > gpurun_out/sel_tests.log
 cat gpurun_out/sel_tests.log
+timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_select.py -x -q -k "small_segments or ragged or arbitrary or special" 2>&1 | tail -15 > gpurun_out/sel_memcheck.log
+cat gpurun_out/sel_memcheck.log
+rm -f gpurun_out/sel_perf.jsonl
 timeout 300 python tools/perf_select.py 16 800 800 > gpurun_out/sel_perf.jsonl 2> gpurun_out/sel_perf.err
 UB_PERF_STD_FLOOR=0 timeout 300 python tools/perf_select.py 16 800 800 >> gpurun_out/sel_perf.jsonl 2>> gpurun_out/sel_perf.err
 timeout 300 python tools/perf_select.py 8 840 1297 >> gpurun_out/sel_perf.jsonl 2>> gpurun_out/sel_perf.err

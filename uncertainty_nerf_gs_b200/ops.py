@@ -576,7 +576,7 @@ def cut_select_sums(families: Sequence[Tuple[Tensor, Tensor, Optional[Tensor]]],
         _lib.check(lib.ub_cut_select_sums(kp, p0p, p1p, nf, nseg, seg.offsets.data_ptr(), total, seg.max_len,
                                           cuts_dev.data_ptr(), ncuts, out.data_ptr(), ws.data_ptr(), ws.numel(),
                                           _stream()))
-    _count(8 + (12 if total > 0 else 0) + 2)
+    _count(9)
     return out
 
 
