@@ -20,7 +20,7 @@ def declared_symbols():
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for s in ("ub_composite_rays", "ub_render_weights", "ub_reduce_members", "ub_score_prologue",
-              "ub_segmented_sort", "ub_cut_prefix_sums", "ub_laplace_ll_moments", "ub_composite_tiles",
+              "ub_segmented_sort", "ub_cut_prefix_sums", "ub_cut_select_sums", "ub_laplace_ll_moments", "ub_composite_tiles",
               "ub_abi_version", "ub_last_error"):
         assert s in syms
 

@@ -14,7 +14,7 @@
 //   fine       histogram over the fine bins
 //   locate     prefix over the fine bins; every cut falls into one bin (its "cell") at a residual rank r;
 //              a bin that holds no cut gets a class = number of cuts that exclude it
-//   cells      per (cell, 2048-key tile) counts + key range of every cell
+//   ties       per 2048-key tile counts of the heavy tie values that hold a cut
 //   plan       a big cell whose keys are all equal (a tie group) is resolved by index: stable order inside
 //              it is the element order, so the tile where the running count crosses r follows from the
 //              per-tile counts and only that tile's members stay undecided; other cells stay undecided whole
@@ -34,6 +34,8 @@ namespace ub {
 
 constexpr int kSelThreads = 256;
 constexpr int kSelWarps = kSelThreads / 32;
+constexpr int kSelLocThreads = 1024;  // sel_locate: one block per segment, latency-bound
+constexpr int kSelResThreads = 128;   // sel_resolve: many small runs
 constexpr int kSelCoarse = 4096;   // top 12 key bits
 constexpr int kSelLowBits = 20;
 constexpr uint32_t kSelLowMask = (1u << kSelLowBits) - 1u;
@@ -42,32 +44,41 @@ constexpr int kSelMaxHeavy = 16;   // tie values that get a bin of their own
 constexpr int kSelBins = kSelFine + 2 * kSelMaxHeavy;
 constexpr int kSelSample = 1024;   // keys sampled per segment to find the heavy tie values
 constexpr int kSelHeavyHits = 8;   // sample hits that make a key heavy (~0.8 % of the segment)
-constexpr int kSelTile = 2048;     // counting / compaction tile
+constexpr int kSelTile = 2048;     // classification tile
 constexpr int kSelItems = kSelTile / kSelThreads;
 constexpr int kSelMaxTilesPerBlock = 16;
 constexpr int kSelChunk = 8192;    // keys per block in the histogram kernels
 constexpr int kSelMaxCuts = 128;
 constexpr int kSelMaxFamilies = 4;
 constexpr uint32_t kSelTiledMin = 2 * kSelTile;  // tie groups above this size are resolved by tile
-constexpr int kSelBrute = 2048;    // records ranked pairwise in shared memory
+constexpr int kSelBrute = 2048;    // records of a run handled in shared memory
 constexpr uint16_t kSelCellFlag = 0x8000u;
 constexpr uint8_t kSelCompact = 0xFFu;
 
+struct RunDesc {        // what the resolve block of cut j works on
+  int leader;           // 0: nothing to do for this cut's block
+  int cell, j0, nj;     // the cell and its cuts [j0, j0 + nj)
+  uint32_t start, len;  // records [start, start + len) of the cell's slot
+  uint32_t base;        // first record of the cell's slot in the segment's side list
+  uint32_t pad;
+};
+
 struct SegPlan {
-  int nfine, nbins, ncells, nheavy;
-  uint32_t heavy[kSelMaxHeavy];      // ascending
+  int nfine, nbins, ncells, nheavy, ntiled, pad0, pad1, pad2;
+  uint32_t heavy[kSelMaxHeavy];      // heavy tie values (any order)
+  uint32_t tkey[kSelMaxHeavy];       // tiled cells: tie groups that hold a cut and are resolved by tile
+  int tcell[kSelMaxHeavy];
   int cut_k[kSelMaxCuts];            // original index of the j-th smallest cut
-  int cut_T[kSelMaxCuts];            // fine bins < T are under the cut
+  int cut_T[kSelMaxCuts];            // bins < T are under the cut
   int cut_cell[kSelMaxCuts];         // cell that holds the cut, -1 if the cut is a bin boundary
   uint32_t cut_r[kSelMaxCuts];       // elements of the cell under the cut (stable order)
   uint32_t cut_posoff[kSelMaxCuts];  // records of the cell's slot under the cut (in (key, index) order)
-  int cut_leader[kSelMaxCuts];       // the cut's block resolves a run of records
-  uint32_t cut_run_start[kSelMaxCuts], cut_run_len[kSelMaxCuts];
+  RunDesc run[kSelMaxCuts];
   int cell_bin[kSelMaxCuts];
   uint32_t cell_count[kSelMaxCuts];
   uint32_t cell_comp[kSelMaxCuts];   // records in the cell's slot
   int cell_j0[kSelMaxCuts], cell_j1[kSelMaxCuts];  // cuts [j0, j1) lie inside the cell
-  int cell_tiled[kSelMaxCuts];
+  int cell_tiled[kSelMaxCuts];       // index into tkey / tcell, -1: the whole cell goes to the side list
 };
 
 struct SelParams {
@@ -87,13 +98,13 @@ struct SelParams {
   double* out;                    // [B][V][num_cuts]
   uint32_t* hist_c;       // [G][kSelCoarse]                               zeroed
   uint32_t* hist_f;       // [G][kSelBins]                                 zeroed
-  uint32_t* cell_mm;      // [G][kSelMaxCuts][2] {max(~u), max(u)}         zeroed
-  double* ssum;           // [G][kSelMaxCuts + 1][2] class sums of the records  zeroed
+  uint32_t* cursor;       // [G][kSelMaxCuts] records written to each cell's slot   zeroed
+  double* ssum;           // [G][kSelMaxCuts + 1][2] class sums of the records      zeroed
   uint32_t* table;        // [G][kSelCoarse]: (first fine bin << 5) | shift of the low 20 key bits
   SegPlan* plan;          // [G]
   uint16_t* binmap;       // [G][kSelBins]: class, or kSelCellFlag | cell
-  uint32_t* tilecounts;   // [G][num_cuts][max_tiles]; after sel_plan_cells: first record of (cell, tile)
-  uint8_t* tilemode;      // [G][max_tiles][kSelMaxCuts]: class of the cell's members in the tile, or kSelCompact
+  uint32_t* tilecounts;   // [G][kSelMaxHeavy][max_tiles]; after sel_plan_tiled: first record of (tiled cell, tile)
+  uint8_t* tilemode;      // [G][max_tiles][kSelMaxHeavy]: class of the tie group's members in the tile, or kSelCompact
   double* spart;          // [G][max_blocks][num_cuts + 1][2]
   uint32_t* ckeys;        // [F * total] records: order-preserving key
   uint32_t* cidx;         // [F * total] records: index within the segment
@@ -115,6 +126,7 @@ __device__ __forceinline__ int sel_bin(uint32_t u, uint32_t t, const uint32_t* h
   return bin;
 }
 
+// exclusive scan of one value per thread over a block of kSelThreads threads
 __device__ __forceinline__ uint32_t sel_block_excl_scan(uint32_t v, uint32_t* warp_tmp, uint32_t* total_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t incl = v;
@@ -306,28 +318,36 @@ __global__ void __launch_bounds__(kSelThreads) sel_fine_hist(const SelParams p) 
   }
 }
 
-// ---- locate: one block per segment -----------------------------------------------------------------------
-__global__ void __launch_bounds__(kSelThreads) sel_locate(const SelParams p) {
-  constexpr int kPad = (kSelBins + 2047) / 2048 * 2048;  // 8 warps x (a multiple of 8 rounds of 32 bins)
+// ---- locate: one block of 1024 threads per segment -----------------------------------------------------------
+__global__ void __launch_bounds__(kSelLocThreads) sel_locate(const SelParams p) {
+  constexpr int kLocWarps = kSelLocThreads / 32;
+  constexpr int kPad = (kSelBins + kLocWarps * 32 - 1) / (kLocWarps * 32) * (kLocWarps * 32);
+  constexpr int span = kPad / kLocWarps, rounds = span / 32;
   __shared__ uint32_t excl[kPad + 1];
-  __shared__ uint32_t s_wtot[kSelWarps];
+  __shared__ uint32_t s_wtot[kLocWarps];
   __shared__ uint32_t s_raw[kSelMaxCuts], s_c[kSelMaxCuts], s_r[kSelMaxCuts];
   __shared__ int s_k[kSelMaxCuts], s_T[kSelMaxCuts], s_part[kSelMaxCuts], s_cutcell[kSelMaxCuts];
-  __shared__ int s_cellbin[kSelMaxCuts];
-  __shared__ int s_ncells;
-  static_assert(kPad % (kSelWarps * 32 * 8) == 0 && kPad * 4 < 44 * 1024, "locate scan layout");
+  __shared__ int s_cellbin[kSelMaxCuts], s_celltiled[kSelMaxCuts], s_cellj0[kSelMaxCuts], s_cellj1[kSelMaxCuts];
+  __shared__ uint32_t s_cellcount[kSelMaxCuts];
+  __shared__ int s_hbin[kSelMaxHeavy];
+  __shared__ int s_ncells, s_wc[4], s_wc2[4], s_tmp[kSelMaxCuts];
+  static_assert(kPad * 4 < 44 * 1024, "locate scan layout");
   const int g = blockIdx.x, tid = threadIdx.x, nc = p.num_cuts, lane = tid & 31, warp = tid >> 5;
   int f, b;
   long long lo, len;
   sel_segment(p, g, f, b, lo, len);
   SegPlan& pl = p.plan[g];
-  const int nb = max(1, pl.nbins);
+  const int nb = max(1, pl.nbins), nh = pl.nheavy;
 
   // cuts ascending (stable rank by counting)
   if (tid < nc) {
     long long c = p.cuts[(size_t)b * nc + tid];
     c = max(0LL, min(c, len));
     s_raw[tid] = (uint32_t)c;
+  }
+  if (tid < nh) {  // the bin every heavy tie value owns
+    const uint32_t key = pl.heavy[tid];
+    s_hbin[tid] = sel_bin(key, p.table[(size_t)g * kSelCoarse + (key >> kSelLowBits)], pl.heavy, nh);
   }
   __syncthreads();
   if (tid < nc) {
@@ -339,33 +359,29 @@ __global__ void __launch_bounds__(kSelThreads) sel_locate(const SelParams p) {
   }
   // exclusive prefix of the bin counts: warp w owns bins [span w, span (w + 1)), 32 consecutive bins per round
   {
-    constexpr int span = kPad / kSelWarps, rounds = span / 32;
     const uint32_t* gh = p.hist_f + (size_t)g * kSelBins;
+    uint32_t v[rounds];
+#pragma unroll
+    for (int q = 0; q < rounds; ++q) {
+      const int bin = warp * span + q * 32 + lane;
+      v[q] = bin < nb ? gh[bin] : 0u;
+    }
     uint32_t carry = 0;
-    for (int r0 = 0; r0 < rounds; r0 += 8) {
-      uint32_t v[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int bin = warp * span + (r0 + q) * 32 + lane;
-        v[q] = bin < nb ? gh[bin] : 0u;
+    for (int q = 0; q < rounds; ++q) {
+      uint32_t incl = v[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl += u;
       }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        uint32_t incl = v[q];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t u = __shfl_up_sync(FULL_MASK, incl, o);
-          if (lane >= o) incl += u;
-        }
-        excl[warp * span + (r0 + q) * 32 + lane] = carry + incl - v[q];
-        carry += __shfl_sync(FULL_MASK, incl, 31);
-      }
+      excl[warp * span + q * 32 + lane] = carry + incl - v[q];
+      carry += __shfl_sync(FULL_MASK, incl, 31);
     }
     if (lane == 0) s_wtot[warp] = carry;
     __syncthreads();
     uint32_t base = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < kSelWarps; ++w) {
+    for (int w = 0; w < kLocWarps; ++w) {
       if (w < warp) base += s_wtot[w];
       tot += s_wtot[w];
     }
@@ -394,36 +410,89 @@ __global__ void __launch_bounds__(kSelThreads) sel_locate(const SelParams p) {
   }
   __syncthreads();
 
-  if (tid == 0) {
-    int ncells = 0;
-    for (int j = 0; j < nc; ++j) {
-      if (!s_part[j]) { s_cutcell[j] = -1; continue; }
-      const bool fresh = j == 0 || !s_part[j - 1] || s_T[j - 1] != s_T[j];
-      if (fresh) {
-        s_cellbin[ncells] = s_T[j];
-        pl.cell_bin[ncells] = s_T[j];
-        pl.cell_count[ncells] = excl[s_T[j] + 1] - excl[s_T[j]];
-        pl.cell_j0[ncells] = j;
-        ++ncells;
-      }
-      s_cutcell[j] = ncells - 1;
-      pl.cell_j1[ncells - 1] = j + 1;
-    }
-    s_ncells = ncells;
-    pl.ncells = ncells;
+  // cells = runs of consecutive cuts inside one bin: numbered by a ballot prefix over the (<= 128) cuts
+  static_assert(kSelMaxCuts == 128, "four warps cover the cuts");
+  const unsigned le_mask = 0xFFFFFFFFu >> (31 - lane);
+  bool fresh = false;
+  if (tid < kSelMaxCuts) {
+    fresh = tid < nc && s_part[tid] && (tid == 0 || !s_part[tid - 1] || s_T[tid - 1] != s_T[tid]);
+    const unsigned bal = __ballot_sync(FULL_MASK, fresh);
+    if (lane == 0) s_wc[warp] = __popc(bal);
+    s_cutcell[tid] = __popc(bal & le_mask);  // starts at or before this cut inside its warp
+    s_cellj1[tid] = 0;
   }
   __syncthreads();
+  if (tid < kSelMaxCuts) {
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_wc[w];
+    const int cell = before + s_cutcell[tid] - 1;
+    s_cutcell[tid] = (tid < nc && s_part[tid]) ? cell : -1;
+    if (fresh) {
+      const int bin = s_T[tid];
+      const uint32_t cnt = excl[bin + 1] - excl[bin];
+      int hk = -1;
+      if (cnt > kSelTiledMin)
+        for (int h = 0; h < nh; ++h)
+          if (s_hbin[h] == bin) hk = h;  // the cell is exactly one tie group
+      s_cellbin[cell] = bin;
+      s_cellcount[cell] = cnt;
+      s_celltiled[cell] = hk;  // heavy-key index for now
+      s_cellj0[cell] = tid;
+    }
+    if (tid == 0) s_ncells = s_wc[0] + s_wc[1] + s_wc[2] + s_wc[3];
+  }
+  __syncthreads();
+  if (tid < nc && s_cutcell[tid] >= 0) atomicMax(&s_cellj1[s_cutcell[tid]], tid + 1);
+  if (tid < kSelMaxCuts) {  // number the tie-group cells
+    const bool is_t = tid < s_ncells && s_celltiled[tid] >= 0;
+    const unsigned bal = __ballot_sync(FULL_MASK, is_t);
+    if (lane == 0) s_wc2[warp] = __popc(bal);
+    s_tmp[tid] = __popc(bal & le_mask) - 1;
+  }
+  __syncthreads();
+  if (tid < s_ncells) {
+    const int cell = tid;
+    int ti = -1;
+    if (s_celltiled[cell] >= 0) {
+      ti = s_tmp[cell];
+      for (int w = 0; w < warp; ++w) ti += s_wc2[w];
+      pl.tkey[ti] = pl.heavy[s_celltiled[cell]];
+      pl.tcell[ti] = cell;
+    }
+    s_celltiled[cell] = ti;
+    pl.cell_bin[cell] = s_cellbin[cell];
+    pl.cell_count[cell] = s_cellcount[cell];
+    pl.cell_tiled[cell] = ti;
+    pl.cell_j0[cell] = s_cellj0[cell];
+    pl.cell_j1[cell] = s_cellj1[cell];
+    if (ti < 0) pl.cell_comp[cell] = s_cellcount[cell];
+  }
+  if (tid == 0) {
+    pl.ncells = s_ncells;
+    pl.ntiled = s_wc2[0] + s_wc2[1] + s_wc2[2] + s_wc2[3];
+  }
+  __syncthreads();
+  const int ncells = s_ncells;
   if (tid < nc) {
+    const int cell = s_cutcell[tid];
     pl.cut_k[tid] = s_k[tid];
     pl.cut_T[tid] = s_T[tid];
-    pl.cut_cell[tid] = s_cutcell[tid];
+    pl.cut_cell[tid] = cell;
     pl.cut_r[tid] = s_r[tid];
-    pl.cut_posoff[tid] = 0;
-    pl.cut_leader[tid] = 0;
+    RunDesc rd{};
+    if (cell >= 0 && s_celltiled[cell] < 0) {  // the whole cell is one run, resolved by its first cut's block
+      pl.cut_posoff[tid] = s_r[tid];
+      rd.leader = tid == s_cellj0[cell];
+      rd.cell = cell;
+      rd.j0 = s_cellj0[cell];
+      rd.nj = s_cellj1[cell] - s_cellj0[cell];
+      rd.start = 0u;
+      rd.len = s_cellcount[cell];
+    }
+    if (cell < 0 || s_celltiled[cell] < 0) pl.run[tid] = rd;  // tiled cells: sel_plan_tiled writes their runs
   }
-  const int ncells = s_ncells;
   uint16_t* map = p.binmap + (size_t)g * kSelBins;
-  for (int bin = tid; bin < nb; bin += kSelThreads) {
+  for (int bin = tid; bin < nb; bin += kSelLocThreads) {
     int l = 0, h = nc;  // number of cuts with T <= bin
     while (l < h) {
       const int mid = (l + h) >> 1;
@@ -440,26 +509,22 @@ __global__ void __launch_bounds__(kSelThreads) sel_locate(const SelParams p) {
   }
 }
 
-// ---- per (cell, tile) counts and the key range of every cell ---------------------------------------------
-__global__ void __launch_bounds__(kSelThreads) sel_cell_counts(const SelParams p) {
-  __shared__ BinTables bt;
-  __shared__ uint32_t s_cnt[kSelMaxCuts];
-  __shared__ uint32_t s_mm[kSelMaxCuts][2];
+// ---- ties: per-tile counts of the tie groups that hold a cut --------------------------------------------------
+__global__ void __launch_bounds__(kSelThreads) sel_tie_counts(const SelParams p) {
+  __shared__ uint32_t s_cnt[kSelMaxHeavy];
+  __shared__ uint32_t s_key[kSelMaxHeavy];
   const int g = blockIdx.y, tid = threadIdx.x;
   const SegPlan& pl = p.plan[g];
-  const int ncells = pl.ncells;
-  if (ncells == 0) return;
+  const int nt = pl.ntiled;
+  if (nt == 0) return;
   int f, b;
   long long lo, len;
   sel_segment(p, g, f, b, lo, len);
   const int t0 = blockIdx.x * p.tiles_per_block;
   if ((long long)t0 * kSelTile >= len) return;
-  const int nh = pl.nheavy;
-  sel_load_tables(p, g, pl, bt, true);
-  if (tid < kSelMaxCuts) {
+  if (tid < kSelMaxHeavy) {
     s_cnt[tid] = 0u;
-    s_mm[tid][0] = 0u;
-    s_mm[tid][1] = 0u;
+    s_key[tid] = tid < nt ? pl.tkey[tid] : 0xFFFFFFFFu;
   }
   __syncthreads();
   const float* k = p.keys[f] + lo;
@@ -471,45 +536,38 @@ __global__ void __launch_bounds__(kSelThreads) sel_cell_counts(const SelParams p
     float v[kSelItems];
 #pragma unroll
     for (int i = 0; i < kSelItems; ++i) v[i] = __ldg(k + tile_lo + min(i * kSelThreads + tid, count - 1));
+    for (int h = 0; h < nt; ++h) {
+      const uint32_t want = s_key[h];
+      uint32_t c = 0;
 #pragma unroll
-    for (int i = 0; i < kSelItems; ++i) {
-      if (i * kSelThreads + tid < count) {
-        const uint32_t key = sort_key_from_float(v[i]);
-        const uint16_t m = bt.map[sel_bin(key, bt.tab[key >> kSelLowBits], bt.heavy, nh)];
-        if (m & kSelCellFlag) {
-          const int cell = m & 0x7FFF;
-          atomicAdd(&s_cnt[cell], 1u);
-          atomicMax(&s_mm[cell][0], ~key);
-          atomicMax(&s_mm[cell][1], key);
-        }
-      }
+      for (int i = 0; i < kSelItems; ++i)
+        c += (i * kSelThreads + tid < count) && sort_key_from_float(v[i]) == want;
+      c = __reduce_add_sync(FULL_MASK, c);
+      if ((tid & 31) == 0 && c) atomicAdd(&s_cnt[h], c);
     }
     __syncthreads();
-    if (tid < ncells) {
-      p.tilecounts[((size_t)g * p.num_cuts + tid) * p.max_tiles + t] = s_cnt[tid];
+    if (tid < nt) {
+      p.tilecounts[((size_t)g * kSelMaxHeavy + tid) * p.max_tiles + t] = s_cnt[tid];
       s_cnt[tid] = 0u;
     }
     __syncthreads();
   }
-  if (tid < ncells && (s_mm[tid][0] | s_mm[tid][1])) {
-    atomicMax(p.cell_mm + ((size_t)g * kSelMaxCuts + tid) * 2, s_mm[tid][0]);
-    atomicMax(p.cell_mm + ((size_t)g * kSelMaxCuts + tid) * 2 + 1, s_mm[tid][1]);
-  }
 }
 
-// ---- plan: one block per (cell, segment) ---------------------------------------------------------------
-__global__ void __launch_bounds__(kSelThreads) sel_plan_cells(const SelParams p) {
+// ---- plan of the tie groups: one block per (tiled cell, segment) ------------------------------------------------
+__global__ void __launch_bounds__(kSelThreads) sel_plan_tiled(const SelParams p) {
   __shared__ uint32_t warp_tmp[kSelWarps];
   __shared__ int s_tstar[kSelMaxCuts];
   __shared__ uint32_t s_rho[kSelMaxCuts];
-  const int cell = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
+  const int h = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
   SegPlan& pl = p.plan[g];
-  if (cell >= pl.ncells) return;
+  if (h >= pl.ntiled) return;
+  const int cell = pl.tcell[h];
   int f, b;
   long long lo, len;
   sel_segment(p, g, f, b, lo, len);
   const int ntiles = (int)((len + kSelTile - 1) / kSelTile);
-  uint32_t* row = p.tilecounts + ((size_t)g * p.num_cuts + cell) * p.max_tiles;
+  uint32_t* row = p.tilecounts + ((size_t)g * kSelMaxHeavy + h) * p.max_tiles;
   uint32_t carry = 0;
   for (int base = 0; base < ntiles; base += kSelThreads) {
     const int i = base + tid;
@@ -521,44 +579,27 @@ __global__ void __launch_bounds__(kSelThreads) sel_plan_cells(const SelParams p)
   }
   __syncthreads();
   const uint32_t cell_count = carry;  // == pl.cell_count[cell]
-  const uint32_t* mm = p.cell_mm + ((size_t)g * kSelMaxCuts + cell) * 2;
-  const bool pure = (~mm[0]) == mm[1];
-  const bool tiled = pure && cell_count > kSelTiledMin;
   const int j0 = pl.cell_j0[cell], nj = pl.cell_j1[cell] - j0;
-  uint8_t* mode = p.tilemode + (size_t)g * p.max_tiles * kSelMaxCuts + cell;
-  if (!tiled) {
-    for (int t = tid; t < ntiles; t += kSelThreads) mode[(size_t)t * kSelMaxCuts] = kSelCompact;
-    for (int jj = tid; jj < nj; jj += kSelThreads) {
-      pl.cut_posoff[j0 + jj] = pl.cut_r[j0 + jj];
-      pl.cut_leader[j0 + jj] = jj == 0;
-      pl.cut_run_start[j0 + jj] = 0u;
-      pl.cut_run_len[j0 + jj] = cell_count;
-    }
-    if (tid == 0) {
-      pl.cell_comp[cell] = cell_count;
-      pl.cell_tiled[cell] = 0;
-    }
-    return;
-  }
+  uint8_t* mode = p.tilemode + (size_t)g * p.max_tiles * kSelMaxHeavy + h;
   for (int jj = tid; jj < nj; jj += kSelThreads) {
     const uint32_t r = pl.cut_r[j0 + jj];  // 1 <= r < cell_count
-    int l = 0, h = ntiles - 1;             // largest tile with row[tile] < r
-    while (l < h) {
-      const int mid = (l + h + 1) >> 1;
-      if (row[mid] < r) l = mid; else h = mid - 1;
+    int l = 0, hi = ntiles - 1;            // largest tile with row[tile] < r
+    while (l < hi) {
+      const int mid = (l + hi + 1) >> 1;
+      if (row[mid] < r) l = mid; else hi = mid - 1;
     }
     s_tstar[jj] = l;
     s_rho[jj] = r - row[l];
   }
   __syncthreads();
   for (int t = tid; t < ntiles; t += kSelThreads) {
-    int l = 0, h = nj;  // number of cuts whose tile lies before t
-    while (l < h) {
-      const int mid = (l + h) >> 1;
-      if (s_tstar[mid] < t) l = mid + 1; else h = mid;
+    int l = 0, hi = nj;  // number of cuts whose tile lies before t
+    while (l < hi) {
+      const int mid = (l + hi) >> 1;
+      if (s_tstar[mid] < t) l = mid + 1; else hi = mid;
     }
     const bool star = l < nj && s_tstar[l] == t;
-    mode[(size_t)t * kSelMaxCuts] = star ? kSelCompact : (uint8_t)(j0 + l);
+    mode[(size_t)t * kSelMaxHeavy] = star ? kSelCompact : (uint8_t)(j0 + l);
   }
   if (tid == 0) {
     uint32_t acc = 0, cur = 0, raw = 0;
@@ -572,12 +613,16 @@ __global__ void __launch_bounds__(kSelThreads) sel_plan_cells(const SelParams p)
         row[t] = cur;  // first record of this tile inside the cell's slot (tiles ascend: row[t + 1] is still a prefix)
       }
       pl.cut_posoff[j0 + jj] = cur + s_rho[jj];
-      pl.cut_leader[j0 + jj] = fresh;
-      pl.cut_run_start[j0 + jj] = cur;
-      pl.cut_run_len[j0 + jj] = raw;
+      RunDesc rd{};
+      rd.leader = fresh;
+      rd.cell = cell;
+      rd.j0 = j0;
+      rd.nj = nj;
+      rd.start = cur;
+      rd.len = raw;
+      pl.run[j0 + jj] = rd;
     }
     pl.cell_comp[cell] = acc;
-    pl.cell_tiled[cell] = 1;
   }
 }
 
@@ -588,10 +633,9 @@ __device__ __forceinline__ void sel_cell_bases(const SegPlan& pl, uint32_t* s_ba
   const int tid = threadIdx.x, ncells = pl.ncells;
   if (tid == 0) *s_hot = 0u;
   const uint32_t v = tid < ncells ? pl.cell_comp[tid] : 0u;
-  uint32_t tot;
-  const uint32_t ex = sel_block_excl_scan(v, warp_tmp, &tot);  // syncs
+  const uint32_t ex = sel_block_excl_scan(v, warp_tmp, nullptr);  // syncs
   if (tid <= ncells && tid <= kSelMaxCuts) s_base[tid] = ex;
-  if (tid < ncells && pl.cell_tiled[tid]) atomicMax(s_hot, (pl.cell_count[tid] << 7) | (uint32_t)tid);
+  if (tid < ncells && pl.cell_tiled[tid] >= 0) atomicMax(s_hot, (pl.cell_count[tid] << 7) | (uint32_t)tid);
   __syncthreads();
 }
 
@@ -600,13 +644,14 @@ struct ClassifyShared {
   BinTables bt;
   double sum[kSelMaxCuts + 1][2];
   uint32_t base[kSelMaxCuts + 1];
-  uint32_t slot[kSelMaxCuts];  // first record of (cell, tile) within the segment's side list
-  uint32_t cur[kSelMaxCuts];
+  int8_t tiled[kSelMaxCuts];        // cell -> tiled index or -1
+  uint32_t slot[kSelMaxHeavy];      // first record of (tiled cell, tile) within the segment's side list
+  uint32_t cur[kSelMaxHeavy];
+  uint8_t mode[kSelMaxHeavy];
   uint32_t warp_tmp[kSelWarps];
   uint32_t hot;
   int limb[kSelMaxCuts + 1][2][3];  // per-tile fixed-point class sums (3 x 16 bits), native 32-bit atomics
   uint32_t vmax[2];                 // bits of the largest finite |payload| of the tile
-  uint8_t mode[kSelMaxCuts];
 };
 
 // Class sums without 64-bit shared-memory atomics (those are compare-and-swap loops: ATOMS.CAST.SPIN.64).  Per
@@ -633,15 +678,21 @@ template <int NPAY, bool SELF>
 __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifyShared& sh, int g, int f,
                                                   long long lo, long long len) {
   const int tid = threadIdx.x, lane = tid & 31;
-  const SegPlan& pl = p.plan[g];
-  const int ncells = pl.ncells, nc = p.num_cuts, nh = pl.nheavy;
+  SegPlan& pl = p.plan[g];
+  const int ncells = pl.ncells, nc = p.num_cuts, nh = pl.nheavy, nt = pl.ntiled;
   const int t0 = blockIdx.x * p.tiles_per_block;
   sel_load_tables(p, g, pl, sh.bt, true);
   for (int i = tid; i < (kSelMaxCuts + 1) * 2; i += kSelThreads) (&sh.sum[0][0])[i] = 0.0;
   for (int i = tid; i < (kSelMaxCuts + 1) * 6; i += kSelThreads) (&sh.limb[0][0][0])[i] = 0;
   if (tid < 2) sh.vmax[tid] = 0u;
+  if (tid < kSelMaxCuts) sh.tiled[tid] = tid < ncells ? (int8_t)pl.cell_tiled[tid] : (int8_t)-1;
   sel_cell_bases(pl, sh.base, sh.warp_tmp, &sh.hot);
+  if (blockIdx.x == 0 && tid < nc) {  // the resolve blocks find their slot without redoing the scan
+    const int cell = pl.cut_cell[tid];
+    if (cell >= 0) pl.run[tid].base = sh.base[cell];
+  }
   const int hot = sh.hot ? (int)(sh.hot & 127u) : -1;
+  const int hot_t = hot >= 0 ? (int)sh.tiled[hot] : -1;
   const float* k = p.keys[f] + lo;
   const float* q0 = SELF ? nullptr : p.pay0[f] + lo;
   const float* q1 = NPAY == 2 ? p.pay1[f] + lo : nullptr;
@@ -650,8 +701,9 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
   uint32_t* ci = p.cidx + side;
   float* c0 = SELF ? nullptr : p.cpay0[f] + lo;
   float* c1 = NPAY == 2 ? p.cpay1[f] + lo : nullptr;
-  const uint8_t* modes = p.tilemode + (size_t)g * p.max_tiles * kSelMaxCuts;
-  const uint32_t* rows = p.tilecounts + (size_t)g * p.num_cuts * p.max_tiles;
+  uint32_t* cursor = p.cursor + (size_t)g * kSelMaxCuts;
+  const uint8_t* modes = p.tilemode + (size_t)g * p.max_tiles * kSelMaxHeavy;
+  const uint32_t* rows = p.tilecounts + (size_t)g * kSelMaxHeavy * p.max_tiles;
 
   for (int tt = 0; tt < p.tiles_per_block; ++tt) {
     const int t = t0 + tt;
@@ -659,9 +711,9 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
     if (tile_lo >= len) break;
     const int count = (int)min((long long)kSelTile, len - tile_lo);
     __syncthreads();  // previous tile done with the per-tile tables
-    if (tid < ncells) {
-      sh.mode[tid] = modes[(size_t)t * kSelMaxCuts + tid];
-      sh.slot[tid] = sh.base[tid] + rows[(size_t)tid * p.max_tiles + t];
+    if (tid < nt) {
+      sh.mode[tid] = modes[(size_t)t * kSelMaxHeavy + tid];
+      sh.slot[tid] = sh.base[pl.tcell[tid]] + rows[(size_t)tid * p.max_tiles + t];
       sh.cur[tid] = 0u;
     }
     float kf[kSelItems], a0[kSelItems], a1[kSelItems];
@@ -697,7 +749,7 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
     }
     __syncthreads();  // per-tile tables and maxima visible
     const int emax0 = (int)(sh.vmax[0] >> 23), emax1 = (int)(sh.vmax[1] >> 23);
-    const int hot_cls = hot >= 0 ? (int)sh.mode[hot] : (int)kSelCompact;
+    const int hot_cls = hot_t >= 0 ? (int)sh.mode[hot_t] : (int)kSelCompact;
     double hot0 = 0.0, hot1 = 0.0;
 #pragma unroll
     for (int i = 0; i < kSelItems; ++i) {
@@ -705,31 +757,32 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
       if (pos < count) {
         const uint32_t key = sort_key_from_float(kf[i]);
         const uint16_t m = sh.bt.map[sel_bin(key, sh.bt.tab[key >> kSelLowBits], sh.bt.heavy, nh)];
-        int cls = m;
-        int cell = -1;
         if (m & kSelCellFlag) {
-          cell = m & 0x7FFF;
-          cls = sh.mode[cell];
-        }
-        if (cls == (int)kSelCompact) {  // undecided: a record in the cell's slot (order inside the tile is free:
-          const uint32_t d = sh.slot[cell] + atomicAdd(&sh.cur[cell], 1u);  // records are ranked by (key, index))
-          ck[d] = key;
-          ci[d] = (uint32_t)(tile_lo + pos);
-          if (!SELF) c0[d] = a0[i];
-          if (NPAY == 2) c1[d] = a1[i];
-        } else {
-          const double v0 = (double)(SELF ? kf[i] : a0[i]);
-          if (cell >= 0 && cell == hot) {  // the big tie group: one class per tile, summed in registers
-            hot0 += v0;
+          const int cell = m & 0x7FFF;
+          const int ti = sh.tiled[cell];
+          const int cls = ti >= 0 ? (int)sh.mode[ti] : (int)kSelCompact;
+          if (cls == (int)kSelCompact) {
+            // undecided: a record in the cell's slot (any order: records are ranked by (key, index) later)
+            const uint32_t d = ti >= 0 ? sh.slot[ti] + atomicAdd(&sh.cur[ti], 1u)
+                                       : sh.base[cell] + atomicAdd(cursor + cell, 1u);
+            ck[d] = key;
+            ci[d] = (uint32_t)(tile_lo + pos);
+            if (!SELF) c0[d] = a0[i];
+            if (NPAY == 2) c1[d] = a1[i];
+          } else if (cell == hot) {  // the big tie group: one class per tile, summed in registers
+            hot0 += (double)(SELF ? kf[i] : a0[i]);
             if (NPAY == 2) hot1 += (double)a1[i];
           } else {
             sel_add_payload(sh, cls, 0, SELF ? kf[i] : a0[i], emax0);
             if (NPAY == 2) sel_add_payload(sh, cls, 1, a1[i], emax1);
           }
+        } else {
+          sel_add_payload(sh, (int)m, 0, SELF ? kf[i] : a0[i], emax0);
+          if (NPAY == 2) sel_add_payload(sh, (int)m, 1, a1[i], emax1);
         }
       }
     }
-    if (hot >= 0 && hot_cls != (int)kSelCompact) {  // uniform over the block
+    if (hot_t >= 0 && hot_cls != (int)kSelCompact) {  // uniform over the block
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         hot0 += shfl_xor_double(FULL_MASK, hot0, o);
@@ -770,38 +823,33 @@ __global__ void __launch_bounds__(kSelThreads) sel_classify(const SelParams p) {
 }
 
 // ---- resolve: exact class of every record, one block per run of records ------------------------------------
-__global__ void __launch_bounds__(kSelThreads) sel_resolve(const SelParams p) {
+__global__ void __launch_bounds__(kSelResThreads) sel_resolve(const SelParams p) {
   __shared__ unsigned long long s_comp[kSelBrute];
   __shared__ double s_sum[kSelMaxCuts + 1][2];
   __shared__ uint32_t s_pos[kSelMaxCuts];
   __shared__ unsigned long long s_thr[kSelMaxCuts];
-  __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_base[kSelMaxCuts + 1];
-  __shared__ uint32_t warp_tmp[kSelWarps];
-  __shared__ unsigned long long s_prefix;
-  __shared__ uint32_t s_rank, s_hot, s_nl;
-  __shared__ uint32_t s_or[2], s_dstart[256], s_hotd[256];
+  __shared__ uint32_t s_hist[256], s_dstart[256], s_hotd[256];
   __shared__ uint16_t s_list[kSelBrute];
+  __shared__ uint32_t s_or[2];
+  __shared__ unsigned long long s_prefix;
+  __shared__ uint32_t s_rank, s_nl;
   const int j = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
   const SegPlan& pl = p.plan[g];
-  if (j >= p.num_cuts) return;
-  const int cell = pl.cut_cell[j];
-  if (cell < 0 || !pl.cut_leader[j]) return;
+  const RunDesc rd = pl.run[j];
+  if (!rd.leader) return;
   int f, b;
   long long lo, len;
   sel_segment(p, g, f, b, lo, len);
-  sel_cell_bases(pl, s_base, warp_tmp, &s_hot);
-  const int j0 = pl.cell_j0[cell], nj = pl.cell_j1[cell] - j0;
-  const uint32_t start = pl.cut_run_start[j], rlen = pl.cut_run_len[j];
-  const long long first = lo + s_base[cell] + start;
+  const int j0 = rd.j0, nj = rd.nj;
+  const uint32_t start = rd.start, rlen = rd.len;
+  const long long first = lo + rd.base + start;
   const uint32_t* ck = p.ckeys + (long long)f * p.total + first;
   const uint32_t* ci = p.cidx + (long long)f * p.total + first;
   const bool self = p.self_payload[f] != 0;
   const float* c0 = self ? nullptr : p.cpay0[f] + first;
   const float* c1 = p.pay1[f] ? p.cpay1[f] + first : nullptr;
-  for (int i = tid; i < nj; i += kSelThreads) s_pos[i] = pl.cut_posoff[j0 + i];
-  for (int i = tid; i < (nj + 1) * 2; i += kSelThreads) (&s_sum[0][0])[i] = 0.0;
-  __syncthreads();
+  for (int i = tid; i < nj; i += kSelResThreads) s_pos[i] = pl.cut_posoff[j0 + i];
+  for (int i = tid; i < (nj + 1) * 2; i += kSelResThreads) (&s_sum[0][0])[i] = 0.0;
 
   if (rlen <= (uint32_t)kSelBrute) {
     // bucket the records by the top 8 bits in which their (key, index) composites differ: a bucket that no cut
@@ -811,16 +859,18 @@ __global__ void __launch_bounds__(kSelThreads) sel_resolve(const SelParams p) {
       s_or[1] = 0u;
       s_nl = 0u;
     }
-    s_hist[tid] = 0u;
-    s_hotd[tid] = 0u;
-    for (uint32_t i = tid; i < rlen; i += kSelThreads)
+    for (int i = tid; i < 256; i += kSelResThreads) {
+      s_hist[i] = 0u;
+      s_hotd[i] = 0u;
+    }
+    for (uint32_t i = tid; i < rlen; i += kSelResThreads)
       s_comp[i] = ((unsigned long long)ck[i] << 32) | ci[i];
     __syncthreads();
     {
-      const unsigned long long c0 = s_comp[0];
+      const unsigned long long first_c = s_comp[0];
       uint32_t xl = 0u, xh = 0u;
-      for (uint32_t i = tid; i < rlen; i += kSelThreads) {
-        const unsigned long long x = s_comp[i] ^ c0;
+      for (uint32_t i = tid; i < rlen; i += kSelResThreads) {
+        const unsigned long long x = s_comp[i] ^ first_c;
         xl |= (uint32_t)x;
         xh |= (uint32_t)(x >> 32);
       }
@@ -834,12 +884,22 @@ __global__ void __launch_bounds__(kSelThreads) sel_resolve(const SelParams p) {
     __syncthreads();
     const unsigned long long diff = ((unsigned long long)s_or[1] << 32) | s_or[0];
     const int sh = diff ? max(0, 63 - __clzll((long long)diff) - 7) : 0;
-    for (uint32_t i = tid; i < rlen; i += kSelThreads) atomicAdd(&s_hist[(uint32_t)(s_comp[i] >> sh) & 0xFFu], 1u);
+    for (uint32_t i = tid; i < rlen; i += kSelResThreads)
+      atomicAdd(&s_hist[(uint32_t)(s_comp[i] >> sh) & 0xFFu], 1u);
     __syncthreads();
-    {
-      const uint32_t cnt = s_hist[tid];
-      const uint32_t ex = sel_block_excl_scan(cnt, warp_tmp, nullptr);
-      s_dstart[tid] = ex;
+    if (tid < 32) {  // exclusive scan of the 256 bucket sizes by one warp
+      uint32_t carry = 0;
+      for (int r = 0; r < 8; ++r) {
+        const uint32_t v = s_hist[r * 32 + tid];
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t u = __shfl_up_sync(FULL_MASK, incl, o);
+          if (tid >= o) incl += u;
+        }
+        s_dstart[r * 32 + tid] = carry + incl - v;
+        carry += __shfl_sync(FULL_MASK, incl, 31);
+      }
     }
     __syncthreads();
     if (tid < nj) {  // the bucket that holds the last record under the cut is split iff it also holds the next one
@@ -854,11 +914,18 @@ __global__ void __launch_bounds__(kSelThreads) sel_resolve(const SelParams p) {
       }
     }
     __syncthreads();
-    for (uint32_t i = tid; i < rlen; i += kSelThreads)
+    for (uint32_t i = tid; i < rlen; i += kSelResThreads)
       if (s_hotd[(uint32_t)(s_comp[i] >> sh) & 0xFFu]) s_list[atomicAdd(&s_nl, 1u)] = (uint16_t)i;
     __syncthreads();
     const uint32_t nl = s_nl;
-    for (uint32_t i = tid; i < rlen; i += kSelThreads) {
+    int cls_lo = 0, cls_hi = 0;  // classes are monotone in the position: the run spans [cls_lo, cls_hi]
+    for (int q = 0; q < nj; ++q) {
+      cls_lo += s_pos[q] <= start;
+      cls_hi += s_pos[q] <= start + rlen - 1u;
+    }
+    const bool few = cls_hi - cls_lo <= 3;
+    double acc0[4] = {0.0, 0.0, 0.0, 0.0}, acc1[4] = {0.0, 0.0, 0.0, 0.0};
+    for (uint32_t i = tid; i < rlen; i += kSelResThreads) {
       const unsigned long long mine = s_comp[i];
       const uint32_t d = (uint32_t)(mine >> sh) & 0xFFu;
       uint32_t rank = 0;
@@ -871,19 +938,43 @@ __global__ void __launch_bounds__(kSelThreads) sel_resolve(const SelParams p) {
       int cls = 0;
       for (int q = 0; q < nj; ++q) cls += s_pos[q] <= pos;
       const double v0 = self ? (double)order_key_inv((uint32_t)(mine >> 32)) : (double)c0[i];
-      atomicAdd(&s_sum[cls][0], v0);
-      if (c1) atomicAdd(&s_sum[cls][1], (double)c1[i]);
+      const double v1 = c1 ? (double)c1[i] : 0.0;
+      if (few) {  // all the threads would hammer the same few shared-memory words: sum in registers first
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc0[q] += cls - cls_lo == q ? v0 : 0.0;
+          acc1[q] += cls - cls_lo == q ? v1 : 0.0;
+        }
+      } else {
+        atomicAdd(&s_sum[cls][0], v0);
+        if (c1) atomicAdd(&s_sum[cls][1], v1);
+      }
+    }
+    if (few) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          acc0[q] += shfl_xor_double(FULL_MASK, acc0[q], o);
+          acc1[q] += shfl_xor_double(FULL_MASK, acc1[q], o);
+        }
+        if ((tid & 31) == 0 && cls_lo + q <= nj) {
+          if (acc0[q] != 0.0) atomicAdd(&s_sum[cls_lo + q][0], acc0[q]);
+          if (acc1[q] != 0.0) atomicAdd(&s_sum[cls_lo + q][1], acc1[q]);
+        }
+      }
     }
   } else {
-    // a cell too big to rank pairwise (never a tie-group tile: those hold <= kSelTile records): for every
+    // a cell too big for shared memory (never a tie-group tile: those hold <= kSelTile records): for every
     // cut of the cell, radix-select the record at position posoff - 1, then class = number of thresholds below
+    __syncthreads();
     for (int q = 0; q < nj; ++q) {
       unsigned long long prefix = 0ull, mask = 0ull;
       uint32_t want = s_pos[q] - 1u;  // posoff >= 1
       for (int pass = 7; pass >= 0; --pass) {
-        s_hist[tid] = 0u;
+        for (int i = tid; i < 256; i += kSelResThreads) s_hist[i] = 0u;
         __syncthreads();
-        for (uint32_t i = tid; i < rlen; i += kSelThreads) {
+        for (uint32_t i = tid; i < rlen; i += kSelResThreads) {
           const unsigned long long c = ((unsigned long long)ck[i] << 32) | ci[i];
           if ((c & mask) == prefix) atomicAdd(&s_hist[(uint32_t)(c >> (8 * pass)) & 0xFFu], 1u);
         }
@@ -907,7 +998,7 @@ __global__ void __launch_bounds__(kSelThreads) sel_resolve(const SelParams p) {
       if (tid == 0) s_thr[q] = prefix;
     }
     __syncthreads();
-    for (uint32_t i = tid; i < rlen; i += kSelThreads) {
+    for (uint32_t i = tid; i < rlen; i += kSelResThreads) {
       const unsigned long long c = ((unsigned long long)ck[i] << 32) | ci[i];
       int cls = 0;
       for (int q = 0; q < nj; ++q) cls += s_thr[q] < c;  // excluded from the cuts whose last record precedes it
@@ -918,14 +1009,17 @@ __global__ void __launch_bounds__(kSelThreads) sel_resolve(const SelParams p) {
   }
   __syncthreads();
   double* gs = p.ssum + ((size_t)g * (kSelMaxCuts + 1) + j0) * 2;
-  for (int i = tid; i < (nj + 1) * 2; i += kSelThreads) {
+  for (int i = tid; i < (nj + 1) * 2; i += kSelResThreads) {
     const double v = (&s_sum[0][0])[i];
     if (v != 0.0) atomicAdd(gs + i, v);
   }
 }
 
 // ---- finish: class sums -> sums under every cut, one block per segment ---------------------------------------
-__global__ void __launch_bounds__(kSelThreads) sel_finish(const SelParams p) {
+constexpr int kSelFinThreads = 1024;
+__global__ void __launch_bounds__(kSelFinThreads) sel_finish(const SelParams p) {
+  constexpr int kSlices = kSelFinThreads / 256;
+  __shared__ double s_part[kSlices][(kSelMaxCuts + 1) * 2];
   __shared__ double s_tot[(kSelMaxCuts + 1) * 2];
   const int g = blockIdx.x, tid = threadIdx.x, nc = p.num_cuts;
   int f, b;
@@ -933,12 +1027,29 @@ __global__ void __launch_bounds__(kSelThreads) sel_finish(const SelParams p) {
   sel_segment(p, g, f, b, lo, len);
   const int ntiles = (int)((len + kSelTile - 1) / kSelTile);
   const int nblk = (ntiles + p.tiles_per_block - 1) / p.tiles_per_block;
-  const size_t stride = (size_t)(nc + 1) * 2;
+  const int stride = (nc + 1) * 2;
   const double* sp = p.spart + (size_t)g * p.max_blocks * stride;
   const double* gs = p.ssum + (size_t)g * (kSelMaxCuts + 1) * 2;
-  for (int i = tid; i < (int)stride; i += kSelThreads) {
+  const int slice = tid >> 8;
+  for (int i = tid & 255; i < stride; i += 256) {  // slice s adds blocks s, s + kSlices, ... (8 loads in flight)
+    double s = 0.0;
+    for (int blk0 = slice; blk0 < nblk; blk0 += 8 * kSlices) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int blk = blk0 + u * kSlices;
+        v[u] = blk < nblk ? sp[(size_t)blk * stride + i] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    s_part[slice][i] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < stride; i += kSelFinThreads) {
     double s = gs[i];
-    for (int blk = 0; blk < nblk; ++blk) s += sp[(size_t)blk * stride + i];
+#pragma unroll
+    for (int q = 0; q < kSlices; ++q) s += s_part[q][i];
     s_tot[i] = s;
   }
   __syncthreads();
@@ -954,7 +1065,7 @@ __global__ void __launch_bounds__(kSelThreads) sel_finish(const SelParams p) {
 }
 
 struct SelLayout {
-  size_t off_zero, zero_bytes, off_histc, off_histf, off_cellmm, off_ssum;
+  size_t off_zero, zero_bytes, off_histc, off_histf, off_cursor, off_ssum;
   size_t off_table, off_plan, off_binmap, off_tilecounts, off_tilemode, off_spart, off_ckeys, off_cidx, off_cpay,
       total;
   int max_tiles, max_blocks, tiles_per_block, G;
@@ -967,7 +1078,7 @@ static SelLayout sel_layout(int F, int B, int num_cuts, int num_side_arrays, lon
   if (l.max_tiles < 1) l.max_tiles = 1;
   // blocks of the counting / classifying passes: enough of them to fill the device, each as long as that
   // allows (a block stages 50 KB of binning tables)
-  long long tpb = (long long)l.max_tiles * l.G / 1184;
+  long long tpb = (long long)l.max_tiles * l.G / 600;
   l.tiles_per_block = (int)(tpb < 1 ? 1 : tpb > kSelMaxTilesPerBlock ? kSelMaxTilesPerBlock : tpb);
   l.max_blocks = (l.max_tiles + l.tiles_per_block - 1) / l.tiles_per_block;
   const size_t G = (size_t)l.G;
@@ -980,14 +1091,14 @@ static SelLayout sel_layout(int F, int B, int num_cuts, int num_side_arrays, lon
   l.off_zero = o;
   l.off_histc = take(G * kSelCoarse * sizeof(uint32_t));
   l.off_histf = take(G * kSelBins * sizeof(uint32_t));
-  l.off_cellmm = take(G * kSelMaxCuts * 2 * sizeof(uint32_t));
+  l.off_cursor = take(G * kSelMaxCuts * sizeof(uint32_t));
   l.off_ssum = take(G * (kSelMaxCuts + 1) * 2 * sizeof(double));
   l.zero_bytes = o - l.off_zero;
   l.off_table = take(G * kSelCoarse * sizeof(uint32_t));
   l.off_plan = take(G * sizeof(SegPlan));
   l.off_binmap = take(G * kSelBins * sizeof(uint16_t));
-  l.off_tilecounts = take(G * (size_t)num_cuts * l.max_tiles * sizeof(uint32_t));
-  l.off_tilemode = take(G * (size_t)l.max_tiles * kSelMaxCuts);
+  l.off_tilecounts = take(G * (size_t)kSelMaxHeavy * l.max_tiles * sizeof(uint32_t));
+  l.off_tilemode = take(G * (size_t)l.max_tiles * kSelMaxHeavy);
   l.off_spart = take(G * (size_t)l.max_blocks * (num_cuts + 1) * 2 * sizeof(double));
   l.off_ckeys = take((size_t)F * total * sizeof(uint32_t));
   l.off_cidx = take((size_t)F * total * sizeof(uint32_t));
@@ -1057,7 +1168,7 @@ int ub_cut_select_sums(const float* const* keys_host, const float* const* pay0_h
   p.out = out_sums;
   p.hist_c = reinterpret_cast<uint32_t*>(ws + lay.off_histc);
   p.hist_f = reinterpret_cast<uint32_t*>(ws + lay.off_histf);
-  p.cell_mm = reinterpret_cast<uint32_t*>(ws + lay.off_cellmm);
+  p.cursor = reinterpret_cast<uint32_t*>(ws + lay.off_cursor);
   p.ssum = reinterpret_cast<double*>(ws + lay.off_ssum);
   p.table = reinterpret_cast<uint32_t*>(ws + lay.off_table);
   p.plan = reinterpret_cast<SegPlan*>(ws + lay.off_plan);
@@ -1086,12 +1197,12 @@ int ub_cut_select_sums(const float* const* keys_host, const float* const* pay0_h
   sel_coarse_hist<<<grid_chunks, kSelThreads, 0, stream>>>(p);
   sel_alloc<<<G, kSelThreads, 0, stream>>>(p);
   sel_fine_hist<<<grid_chunks, kSelThreads, 0, stream>>>(p);
-  sel_locate<<<G, kSelThreads, 0, stream>>>(p);
-  sel_cell_counts<<<grid_blocks, kSelThreads, 0, stream>>>(p);
-  sel_plan_cells<<<grid_cells, kSelThreads, 0, stream>>>(p);
+  sel_locate<<<G, kSelLocThreads, 0, stream>>>(p);
+  sel_tie_counts<<<grid_blocks, kSelThreads, 0, stream>>>(p);
+  sel_plan_tiled<<<dim3(kSelMaxHeavy, (unsigned)G), kSelThreads, 0, stream>>>(p);
   sel_classify<<<grid_blocks, kSelThreads, 0, stream>>>(p);
-  sel_resolve<<<grid_cells, kSelThreads, 0, stream>>>(p);
-  sel_finish<<<G, kSelThreads, 0, stream>>>(p);
+  sel_resolve<<<grid_cells, kSelResThreads, 0, stream>>>(p);
+  sel_finish<<<G, kSelFinThreads, 0, stream>>>(p);
   return check_launch("cut_select_sums");
 }
 
