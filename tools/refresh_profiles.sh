@@ -14,7 +14,7 @@ ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.s
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $out/${tag}_launches_bench.log 2>&1
 # one full capture of the heaviest kernels of the step
 ncu --profile-from-start off --set full --import-source on --clock-control none \
-    -k regex:'composite_rays_tma|reduce_members_batched|sort_downsweep|score_prologue_kernel' -c 8 -f -o $out/${tag}_full \
+    -k regex:'composite_rays_tma|reduce_members_batched|sel_classify|score_prologue_kernel' -c 8 -f -o $out/${tag}_full \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $out/${tag}_full.log 2>&1
 python tools/perf_kernels.py > $out/${tag}_perf_kernels.jsonl 2> $out/${tag}_perf_kernels.err
 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
