@@ -46,7 +46,7 @@ constexpr int kSelSample = 1024;   // keys sampled per segment to find the heavy
 constexpr int kSelHeavyHits = 8;   // sample hits that make a key heavy (~0.8 % of the segment)
 constexpr int kSelTile = 2048;     // classification tile
 constexpr int kSelItems = kSelTile / kSelThreads;
-constexpr int kSelMaxTilesPerBlock = 16;
+constexpr int kSelMaxTilesPerBlock = 8;   // 16384 keys: the 16-bit fixed-point limbs of a block stay below 2^31
 constexpr int kSelChunk = 8192;    // keys per block in the histogram kernels
 constexpr int kSelMaxCuts = 128;
 constexpr int kSelMaxFamilies = 4;
@@ -64,7 +64,9 @@ struct RunDesc {        // what the resolve block of cut j works on
 };
 
 struct SegPlan {
-  int nfine, nbins, ncells, nheavy, ntiled, pad0, pad1, pad2;
+  int nfine, nbins, ncells, nheavy, ntiled;
+  int emax;  // biased exponent of the largest finite |key| of the segment
+  int pad1, pad2;
   uint32_t heavy[kSelMaxHeavy];      // heavy tie values (any order)
   uint32_t tkey[kSelMaxHeavy];       // tiled cells: tie groups that hold a cut and are resolved by tile
   int tcell[kSelMaxHeavy];
@@ -88,6 +90,7 @@ struct SelParams {
   int self_payload[kSelMaxFamilies];   // payload 0 is the key itself
   int row0[kSelMaxFamilies];           // first output row of the family
   int npay[kSelMaxFamilies];
+  int pay_src[kSelMaxFamilies][2];     // family whose keys are this payload array (its magnitude bound is known), or -1
   float* cpay0[kSelMaxFamilies];       // record payloads [total] (NULL when self_payload)
   float* cpay1[kSelMaxFamilies];
   int num_families, num_views, num_values, num_cuts;
@@ -212,9 +215,15 @@ __global__ void __launch_bounds__(kSelThreads) sel_alloc(const SelParams p) {
   constexpr int per = kSelCoarse / kSelThreads;
   const uint32_t* gh = p.hist_c + (size_t)g * kSelCoarse;
   uint32_t nsub[per], lg[per], sum = 0;
+  int emax = 0;
 #pragma unroll
   for (int i = 0; i < per; ++i) {
     const uint32_t cnt = gh[tid * per + i];
+    if (cnt) {  // exponent field of the keys of this coarse bin (sign, 8 exponent bits, 3 mantissa bits)
+      const int c = tid * per + i;
+      const int ex = ((c >= 2048 ? c : ~c) >> 3) & 0xFF;
+      if (ex != 255) emax = max(emax, ex);
+    }
     uint32_t l = 0;
     if (cnt > target) {
       const uint32_t q = (cnt + target - 1) / target;  // >= 2
@@ -254,8 +263,12 @@ __global__ void __launch_bounds__(kSelThreads) sel_alloc(const SelParams p) {
       __syncthreads();
     }
   }
-  __shared__ int s_nh;
+  __shared__ int s_nh, s_emax;
   __shared__ uint32_t s_hv[kSelMaxHeavy];
+  if (tid == 0) s_emax = 0;
+  __syncthreads();
+  emax = __reduce_max_sync(FULL_MASK, emax);
+  if ((tid & 31) == 0 && emax) atomicMax(&s_emax, emax);
   for (int thresh = kSelHeavyHits;; thresh *= 2) {  // at most kSelMaxHeavy values: raise the bar until they fit
     if (tid == 0) s_nh = 0;
     __syncthreads();
@@ -274,6 +287,7 @@ __global__ void __launch_bounds__(kSelThreads) sel_alloc(const SelParams p) {
   const int nh = s_nh;
   if (tid < kSelMaxHeavy) pl.heavy[tid] = tid < nh ? s_hv[tid] : 0xFFFFFFFFu;
   if (tid == 0) {
+    pl.emax = s_emax;
     pl.nheavy = nh;
     pl.nfine = (int)tot;  // <= kSelFine: sum pow2ceil(cnt / target) <= 4096 + 2 n / target
     pl.nbins = (int)tot + 2 * nh;
@@ -655,7 +669,7 @@ struct ClassifyShared {
 };
 
 // Class sums without 64-bit shared-memory atomics (those are compare-and-swap loops: ATOMS.CAST.SPIN.64).  Per
-// tile and payload array the largest finite magnitude fixes a scale 2^(E - 174) (E = its biased exponent); a value
+// segment (or block) and payload array the largest finite magnitude fixes a scale 2^(E - 174) (E = its biased exponent); a value
 // whose lowest mantissa bit is a multiple of that scale -- everything within 2^24 of the maximum -- is an exact
 // integer q < 2^49 and is added as three 16-bit limbs with native integer atomics (exact, order-independent);
 // the few values below that, denormals, NaN and inf take the float64 compare-and-swap add.
@@ -663,7 +677,7 @@ __device__ __forceinline__ void sel_add_payload(ClassifyShared& sh, int cls, int
   const uint32_t bits = __float_as_uint(v);
   const int be = (int)((bits >> 23) & 0xFFu);
   if ((bits << 1) == 0u) return;  // +-0 adds nothing
-  if (be != 0 && be != 255 && be + 24 >= emax) {
+  if (be != 0 && be != 255 && be + 24 >= emax && be <= emax) {
     long long q = (long long)((bits & 0x7FFFFFu) | 0x800000u) << (be + 24 - emax);
     if (bits >> 31) q = -q;
     atomicAdd(&sh.limb[cls][pidx][0], (int)(q & 0xFFFF));
@@ -675,7 +689,7 @@ __device__ __forceinline__ void sel_add_payload(ClassifyShared& sh, int cls, int
 }
 
 template <int NPAY, bool SELF>
-__device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifyShared& sh, int g, int f,
+__device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifyShared& sh, int g, int f, int b,
                                                   long long lo, long long len) {
   const int tid = threadIdx.x, lane = tid & 31;
   SegPlan& pl = p.plan[g];
@@ -705,50 +719,74 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
   const uint8_t* modes = p.tilemode + (size_t)g * p.max_tiles * kSelMaxHeavy;
   const uint32_t* rows = p.tilecounts + (size_t)g * kSelMaxHeavy * p.max_tiles;
 
+  // scale of the fixed-point class sums: exponent of the largest finite magnitude of each payload array over
+  // the segment -- known from the coarse histogram when the payload is the key array of a family (the AUSE
+  // call: the errors are the keys of the two error-sorted families), else the largest of this block's keys
+  int emax0 = p.pay_src[f][0] >= 0 ? p.plan[p.pay_src[f][0] * p.num_views + b].emax : -1;
+  int emax1 = NPAY == 2 ? (p.pay_src[f][1] >= 0 ? p.plan[p.pay_src[f][1] * p.num_views + b].emax : -1) : 0;
+  if (emax0 < 0 || emax1 < 0) {  // uniform over the block
+    uint32_t m0 = 0u, m1 = 0u;
+    const long long blk_lo = (long long)t0 * kSelTile;
+    const long long blk_hi = min(len, blk_lo + (long long)p.tiles_per_block * kSelTile);
+    for (long long i = blk_lo + tid; i < blk_hi; i += kSelThreads) {
+      if (emax0 < 0) {
+        const uint32_t b0 = __float_as_uint(SELF ? k[i] : q0[i]) & 0x7FFFFFFFu;
+        if (b0 < 0x7F800000u) m0 = max(m0, b0);
+      }
+      if (NPAY == 2 && emax1 < 0) {
+        const uint32_t b1 = __float_as_uint(q1[i]) & 0x7FFFFFFFu;
+        if (b1 < 0x7F800000u) m1 = max(m1, b1);
+      }
+    }
+    m0 = __reduce_max_sync(FULL_MASK, m0);
+    m1 = __reduce_max_sync(FULL_MASK, m1);
+    if (lane == 0) {
+      if (m0) atomicMax(&sh.vmax[0], m0);
+      if (m1) atomicMax(&sh.vmax[1], m1);
+    }
+    __syncthreads();
+    if (emax0 < 0) emax0 = (int)(sh.vmax[0] >> 23);
+    if (emax1 < 0) emax1 = (int)(sh.vmax[1] >> 23);
+  }
+
   for (int tt = 0; tt < p.tiles_per_block; ++tt) {
     const int t = t0 + tt;
     const long long tile_lo = (long long)t * kSelTile;
     if (tile_lo >= len) break;
     const int count = (int)min((long long)kSelTile, len - tile_lo);
-    __syncthreads();  // previous tile done with the per-tile tables
-    if (tid < nt) {
-      sh.mode[tid] = modes[(size_t)t * kSelMaxHeavy + tid];
-      sh.slot[tid] = sh.base[pl.tcell[tid]] + rows[(size_t)tid * p.max_tiles + t];
-      sh.cur[tid] = 0u;
+    if (nt > 0) {  // per-tile tables of the tie groups (uniform over the block)
+      __syncthreads();
+      if (tid < nt) {
+        sh.mode[tid] = modes[(size_t)t * kSelMaxHeavy + tid];
+        sh.slot[tid] = sh.base[pl.tcell[tid]] + rows[(size_t)tid * p.max_tiles + t];
+        sh.cur[tid] = 0u;
+      }
     }
     float kf[kSelItems], a0[kSelItems], a1[kSelItems];
+    if (count == kSelTile) {
 #pragma unroll
-    for (int i = 0; i < kSelItems; ++i) kf[i] = __ldcs(k + tile_lo + min(i * kSelThreads + tid, count - 1));
-    if (!SELF) {
+      for (int i = 0; i < kSelItems; ++i) kf[i] = __ldcs(k + tile_lo + i * kSelThreads + tid);
+      if (!SELF) {
 #pragma unroll
-      for (int i = 0; i < kSelItems; ++i) a0[i] = __ldcs(q0 + tile_lo + min(i * kSelThreads + tid, count - 1));
-    }
-    if (NPAY == 2) {
-#pragma unroll
-      for (int i = 0; i < kSelItems; ++i) a1[i] = __ldcs(q1 + tile_lo + min(i * kSelThreads + tid, count - 1));
-    }
-    {  // largest finite payload magnitudes of the tile
-      uint32_t m0 = 0u, m1 = 0u;
-#pragma unroll
-      for (int i = 0; i < kSelItems; ++i) {
-        if (i * kSelThreads + tid < count) {
-          const uint32_t b0 = __float_as_uint(SELF ? kf[i] : a0[i]) & 0x7FFFFFFFu;
-          if (b0 < 0x7F800000u) m0 = max(m0, b0);
-          if (NPAY == 2) {
-            const uint32_t b1 = __float_as_uint(a1[i]) & 0x7FFFFFFFu;
-            if (b1 < 0x7F800000u) m1 = max(m1, b1);
-          }
-        }
+        for (int i = 0; i < kSelItems; ++i) a0[i] = __ldcs(q0 + tile_lo + i * kSelThreads + tid);
       }
-      m0 = __reduce_max_sync(FULL_MASK, m0);
-      if (NPAY == 2) m1 = __reduce_max_sync(FULL_MASK, m1);
-      if (lane == 0) {
-        if (m0) atomicMax(&sh.vmax[0], m0);
-        if (NPAY == 2 && m1) atomicMax(&sh.vmax[1], m1);
+      if (NPAY == 2) {
+#pragma unroll
+        for (int i = 0; i < kSelItems; ++i) a1[i] = __ldcs(q1 + tile_lo + i * kSelThreads + tid);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kSelItems; ++i) kf[i] = __ldcs(k + tile_lo + min(i * kSelThreads + tid, count - 1));
+      if (!SELF) {
+#pragma unroll
+        for (int i = 0; i < kSelItems; ++i) a0[i] = __ldcs(q0 + tile_lo + min(i * kSelThreads + tid, count - 1));
+      }
+      if (NPAY == 2) {
+#pragma unroll
+        for (int i = 0; i < kSelItems; ++i) a1[i] = __ldcs(q1 + tile_lo + min(i * kSelThreads + tid, count - 1));
       }
     }
-    __syncthreads();  // per-tile tables and maxima visible
-    const int emax0 = (int)(sh.vmax[0] >> 23), emax1 = (int)(sh.vmax[1] >> 23);
+    if (nt > 0) __syncthreads();  // per-tile tables visible
     const int hot_cls = hot_t >= 0 ? (int)sh.mode[hot_t] : (int)kSelCompact;
     double hot0 = 0.0, hot1 = 0.0;
 #pragma unroll
@@ -793,21 +831,16 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
         if (NPAY == 2) atomicAdd(&sh.sum[hot_cls][1], hot1);
       }
     }
-    __syncthreads();  // all adds of the tile done: fold the limbs into the float64 sums
-    for (int i = tid; i < (nc + 1) * 2; i += kSelThreads) {
-      int* l = &sh.limb[0][0][0] + i * 3;
-      const long long tot = ((long long)l[2] << 32) + ((long long)l[1] << 16) + (long long)l[0];
-      if (tot != 0) (&sh.sum[0][0])[i] += ldexp((double)tot, (int)(sh.vmax[i & 1] >> 23) - 174);
-      l[0] = 0;
-      l[1] = 0;
-      l[2] = 0;
-    }
-    __syncthreads();
-    if (tid < 2) sh.vmax[tid] = 0u;
   }
-  __syncthreads();
+  __syncthreads();  // all adds of the block done: fold the limbs into the float64 sums
   double* sp = p.spart + ((size_t)g * p.max_blocks + blockIdx.x) * (size_t)(nc + 1) * 2;
-  for (int i = tid; i < (nc + 1) * 2; i += kSelThreads) sp[i] = (&sh.sum[0][0])[i];
+  for (int i = tid; i < (nc + 1) * 2; i += kSelThreads) {
+    const int* l = &sh.limb[0][0][0] + i * 3;
+    const long long tot = ((long long)l[2] << 32) + ((long long)l[1] << 16) + (long long)l[0];
+    double v = (&sh.sum[0][0])[i];
+    if (tot != 0) v += ldexp((double)tot, ((i & 1) ? emax1 : emax0) - 174);
+    sp[i] = v;
+  }
 }
 
 __global__ void __launch_bounds__(kSelThreads) sel_classify(const SelParams p) {
@@ -817,9 +850,9 @@ __global__ void __launch_bounds__(kSelThreads) sel_classify(const SelParams p) {
   long long lo, len;
   sel_segment(p, g, f, b, lo, len);
   if ((long long)blockIdx.x * p.tiles_per_block * kSelTile >= len) return;
-  if (p.self_payload[f]) sel_classify_body<1, true>(p, sh, g, f, lo, len);
-  else if (p.pay1[f]) sel_classify_body<2, false>(p, sh, g, f, lo, len);
-  else sel_classify_body<1, false>(p, sh, g, f, lo, len);
+  if (p.self_payload[f]) sel_classify_body<1, true>(p, sh, g, f, b, lo, len);
+  else if (p.pay1[f]) sel_classify_body<2, false>(p, sh, g, f, b, lo, len);
+  else sel_classify_body<1, false>(p, sh, g, f, b, lo, len);
 }
 
 // ---- resolve: exact class of every record, one block per run of records ------------------------------------
@@ -1146,6 +1179,11 @@ int ub_cut_select_sums(const float* const* keys_host, const float* const* pay0_h
     p.pay1[f] = pay1_host ? pay1_host[f] : nullptr;
     p.self_payload[f] = p.pay0[f] == p.keys[f] && p.pay1[f] == nullptr;
     p.npay[f] = p.pay1[f] ? 2 : 1;
+    p.pay_src[f][0] = p.pay_src[f][1] = -1;
+    for (int f2 = 0; f2 < num_families; ++f2) {
+      if (keys_host[f2] == p.pay0[f]) p.pay_src[f][0] = f2;
+      if (p.pay1[f] && keys_host[f2] == p.pay1[f]) p.pay_src[f][1] = f2;
+    }
     p.row0[f] = V;
     V += p.npay[f];
     if (!p.self_payload[f]) side += p.npay[f];
