@@ -6,17 +6,17 @@ set -u
 tag=${1:-r1}
 out=gpurun_out
 mkdir -p $out
-python bench.py --steps 30 --warmup 5 2> $out/${tag}_bench.err | tail -1 > $out/${tag}_bench_n1.json
-python bench.py --impl reference --steps 2 --warmup 1 2>> $out/${tag}_bench.err | tail -1 > $out/${tag}_bench_reference.json
+timeout 400 python bench.py --steps 30 --warmup 5 2> $out/${tag}_bench.err | tail -1 > $out/${tag}_bench_n1.json
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>> $out/${tag}_bench.err | tail -1 > $out/${tag}_bench_reference.json
 # launch list of the timed region (per-launch durations, cold cache, serialised: compare shares)
-ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $out/${tag}_launches_bench.log 2>&1
 # one full capture of the heaviest kernels of the step
-ncu --profile-from-start off --set full --import-source on --clock-control none \
+timeout 400 ncu --profile-from-start off --set full --import-source on --clock-control none \
     -k regex:'composite_rays_tma|reduce_members_batched|sel_classify|score_prologue_kernel' -c 8 -f -o $out/${tag}_full \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $out/${tag}_full.log 2>&1
-python tools/perf_kernels.py > $out/${tag}_perf_kernels.jsonl 2> $out/${tag}_perf_kernels.err
-ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+timeout 400 python tools/perf_kernels.py > $out/${tag}_perf_kernels.jsonl 2> $out/${tag}_perf_kernels.err
+timeout 200 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none --csv --log-file $out/${tag}_score16_launches.csv python tools/profile_score.py > $out/${tag}_score16.log 2>&1
 echo done
