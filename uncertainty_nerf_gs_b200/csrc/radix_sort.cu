@@ -18,7 +18,6 @@
 // writes straight into the caller's outputs.  Ping-pong buffers live in the workspace and stay
 // L2-resident for image-sized segments.
 #include "ub_common.cuh"
-#include "sort_internal.cuh"
 
 namespace ub {
 
@@ -36,7 +35,6 @@ struct SortPass {
   float* out_float;          // last pass: sorted keys as float (may be NULL)
   int32_t* out_vals;         // NULL for keys-only
   const long long* seg_offsets;
-  const long long* seg_lens;  // optional: used length of every segment (<= its slot); NULL = the whole slot
   uint32_t* counts;          // [num_segments][kRadix][max_tiles]
   uint32_t* totals;          // [num_segments][kRadix]
   int max_tiles;
@@ -45,9 +43,6 @@ struct SortPass {
   int last_pass;
 };
 
-__device__ __forceinline__ long long seg_len(const SortPass& p, int seg) {
-  return p.seg_lens ? p.seg_lens[seg] : p.seg_offsets[seg + 1] - p.seg_offsets[seg];
-}
 __device__ __forceinline__ uint32_t load_key(const SortPass& p, long long gidx) {
   return p.first_pass ? sort_key_from_float(p.in_float[gidx]) : p.in_keys[gidx];
 }
@@ -81,7 +76,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_upsweep(const SortPass p) {
   __shared__ uint32_t hist[kSortWarps][kRadix];
   const int seg = blockIdx.y, tile = blockIdx.x;
   const long long seg_lo = p.seg_offsets[seg];
-  const long long len = seg_len(p, seg);
+  const long long len = p.seg_offsets[seg + 1] - seg_lo;
   const long long tile_lo = (long long)tile * kTile;
   if (tile_lo >= len) return;
   const int warp = threadIdx.x >> 5;
@@ -104,7 +99,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scan_rows(const SortPass p)
   __shared__ uint32_t warp_tmp[kSortWarps];
   __shared__ uint32_t chunk_total;
   const int d = blockIdx.x, seg = blockIdx.y;
-  const long long len = seg_len(p, seg);
+  const long long len = p.seg_offsets[seg + 1] - p.seg_offsets[seg];
   const int tiles = (int)((len + kTile - 1) / kTile);
   uint32_t* row = p.counts + ((size_t)seg * kRadix + d) * p.max_tiles;
   uint32_t carry = 0;
@@ -130,7 +125,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) sort_downsweep(const SortPass
 
   const int seg = blockIdx.y, tile = blockIdx.x;
   const long long seg_lo = p.seg_offsets[seg];
-  const long long len = seg_len(p, seg);
+  const long long len = p.seg_offsets[seg + 1] - seg_lo;
   const long long tile_lo = (long long)tile * kTile;
   if (tile_lo >= len) return;
   const int count = (int)min((long long)kTile, len - tile_lo);
@@ -288,11 +283,7 @@ struct CutParams {
   const int32_t* perms[kMaxCutValues];  // per value array: gather permutation or NULL
   int num_values;
   const long long* seg_offsets;
-  const long long* seg_lens;     // optional [num_values or 1][num_segments] used lengths; NULL = whole slots
-  long long lens_value_stride;   // 0: one length table for every value array
-  const long long* cuts;  // [num_values or 1][num_segments][num_cuts]
-  long long cuts_value_stride;   // 0: one cut table for every value array
-  const double* add;      // optional [num_segments][num_values][num_cuts], added to the result
+  const long long* cuts;  // [num_segments][num_cuts]
   int num_cuts;
   double* block_tot;  // [num_segments][num_values][max_blocks]
   int max_blocks;
@@ -316,7 +307,7 @@ __global__ void __launch_bounds__(kCutThreads) cut_block_totals(const CutParams 
   __shared__ double red[kCutThreads / 32];
   const int blk = blockIdx.x, v = blockIdx.y, seg = blockIdx.z;
   const long long seg_lo = p.seg_offsets[seg];
-  const long long len = p.seg_lens ? p.seg_lens[v * p.lens_value_stride + seg] : p.seg_offsets[seg + 1] - seg_lo;
+  const long long len = p.seg_offsets[seg + 1] - seg_lo;
   const long long lo = (long long)blk * kCutChunk;
   if (lo >= len) return;
   const long long hi = min(len, lo + kCutChunk);
@@ -336,7 +327,7 @@ __global__ void __launch_bounds__(kCutThreads) cut_prefix_finish(const CutParams
   __shared__ double red[kCutThreads / 32];
   const int c = blockIdx.x, v = blockIdx.y, seg = blockIdx.z;
   const long long seg_lo = p.seg_offsets[seg];
-  const long long cut = p.cuts[v * p.cuts_value_stride + (size_t)seg * p.num_cuts + c];
+  const long long cut = p.cuts[(size_t)seg * p.num_cuts + c];
   const long long full_blocks = cut / kCutChunk;
   const double* bt = p.block_tot + ((size_t)seg * p.num_values + v) * p.max_blocks;
   const float* val = p.values[v];
@@ -348,10 +339,7 @@ __global__ void __launch_bounds__(kCutThreads) cut_prefix_finish(const CutParams
     acc += (double)val[src];
   }
   const double t = block_sum_256(acc, red);
-  if (threadIdx.x == 0) {
-    const size_t o = ((size_t)seg * p.num_values + v) * p.num_cuts + c;
-    p.out[o] = p.add ? p.add[o] + t : t;
-  }
+  if (threadIdx.x == 0) p.out[((size_t)seg * p.num_values + v) * p.num_cuts + c] = t;
 }
 
 struct CutLayout {
@@ -373,17 +361,20 @@ static CutLayout cut_layout(int num_segments, long long max_len, int num_values,
   return l;
 }
 
+}  // namespace ub
 
-size_t segmented_sort_workspace(int num_segments, long long total, long long max_len, bool with_vals) {
-  return sort_layout(num_segments, total, max_len, with_vals).total;
-}
-size_t cut_prefix_workspace(int num_segments, long long max_len, int num_values, int num_cuts) {
-  return cut_layout(num_segments, max_len, num_values, num_cuts).total;
+extern "C" {
+
+size_t ub_segmented_sort_workspace_bytes(int32_t num_segments, int64_t total, int64_t max_segment_len,
+                                         int32_t with_perm) {
+  if (num_segments < 1 || total < 0 || max_segment_len < 0) return 256;
+  return ub::sort_layout(num_segments, total, max_segment_len, with_perm != 0).total;
 }
 
-int segmented_sort_impl(const float* keys, int32_t num_segments, const int64_t* seg_offsets,
-                        const int64_t* seg_lens, int64_t total, int64_t max_segment_len, float* out_sorted_keys,
-                        int32_t* out_perm, void* workspace, size_t workspace_bytes, void* stream_v) {
+int ub_segmented_sort(const float* keys, int32_t num_segments, const int64_t* seg_offsets, int64_t total,
+                      int64_t max_segment_len, float* out_sorted_keys, int32_t* out_perm, void* workspace,
+                      size_t workspace_bytes, void* stream_v) {
+  using namespace ub;
   UB_REQUIRE(num_segments >= 1 && num_segments <= 65535 && seg_offsets != nullptr, UB_ERR_BAD_ARG,
              "segmented_sort: bad segments");
   UB_REQUIRE(total >= 0 && max_segment_len >= 0 && max_segment_len <= total, UB_ERR_BAD_ARG,
@@ -411,7 +402,6 @@ int segmented_sort_impl(const float* keys, int32_t num_segments, const int64_t* 
   for (int pass = 0; pass < 4; ++pass) {
     SortPass p{};
     p.seg_offsets = reinterpret_cast<const long long*>(seg_offsets);
-    p.seg_lens = reinterpret_cast<const long long*>(seg_lens);
     p.counts = reinterpret_cast<uint32_t*>(ws + lay.off_counts);
     p.totals = reinterpret_cast<uint32_t*>(ws + lay.off_totals);
     p.max_tiles = lay.max_tiles;
@@ -440,12 +430,17 @@ int segmented_sort_impl(const float* keys, int32_t num_segments, const int64_t* 
   return UB_OK;
 }
 
+size_t ub_cut_prefix_sums_workspace_bytes(int32_t num_segments, int64_t max_segment_len,
+                                          int32_t num_values, int32_t num_cuts) {
+  if (num_segments < 1 || num_values < 1 || num_cuts < 1 || max_segment_len < 0) return 256;
+  return ub::cut_layout(num_segments, max_segment_len, num_values, num_cuts).total;
+}
 
-int cut_prefix_impl(const float* const* values_host, const int32_t* const* perms_host, int32_t num_values,
-                    int32_t num_segments, const int64_t* seg_offsets, const int64_t* seg_lens,
-                    int64_t lens_value_stride, int64_t max_segment_len, const int64_t* cuts,
-                    int64_t cuts_value_stride, int32_t num_cuts, const double* add, double* out_sums,
-                    void* workspace, size_t workspace_bytes, void* stream_v) {
+int ub_cut_prefix_sums(const float* const* values_host, const int32_t* const* perms_host,
+                       int32_t num_values, int32_t num_segments, const int64_t* seg_offsets,
+                       int64_t max_segment_len, const int64_t* cuts, int32_t num_cuts, double* out_sums,
+                       void* workspace, size_t workspace_bytes, void* stream_v) {
+  using namespace ub;
   UB_REQUIRE(values_host != nullptr && num_values >= 1 && num_values <= kMaxCutValues, UB_ERR_BAD_ARG,
              "cut_prefix_sums: num_values must be in [1, %d]", kMaxCutValues);
   UB_REQUIRE(num_segments >= 1 && num_segments <= 65535 && seg_offsets != nullptr, UB_ERR_BAD_ARG,
@@ -468,11 +463,7 @@ int cut_prefix_impl(const float* const* values_host, const int32_t* const* perms
   }
   p.num_values = num_values;
   p.seg_offsets = reinterpret_cast<const long long*>(seg_offsets);
-  p.seg_lens = reinterpret_cast<const long long*>(seg_lens);
-  p.lens_value_stride = lens_value_stride;
   p.cuts = reinterpret_cast<const long long*>(cuts);
-  p.cuts_value_stride = cuts_value_stride;
-  p.add = add;
   p.num_cuts = num_cuts;
   p.block_tot = reinterpret_cast<double*>(ws + lay.off_tot);
   p.max_blocks = lay.max_blocks;
@@ -484,39 +475,6 @@ int cut_prefix_impl(const float* const* values_host, const int32_t* const* perms
   dim3 g2((unsigned)num_cuts, (unsigned)num_values, (unsigned)num_segments);
   cut_prefix_finish<<<g2, kCutThreads, 0, stream>>>(p);
   return check_launch("cut_prefix_sums");
-}
-
-
-}  // namespace ub
-
-extern "C" {
-
-size_t ub_segmented_sort_workspace_bytes(int32_t num_segments, int64_t total, int64_t max_segment_len,
-                                         int32_t with_perm) {
-  if (num_segments < 1 || total < 0 || max_segment_len < 0) return 256;
-  return ub::sort_layout(num_segments, total, max_segment_len, with_perm != 0).total;
-}
-
-int ub_segmented_sort(const float* keys, int32_t num_segments, const int64_t* seg_offsets, int64_t total,
-                      int64_t max_segment_len, float* out_sorted_keys, int32_t* out_perm, void* workspace,
-                      size_t workspace_bytes, void* stream_v) {
-  return ub::segmented_sort_impl(keys, num_segments, seg_offsets, nullptr, total, max_segment_len, out_sorted_keys,
-                                 out_perm, workspace, workspace_bytes, stream_v);
-}
-
-size_t ub_cut_prefix_sums_workspace_bytes(int32_t num_segments, int64_t max_segment_len,
-                                          int32_t num_values, int32_t num_cuts) {
-  if (num_segments < 1 || num_values < 1 || num_cuts < 1 || max_segment_len < 0) return 256;
-  return ub::cut_layout(num_segments, max_segment_len, num_values, num_cuts).total;
-}
-
-int ub_cut_prefix_sums(const float* const* values_host, const int32_t* const* perms_host,
-                       int32_t num_values, int32_t num_segments, const int64_t* seg_offsets,
-                       int64_t max_segment_len, const int64_t* cuts, int32_t num_cuts, double* out_sums,
-                       void* workspace, size_t workspace_bytes, void* stream_v) {
-  return ub::cut_prefix_impl(values_host, perms_host, num_values, num_segments, seg_offsets, nullptr, 0,
-                             max_segment_len, cuts, 0, num_cuts, nullptr, out_sums, workspace, workspace_bytes,
-                             stream_v);
 }
 
 }  // extern "C"
