@@ -176,3 +176,38 @@ def test_scorer_select_equals_sort(built_library, monkeypatch):
         for k in da:
             np.testing.assert_allclose(np.asarray(da[k], dtype=np.float64), np.asarray(dc[k], dtype=np.float64),
                                        rtol=1e-6, atol=1e-12, err_msg=k)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_select_randomized_mixtures(built_library, seed):
+    """Random mixtures of what breaks selection schemes: tie groups of every size (some a few ulps apart, some
+    next to a continuous bulk), heavy tails over many octaves, negative keys, ragged segment lengths, random cuts."""
+    rng = np.random.default_rng(1000 + seed)
+    g = torch.Generator().manual_seed(1000 + seed)
+    nseg = int(rng.integers(1, 5))
+    lens = [int(rng.integers(1, 120000)) for _ in range(nseg)]
+    keys = []
+    for n in lens:
+        kind = seed % 4
+        x = torch.rand(n, generator=g)
+        if kind == 0:      # log-uniform over 12 octaves with a floor tie group and its near neighbours
+            x = torch.exp2(-12.0 * x)
+            x = torch.clamp(x, min=float(rng.choice([1e-3, 0.05, 0.3])))
+        elif kind == 1:    # a few tie values a few ulps apart inside a continuous bulk
+            base = np.float32(0.37)
+            ties = torch.tensor([base, np.nextafter(base, np.float32(1)), np.nextafter(base, np.float32(0)), 0.5, 0.0],
+                                dtype=torch.float32)
+            pick = torch.randint(0, 12, (n,), generator=g)
+            x = torch.where(pick < len(ties), ties[pick.clamp(max=len(ties) - 1)], x)
+        elif kind == 2:    # signed, heavy-tailed
+            x = torch.randn(n, generator=g) ** 3 * 10.0 ** float(rng.integers(-6, 6))
+        else:              # coarse quantisation: every key is a tie
+            x = torch.round(x * float(rng.choice([3, 17, 1000]))) / 7.0
+        keys.append(x)
+    var = torch.cat(keys)
+    total = sum(lens)
+    ae = torch.rand(total, generator=g) * 10.0 ** float(rng.integers(-3, 3))
+    se = torch.exp2(-20.0 * torch.rand(total, generator=g))
+    ncut = int(rng.integers(1, 129))
+    cuts = np.stack([rng.integers(0, n + 1, size=ncut) for n in lens]).astype(np.int64)
+    _check(var, ae, se, lens, cuts, check_sort_path=seed % 3 == 0)
