@@ -655,7 +655,8 @@ __device__ __forceinline__ void sel_cell_bases(const SegPlan& pl, uint32_t* s_ba
 
 // ---- classify: class sums of the decided elements, records of the undecided ones ---------------------------
 struct ClassifyShared {
-  BinTables bt;
+  uint16_t map[kSelBins];           // bin -> class or cell; the coarse table is read through L1 (__ldg): six blocks per SM
+  uint32_t heavy[kSelMaxHeavy];
   double sum[kSelMaxCuts + 1][2];
   uint32_t base[kSelMaxCuts + 1];
   int8_t tiled[kSelMaxCuts];        // cell -> tiled index or -1
@@ -695,7 +696,13 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
   SegPlan& pl = p.plan[g];
   const int ncells = pl.ncells, nc = p.num_cuts, nh = pl.nheavy, nt = pl.ntiled;
   const int t0 = blockIdx.x * p.tiles_per_block;
-  sel_load_tables(p, g, pl, sh.bt, true);
+  {
+    const uint16_t* map = p.binmap + (size_t)g * kSelBins;
+    const int nb = pl.nbins;
+    for (int i = tid; i < nb; i += kSelThreads) sh.map[i] = map[i];
+    if (tid < kSelMaxHeavy) sh.heavy[tid] = pl.heavy[tid];
+  }
+  const uint32_t* tab = p.table + (size_t)g * kSelCoarse;
   for (int i = tid; i < (kSelMaxCuts + 1) * 2; i += kSelThreads) (&sh.sum[0][0])[i] = 0.0;
   for (int i = tid; i < (kSelMaxCuts + 1) * 6; i += kSelThreads) (&sh.limb[0][0][0])[i] = 0;
   if (tid < 2) sh.vmax[tid] = 0u;
@@ -794,7 +801,7 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
       const int pos = i * kSelThreads + tid;
       if (pos < count) {
         const uint32_t key = sort_key_from_float(kf[i]);
-        const uint16_t m = sh.bt.map[sel_bin(key, sh.bt.tab[key >> kSelLowBits], sh.bt.heavy, nh)];
+        const uint16_t m = sh.map[sel_bin(key, __ldg(tab + (key >> kSelLowBits)), sh.heavy, nh)];
         if (m & kSelCellFlag) {
           const int cell = m & 0x7FFF;
           const int ti = sh.tiled[cell];
@@ -843,7 +850,7 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
   }
 }
 
-__global__ void __launch_bounds__(kSelThreads) sel_classify(const SelParams p) {
+__global__ void __launch_bounds__(kSelThreads, 6) sel_classify(const SelParams p) {
   __shared__ ClassifyShared sh;
   const int g = blockIdx.y;
   int f, b;
