@@ -313,16 +313,29 @@ __global__ void __launch_bounds__(kSelThreads) sel_fine_hist(const SelParams p) 
   const float* k = p.keys[f] + lo + start;
   const uint32_t* tab = p.table + (size_t)g * kSelCoarse;
   constexpr int per = kSelChunk / kSelThreads;
-  for (int base = 0; base < per; base += 8) {
-    float v[8];
+  if (count == kSelChunk) {  // whole chunk: no clamps, no predicates
+    for (int base = 0; base < per; base += 8) {
+      float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __ldg(k + min((base + i) * kSelThreads + (int)threadIdx.x, count - 1));
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(k + (base + i) * kSelThreads + (int)threadIdx.x);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if ((base + i) * kSelThreads + (int)threadIdx.x < count) {
+      for (int i = 0; i < 8; ++i) {
         const uint32_t u = sort_key_from_float(v[i]);
         atomicAdd(&h[sel_bin(u, __ldg(tab + (u >> kSelLowBits)), s_heavy, nh)], 1u);
       }
+    }
+  } else {
+    for (int base = 0; base < per; base += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(k + min((base + i) * kSelThreads + (int)threadIdx.x, count - 1));
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if ((base + i) * kSelThreads + (int)threadIdx.x < count) {
+          const uint32_t u = sort_key_from_float(v[i]);
+          atomicAdd(&h[sel_bin(u, __ldg(tab + (u >> kSelLowBits)), s_heavy, nh)], 1u);
+        }
+    }
   }
   __syncthreads();
   uint32_t* gh = p.hist_f + (size_t)g * kSelBins;
