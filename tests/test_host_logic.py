@@ -156,3 +156,18 @@ def test_numa_binding_helper_is_harmless_without_nvml():
     assert pipeline.bind_host_thread_to_gpu(0) in (True, False)       # no GPU here: False, and nothing changes
     if before is not None and not torch.cuda.is_available():
         assert os.sched_getaffinity(0) == before
+
+
+def test_ause_path_switch_and_select_refuses_cpu_tensors(monkeypatch):
+    """The scorer takes the AUSE sums from the select kernels unless UB_AUSE_SORT=1 or a segment exceeds the
+    2^24 keys the select path supports; like every op, the select wrapper has no CPU route."""
+    monkeypatch.delenv("UB_AUSE_SORT", raising=False)
+    assert metrics._use_select(1089480)
+    assert not metrics._use_select((1 << 24) + 1)
+    monkeypatch.setenv("UB_AUSE_SORT", "1")
+    assert not metrics._use_select(1089480)
+    monkeypatch.setenv("UB_AUSE_SORT", "0")
+    assert metrics._use_select(640000)
+    x = torch.rand(100)
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        ops.cut_select_sums([(x, x, None)], [100], metrics.ause_cut_counts(100)[None, :])
