@@ -10,7 +10,8 @@
 //   coarse     per segment: histogram of the top 12 bits of the order-preserving uint32 key
 //   alloc      every coarse bin is split into 2^k fine bins in proportion to its count (<= 8192 fine bins
 //              per segment, each holding <= n/2048 keys unless the keys tie): an equal-frequency binning
-//              that needs neither the key range nor a sample
+//              that needs neither the key range nor splitters; a sorted 1024-key sample finds the heavy
+//              tie values (a clamped uncertainty floor), each of which gets a bin of its own
 //   fine       histogram over the fine bins
 //   locate     prefix over the fine bins; every cut falls into one bin (its "cell") at a residual rank r;
 //              a bin that holds no cut gets a class = number of cuts that exclude it
@@ -18,12 +19,14 @@
 //   plan       a big cell whose keys are all equal (a tie group) is resolved by index: stable order inside
 //              it is the element order, so the tile where the running count crosses r follows from the
 //              per-tile counts and only that tile's members stay undecided; other cells stay undecided whole
-//   classify   one pass over keys + payloads: decided elements add their payload to the float64 sum of their
-//              class; undecided ones (typically 1-3 % of the keys) go to their cell's slot of a side list
+//   classify   one pass over keys + payloads: decided elements add their payload to the sum of their class
+//              (exact fixed-point limbs with native 32-bit shared-memory atomics, folded into float64 per
+//              block); undecided ones (typically 1-3 % of the keys) go to their cell's slot of a side list
 //              as (key, index, payloads) records
-//   resolve    per cell (or per undecided tile of a tie group): exact rank of every record by (key, index),
-//              hence its class; a radix select over the records takes over for cells too big to rank
-//              pairwise (several tie groups inside one fine bin -- correct, only slower)
+//   resolve    per cell (or per undecided tile of a tie group): records bucketed by the top 8 bits in which
+//              their (key, index) differ, the members of a bucket that a cut splits ranked pairwise, hence
+//              the class of every record; a radix select over the records takes over for cells beyond 2048
+//              records (an unsampled tie group next to other keys of its fine bin -- correct, only slower)
 //   finish     class sums -> prefix over the classes = the sums under every cut.
 //
 // The sets of elements under every cut are exactly those of torch.sort(stable=True) (same key transform:
@@ -150,25 +153,6 @@ __device__ __forceinline__ uint32_t sel_block_excl_scan(uint32_t v, uint32_t* wa
   if (total_out) *total_out = tot;
   __syncthreads();
   return base + incl - v;
-}
-
-// per-block copy of the segment's binning tables
-struct BinTables {
-  uint16_t map[kSelBins];
-  uint32_t tab[kSelCoarse];
-  uint32_t heavy[kSelMaxHeavy];
-};
-
-__device__ __forceinline__ void sel_load_tables(const SelParams& p, int g, const SegPlan& pl, BinTables& bt,
-                                                bool with_map) {
-  const uint32_t* tab = p.table + (size_t)g * kSelCoarse;
-  for (int i = threadIdx.x; i < kSelCoarse; i += kSelThreads) bt.tab[i] = tab[i];
-  if (with_map) {
-    const uint16_t* map = p.binmap + (size_t)g * kSelBins;
-    const int nb = pl.nbins;
-    for (int i = threadIdx.x; i < nb; i += kSelThreads) bt.map[i] = map[i];
-  }
-  if (threadIdx.x < kSelMaxHeavy) bt.heavy[threadIdx.x] = pl.heavy[threadIdx.x];
 }
 
 // ---- coarse histogram: top 12 key bits ----------------------------------------------------------------
