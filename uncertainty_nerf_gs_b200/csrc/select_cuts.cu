@@ -391,13 +391,9 @@ __global__ void __launch_bounds__(kSelLocThreads) sel_locate(const SelParams p) 
     }
     if (lane == 0) s_wtot[warp] = carry;
     __syncthreads();
-    uint32_t base = 0, tot = 0;
-    for (int w = 0; w < kLocWarps; ++w) {
-      if (w < warp) base += s_wtot[w];
-      tot += s_wtot[w];
-    }
-    for (int i = lane; i < span; i += 32) excl[warp * span + i] += base;
-    if (tid == 0) excl[kPad] = tot;
+    uint32_t base = 0;
+    for (int w = 0; w < warp; ++w) base += s_wtot[w];
+    for (int i = lane; i < span; i += 32) excl[warp * span + i] += base;  // excl[b] for b >= nbins = the total
   }
   __syncthreads();
 
