@@ -144,7 +144,8 @@ def laplace_outputs_unc(density: Tensor, deltas: Tensor, starts: Tensor, ends: T
                         rgb: Tensor, rgb_var: Tensor, density_var: Optional[Tensor] = None,
                         use_deterministic_density: bool = True,
                         density_noise: Optional[Tensor] = None,
-                        background_color: Background = "last_sample") -> Dict[str, Tensor]:
+                        background_color: Background = "last_sample",
+                        density_draws: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """One chunk of ``NerfactoLaplaceModel.get_outputs_unc`` downstream of the field:
     ``laplace_model.py:471-530``.
 
@@ -153,19 +154,23 @@ def laplace_outputs_unc(density: Tensor, deltas: Tensor, starts: Tensor, ends: T
     accumulation use the mean of the weights of 100 density draws (``:486-521``);
     the draws are ``relu(density + density_std * density_noise[k])`` with the standard
     normal ``density_noise [K, R, S, 1]`` passed in so that oracle and GPU see identical
-    samples (the reference draws them from torch's global generator).
+    samples (the reference draws them from torch's global generator).  ``density_draws [K, R, S, 1]`` passes
+    the draws of ``Normal(density, density_std).sample((K,))`` themselves (before the relu), which is how the
+    reference-executed goldens are replayed bit for bit.
     """
     weights = get_weights(density, deltas)
     out_rgb = render_rgb(rgb, weights, background_color)
     var = render_uncertainty(rgb_var, weights ** 2)
     rgb_std = torch.sqrt(var)
     if not use_deterministic_density:
-        assert density_var is not None and density_noise is not None
+        assert density_var is not None and (density_noise is not None or density_draws is not None)
         density_std = density_var.sqrt()
         density_std = torch.maximum(density_std, torch.tensor([1e-10]))
         if torch.isnan(density_std).any():
             density_std = torch.nan_to_num(density_std, nan=1e-10)
-        sampled = torch.relu(density.unsqueeze(0) + density_std.unsqueeze(0) * density_noise)
+        if density_draws is None:
+            density_draws = density.unsqueeze(0) + density_std.unsqueeze(0) * density_noise
+        sampled = torch.relu(density_draws)
         sampled_w = torch.stack([get_weights(s, deltas) for s in sampled], dim=0)
         weights = sampled_w.mean(dim=0)
     depth = render_depth_median(weights, starts, ends)

@@ -8,8 +8,14 @@ def test_plugin_module_imports_without_nerfstudio():
 
     assert plug.METHOD_NAMES == ("active-nerfacto", "active-splatfacto", "nerfacto-mcdropout", "nerfacto-laplace")
     assert "active-nerfacto" in plug.ENSEMBLE_METHOD_NAMES and "nerfacto" in plug.ENSEMBLE_METHOD_NAMES
-    with pytest.raises(ImportError):
-        plug.patch_reference_models()      # nerfuncertainty / nerfstudio are not installed here
+    # nerfuncertainty / nerfstudio are not installed here: a fresh interpreter must refuse to patch
+    import subprocess
+    import sys
+
+    code = ("from uncertainty_nerf_gs_b200.models import nerfstudio_plugin as p\n"
+            "try:\n    p.patch_reference_models()\nexcept ImportError:\n    print('refused')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(__import__("pathlib").Path(__file__).resolve().parents[1]))
+    assert "refused" in out.stdout, out.stderr
 
 
 def test_output_key_order_constants():
