@@ -21,7 +21,13 @@ def _fake_view_record(view_id: int) -> np.ndarray:
     d = {k: rng.random(100) for k in pipeline.CURVE_KEYS_100}
     d.update({k: rng.random(99) for k in pipeline.CURVE_KEYS_99})
     d.update({k: float(rng.random()) for k in pipeline.SCALAR_KEYS})
-    return pipeline.pack_record(view_id, d)
+    depth = None
+    if True:
+        depth = {k: rng.random(100) for k in pipeline.CURVE_KEYS_100}
+        depth.update({k: rng.random(99) for k in pipeline.CURVE_KEYS_99})
+        depth.update({k: float(rng.random()) for k in pipeline.DEPTH_SCALAR_KEYS})
+    extra = {k: float(rng.random()) for k in pipeline.IMAGE_KEYS + pipeline.TIMING_KEYS}
+    return pipeline.pack_record(view_id, d, depth, extra)
 
 
 def _free_port() -> int:
@@ -36,17 +42,20 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         mine = pipeline.shard_views(NUM_VIEWS, rank, world)
-        per = (NUM_VIEWS + world - 1) // world
         local = np.stack([_fake_view_record(v) for v in mine]) if len(mine) else np.zeros((0, pipeline.RECORD_LEN))
-        # all_gather_into_tensor needs equal shapes: pad short blocks with records marked view id = -1
-        pad = np.zeros((per - local.shape[0], pipeline.RECORD_LEN))
-        pad[:, -1] = -1
-        gathered = pipeline.gather_records(np.concatenate([local, pad]), device=None)
-        gathered = gathered[gathered[:, -1] >= 0]
+        # blocks differ in length (7 views over 2 ranks; 3 views over 2 ranks leaves rank 1 with one, see below):
+        # gather_records pads and strips by itself, with or without the row count given up front
+        gathered = pipeline.gather_records(local, device=None)
+        per = (NUM_VIEWS + world - 1) // world
+        again = pipeline.gather_records(local, device=None, rows_per_rank=per)
+        assert np.array_equal(gathered, again)
+        few = pipeline.gather_records(local[:1] if rank == 0 else local[:0], device=None)      # an empty block
+        assert few.shape == (1, pipeline.RECORD_LEN) and few[0, -1] == 0
         agg = pipeline.aggregate_records(gathered)
         np.save(os.path.join(out_dir, f"ids_{rank}.npy"), gathered[:, -1])
         np.save(os.path.join(out_dir, f"curve_{rank}.npy"), agg["err_var_rmse"])
-        np.save(os.path.join(out_dir, f"scal_{rank}.npy"), np.array([agg[k] for k in pipeline.SCALAR_KEYS]))
+        np.save(os.path.join(out_dir, f"scal_{rank}.npy"), np.array([agg[k] for k in pipeline.ALL_SCALAR_KEYS]))
+        np.save(os.path.join(out_dir, f"dcurve_{rank}.npy"), agg["depth_coverage_values"])
     finally:
         dist.destroy_process_group()
 
@@ -61,7 +70,8 @@ def test_two_rank_gather_equals_single_process(tmp_path):
         assert ids.tolist() == list(range(NUM_VIEWS))           # ordered by view id on every rank
         assert np.array_equal(np.load(tmp_path / f"curve_{rank}.npy"), ref["err_var_rmse"])
         assert np.array_equal(np.load(tmp_path / f"scal_{rank}.npy"),
-                              np.array([ref[k] for k in pipeline.SCALAR_KEYS]))
+                              np.array([ref[k] for k in pipeline.ALL_SCALAR_KEYS]))
+        assert np.array_equal(np.load(tmp_path / f"dcurve_{rank}.npy"), ref["depth_coverage_values"])
 
 
 def test_shard_views_is_a_partition():
@@ -70,10 +80,22 @@ def test_shard_views_is_a_partition():
         assert seen == list(range(n))
 
 
+def agg_keys(recs):
+    return [k for k, v in pipeline.aggregate_records(recs).items() if isinstance(v, float)]
+
+
 def test_record_roundtrip_and_reference_aggregation_semantics():
     recs = np.stack([_fake_view_record(v) for v in range(5)])
     vid, d = pipeline.unpack_record(recs[3])
     assert vid == 3 and d["err_mae"].shape == (100,) and d["coverage_values"].shape == (99,)
+    assert d["depth_err_rmse"].shape == (100,) and "psnr" in d and "depth_nll" in d
+    assert [k for k in agg_keys(recs)] == list(pipeline.ALL_SCALAR_KEYS)
+    # a record without the depth / image-metric groups keeps them out of the aggregate
+    rgb_only = np.stack([pipeline.pack_record(v, {**{k: np.zeros(100) for k in pipeline.CURVE_KEYS_100},
+                                                  **{k: np.zeros(99) for k in pipeline.CURVE_KEYS_99},
+                                                  **{k: 1.0 for k in pipeline.SCALAR_KEYS}}) for v in range(2)])
+    only = pipeline.aggregate_records(rgb_only)
+    assert "depth_nll" not in only and "psnr" not in only and "depth_err_mae" not in only and only["rgb_nll"] == 1.0
     agg = pipeline.aggregate_records(recs)
     # eval_uncertainty.py:1070-1077: float32 mean of python floats; :920-946: float64 curve sums / n
     vals = [pipeline.unpack_record(r)[1]["rgb_nll"] for r in recs]

@@ -75,3 +75,56 @@ def test_splat_one_million_gaussians_full_view(built_library):
     base, al = ops.composite_tiles(sc["xys"], sc["conics"], sc["opacities"], col, ids, bins, h, w, [0, 0, 0])
     shifted, _ = ops.composite_tiles(sc["xys"], sc["conics"], sc["opacities"], col + 0.25, ids, bins, h, w, [0, 0, 0])
     torch.testing.assert_close(shifted, base + 0.25 * al, rtol=1e-4, atol=1e-5)
+
+
+def test_full_view_compositing_against_the_oracle(built_library):
+    """configs[1] at its real size: all 34 eval chunks of one 1297 x 840 view through the CPU oracle (which
+    tests/test_oracle_pinned.py pins bit-for-bit to the reference's own ``get_outputs`` + chunk loop)."""
+    from oracle import compositing as oc
+    from uncertainty_nerf_gs_b200.models.outputs import active_nerfacto_outputs
+
+    h, w, S, chunk = 840, 1297, 48, 1 << 15
+    R = h * w
+    inp = synthetic.ray_samples(R, S, seed=42)
+    keys = ("density", "deltas", "starts", "ends", "rgb", "beta")
+    ref = oc.render_in_chunks(oc.active_nerfacto_outputs, chunk, *[inp[k] for k in keys])
+    out = active_nerfacto_outputs(*[inp[k].cuda() for k in keys], rays_per_chunk=chunk, image_hw=(h, w))
+    assert out["rgb"].shape == (h, w, 3)
+    same_depth = torch.isclose(out["depth"].reshape(R, 1).cpu(), ref["depth"], rtol=1e-6, atol=0.0)[:, 0]
+    assert int((~same_depth).sum()) <= 1e-4 * R                           # borderline median samples only
+    atol = {"rgb": 2e-6, "accumulation": 2e-6, "expected_depth": 2e-6, "rgb_var": 1e-7, "rgb_std": 1e-6}
+    for k, a in atol.items():
+        torch.testing.assert_close(out[k].reshape(R, -1).cpu(), ref[k], rtol=1e-5, atol=a, equal_nan=True, msg=lambda m: f"{k}: {m}")
+    for k in ("depth_var", "depth_std"):
+        torch.testing.assert_close(out[k].reshape(R, 1).cpu()[same_depth], ref[k][same_depth], rtol=1e-5, atol=1e-6)
+
+
+def test_full_size_k10_reduce_against_the_oracle(built_library):
+    """configs[2]'s reduce at full image size: K = 10 MC-dropout passes of a 1297 x 840 view, every nerfacto key."""
+    from oracle import reduce as orc
+    from uncertainty_nerf_gs_b200.models.outputs import mcdropout_reduce
+
+    passes = synthetic.member_renders(10, 840, 1297, seed=7)
+    ref = orc.mcdropout_reduce(passes)
+    out = mcdropout_reduce([{k: v.cuda() for k, v in p.items()} for p in passes])
+    assert list(out.keys()) == list(ref.keys())
+    for k, v in ref.items():
+        torch.testing.assert_close(out[k].cpu(), v, rtol=1e-5, atol=1e-7, msg=lambda m: f"{k}: {m}")
+
+
+@pytest.mark.parametrize("sort_path", [True, False])
+def test_full_scorer_at_800x800_both_ause_paths(built_library, monkeypatch, sort_path):
+    """configs[0]'s image: the whole scorer at 800 x 800 through the per-image segmented radix sort (the north-star's
+    kernel (c), ``UB_AUSE_SORT=1``) and through the sort-free select, against the oracle (= the reference's
+    ``get_unc_metrics_rgb``, pinned): coverage counts exactly, curves / scalars to 1e-5."""
+    from uncertainty_nerf_gs_b200 import metrics
+
+    monkeypatch.setenv("UB_AUSE_SORT", "1" if sort_path else "0")
+    p, s, g = synthetic.scoring_image(800, 800, seed=5)
+    ref = om.unc_metrics_rgb(p, g, s)
+    d = metrics.score_rgb_batch(p.cuda(), g.cuda(), s.cuda())[0]
+    assert np.array_equal(d["coverage_values"], ref["coverage_values"])
+    for k in ("err_mae", "err_mse", "err_rmse", "err_var_mae", "err_var_mse", "err_var_rmse"):
+        np.testing.assert_allclose(np.asarray(d[k], dtype=np.float64), np.asarray(ref[k], dtype=np.float64), rtol=1e-5, err_msg=k)
+    for k in ("ause_mae", "ause_mse", "ause_rmse", "nll_rgb", "avg_var", "auc_abs_error_values", "auc_length_values"):
+        np.testing.assert_allclose(d[k], ref[k], rtol=1e-5, atol=1e-9, err_msg=k)

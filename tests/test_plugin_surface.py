@@ -23,5 +23,6 @@ def test_output_key_order_constants():
     from uncertainty_nerf_gs_b200.models import outputs
 
     assert outputs.STD_KEYS == ("rgb", "depth", "expected_depth")
-    assert pipeline.RECORD_LEN == 6 * 100 + 5 * 99 + 10 + 1
+    assert pipeline.RECORD_LEN == 2 * (6 * 100 + 5 * 99) + 25 + 3 + 1
+    assert pipeline.ALL_SCALAR_KEYS[:4] == ("psnr", "ssim", "lpips", "depth_ause_mse") and pipeline.ALL_SCALAR_KEYS[-1] == "fps"
     assert pipeline.SCALAR_KEYS[:3] == ("rgb_ause_mse", "rgb_ause_mae", "rgb_ause_rmse")

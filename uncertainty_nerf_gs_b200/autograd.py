@@ -70,7 +70,12 @@ def composite_rays_train(density: Tensor, deltas: Tensor, starts: Tensor, ends: 
                          background: Union[str, Sequence[float]] = "last_sample",
                          rays_per_chunk: Optional[int] = None) -> Dict[str, Tensor]:
     """Training-mode fused compositing with gradients.  Inputs ``[R, S, 1]`` / ``[R, S, 3]`` CUDA float32
-    (S in {16, 32, 48, 64, 96}); returns the active-nerfacto training outputs incl. ``weights [R, S, 1]``."""
+    (S in {16, 32, 48, 64, 96}); returns the active-nerfacto training outputs incl. ``weights [R, S, 1]``.
+    The reference's stability guard runs in training too (activenerfacto_model.py:104-106): if any ``beta`` is NaN,
+    all NaNs become 0 -- the same ``nan_to_num`` op as the reference's, so its autograd semantics (no gradient to
+    the replaced entries) carry over."""
+    if torch.isnan(beta).any():
+        beta = torch.nan_to_num(beta, 0.0)
     res = _CompositeRaysFn.apply(density, deltas, starts, ends, rgb, beta, background, rays_per_chunk)
     out = dict(zip(_OUT_KEYS + ("depth",), res))
     return {"rgb": out["rgb"], "accumulation": out["accumulation"], "depth": out["depth"],

@@ -184,9 +184,11 @@ def ause(unc_vec: Tensor, err_vec: Tensor, err_type: str = "rmse"
         unc32, err32 = unc_vec.reshape(-1).to(torch.float32), err_vec.reshape(-1).to(torch.float32)
         sums = ops.cut_select_sums([(err32, err32, None), (unc32, err32, None)], [n], cuts[None, :])
     else:
-        both = torch.stack([unc_vec.reshape(-1), err_vec.reshape(-1)]).to(torch.float32)
+        unc32 = unc_vec.reshape(-1).to(torch.float32)
+        err32 = err_vec.reshape(-1).to(torch.float32).contiguous()
+        both = torch.stack([unc32, err32])
         sorted_all, perm_all = ops.segmented_sort(both.reshape(-1), [n, n], want_perm=True, want_keys=True)
-        sums = ops.cut_prefix_sums([sorted_all[n:], err_vec], [None, perm_all[:n]], [n], cuts[None, :])
+        sums = ops.cut_prefix_sums([sorted_all[n:], err32], [None, perm_all[:n]], [n], cuts[None, :])
     host = sums[0].cpu().numpy()
     return _ause_tail(_prefix_means(host[0], cuts, err_type), _prefix_means(host[1], cuts, err_type))
 
@@ -261,6 +263,39 @@ def auce(mean_values: ArrayLike, sigma_values: ArrayLike, target_values: ArrayLi
     return _auce_from_hist(hist, sigma_sum, float(n), z_values_host())
 
 
+def _score_rgb_device(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb_std_for_nll: float):
+    """The device half of ``score_rgb_batch``: prologue (+ AUCE histogram, NLL), AUSE slice sums, and the packing of
+    everything the host tail needs into one ``[B, 505]`` float64 tensor.  Enqueue-only (CUDA-graph capturable once
+    the segment / cut tables of the shape are cached)."""
+    if rgb_pred.dim() == 3:
+        rgb_pred, rgb_gt, rgb_std = rgb_pred[None], rgb_gt[None], rgb_std[None]
+    b, h, w, c = rgb_pred.shape
+    n = h * w
+    lens = [n] * b
+    z = _z_table(rgb_pred.device)
+    pro = ops.score_prologue(rgb_pred.reshape(-1, c), rgb_gt.reshape(-1, c), rgb_std.reshape(-1), lens, z,
+                             nll_min_std=min_rgb_std_for_nll, sigma_from_var=True, want_vectors=True)
+    vec = pro["vectors"]                                   # [3, total]: var, abs err, sq err
+    cuts_one = ause_cut_counts(n)
+    cuts = _tiled_cuts(n, b)
+    sums = _ause_sums(vec, lens, cuts)                                                # [B, 4, 100]
+    packed_dev = torch.cat([sums.reshape(b, -1), pro["sums"], pro["hist"].to(torch.float64)], dim=1)
+    return packed_dev, b, n, c, cuts_one
+
+
+_TILED: Dict[Tuple[int, int], np.ndarray] = {}
+
+
+def _tiled_cuts(n: int, b: int) -> np.ndarray:
+    key = (n, b)
+    t = _TILED.get(key)
+    if t is None:
+        if len(_TILED) > 64:
+            _TILED.clear()
+        t = _TILED[key] = np.tile(ause_cut_counts(n)[None, :], (b, 1))
+    return t
+
+
 def score_rgb_batch_async(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb_std_for_nll: float = 3e-2
                           ) -> "PendingScores":
     """``get_unc_metrics_rgb`` (eval_uncertainty.py:306-402) for a batch of images in one set of
@@ -269,24 +304,10 @@ def score_rgb_batch_async(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min
     with the reference's scalar / curve entries (``nll_rgb``, ``ause_*``, ``err_*``, ``err_var_*``,
     ``avg_var``, ``mse_mean`` and the 8 AUCE entries).
 
-    Device work: 1 prologue (+ finalize), ONE segmented sort over 3B segments (variance with its
-    permutation, absolute and squared errors), 1 cut-point prefix-sum pass, 1 packed device->host copy."""
-    if rgb_pred.dim() == 3:
-        rgb_pred, rgb_gt, rgb_std = rgb_pred[None], rgb_gt[None], rgb_std[None]
-    b, h, w, c = rgb_pred.shape
-    n = h * w
-    lens = [n] * b
-    total = n * b
-    dev = rgb_pred.device
-    z = _z_table(dev)
-    pro = ops.score_prologue(rgb_pred.reshape(-1, c), rgb_gt.reshape(-1, c), rgb_std.reshape(-1), lens, z,
-                             nll_min_std=min_rgb_std_for_nll, sigma_from_var=True, want_vectors=True)
-    vec = pro["vectors"]                                   # [3, total]: var, abs err, sq err
-    cuts_one = ause_cut_counts(n)
-    cuts = np.tile(cuts_one[None, :], (b, 1))
-    sums = _ause_sums(vec, lens, cuts)                                                # [B, 4, 100]
+    Device work: 1 prologue (+ finalize), the AUSE slice sums (multi-cut select; or ONE segmented sort over 3B
+    segments + 1 cut-point prefix-sum pass with ``UB_AUSE_SORT=1``), 1 packed device->host copy."""
+    packed_dev, b, n, c, cuts_one = _score_rgb_device(rgb_pred, rgb_gt, rgb_std, min_rgb_std_for_nll)
     # one device->host transfer for everything the host tail needs (asynchronous into pinned memory)
-    packed_dev = torch.cat([sums.reshape(b, -1), pro["sums"], pro["hist"].to(torch.float64)], dim=1)
     packed_host = torch.empty(packed_dev.shape, dtype=packed_dev.dtype, pin_memory=True)
     packed_host.copy_(packed_dev, non_blocking=True)
     done = torch.cuda.Event()
@@ -301,8 +322,14 @@ class PendingScores:
     def __init__(self, packed_host, packed_dev, done, b, n, c, cuts_one):
         self.packed_host, self.packed_dev, self.done = packed_host, packed_dev, done
         self.b, self.n, self.c, self.cuts_one = b, n, c, cuts_one
+        self._result: Optional[List[Dict[str, object]]] = None
 
     def finish(self) -> List[Dict[str, object]]:
+        if self._result is None:
+            self._result = self._finish()
+        return self._result
+
+    def _finish(self) -> List[Dict[str, object]]:
         self.done.synchronize()
         packed = self.packed_host.numpy()
         b, n, c, cuts_one = self.b, self.n, self.c, self.cuts_one
@@ -351,6 +378,18 @@ def per_image_rgb_scalars(d: Dict[str, object]) -> Dict[str, float]:
         "rgb_nll": float(d["nll_rgb"]), "rgb_avg_var": float(d["avg_var"]),
         "rgb_auc_abs_error": d["auc_abs_error_values"], "rgb_auc_length": d["auc_length_values"],
         "rgb_auc_neg_error": d["auc_neg_error_values"],
+    }
+
+
+def per_image_depth_scalars(d: Dict[str, object]) -> Dict[str, float]:
+    """The per-image depth entries of ``metrics_dict`` (eval_uncertainty.py:714-725)."""
+    mse = float(d["mse_mean"])
+    return {
+        "depth_ause_mse": float(d["ause_mse"]), "depth_ause_mae": float(d["ause_mae"]),
+        "depth_ause_rmse": float(d["ause_rmse"]), "depth_mse": mse, "depth_rmse": float(np.sqrt(mse)),
+        "depth_nll": float(d["nll_depth"]), "depth_avg_var": float(d["avg_var"]),
+        "depth_auc_abs_error": d["auc_abs_error_values"], "depth_auc_length": d["auc_length_values"],
+        "depth_auc_neg_error": d["auc_neg_error_values"],
     }
 
 

@@ -27,13 +27,28 @@ RAY_KEYS = ("density", "deltas", "starts", "ends", "rgb", "beta")
 # (the drop-in for the pipeline method) still reduces whatever keys it is given.
 PER_SAMPLE_KEYS = ("density",)
 
-# layout of the per-view float64 record that crosses GPUs
+# ---- layout of the per-view float64 record that crosses GPUs -------------------------------------------------
+# Everything ``get_average_uncertainty_metrics`` accumulates per image (eval_uncertainty.py:856-893, 920-946,
+# 1070-1079): the 6 AUSE curves [100] and 5 AUCE curves [99] of the rgb and of the depth modality, and the
+# per-image scalars of ``metrics_dict`` in the reference's insertion order (:684-686 psnr / ssim / lpips,
+# :714-725 depth_*, :765-776 rgb_*, :948-952 num_rays_per_sec / fps).  Three flags say which groups are present
+# (``eval_depth`` / ``eval_rgb`` / image metrics supplied by the model layer); absent groups are zero-filled and
+# left out of the aggregate, like the reference leaves them out of ``metrics.json``.
 CURVE_KEYS_100 = ("err_mae", "err_mse", "err_rmse", "err_var_mae", "err_var_mse", "err_var_rmse")
 CURVE_KEYS_99 = ("coverage_values", "avg_length_values", "coverage_error_values", "abs_coverage_error_values",
                  "neg_coverage_error_values")
-SCALAR_KEYS = ("rgb_ause_mse", "rgb_ause_mae", "rgb_ause_rmse", "rgb_mse", "rgb_rmse", "rgb_nll", "rgb_avg_var",
-               "rgb_auc_abs_error", "rgb_auc_length", "rgb_auc_neg_error")
-RECORD_LEN = 100 * len(CURVE_KEYS_100) + 99 * len(CURVE_KEYS_99) + len(SCALAR_KEYS) + 1  # + view id
+IMAGE_KEYS = ("psnr", "ssim", "lpips")
+_MODALITY_SCALARS = ("ause_mse", "ause_mae", "ause_rmse", "mse", "rmse", "nll", "avg_var", "auc_abs_error", "auc_length",
+                     "auc_neg_error")
+DEPTH_SCALAR_KEYS = tuple("depth_" + k for k in _MODALITY_SCALARS)
+SCALAR_KEYS = tuple("rgb_" + k for k in _MODALITY_SCALARS)          # the rgb group (name kept from round 1)
+TIMING_KEYS = ("num_rays_per_sec", "fps")
+ALL_SCALAR_KEYS = IMAGE_KEYS + DEPTH_SCALAR_KEYS + SCALAR_KEYS + TIMING_KEYS      # metrics.json order
+DEPTH_CURVE_KEYS_100 = tuple("depth_" + k for k in CURVE_KEYS_100)
+DEPTH_CURVE_KEYS_99 = tuple("depth_" + k for k in CURVE_KEYS_99)
+_CURVES = 100 * len(CURVE_KEYS_100) + 99 * len(CURVE_KEYS_99)
+_FLAGS = ("has_rgb", "has_depth", "has_image_metrics")
+RECORD_LEN = 2 * _CURVES + len(ALL_SCALAR_KEYS) + len(_FLAGS) + 1  # + view id (last)
 
 
 def render_members(members: Sequence[Dict[str, Tensor]], height: int, width: int, rays_per_chunk: int,
@@ -187,6 +202,126 @@ class ViewStream:
         return done
 
 
+class GraphedScore:
+    """CUDA-graph replay of the scorer's device work for fixed input tensors (``score_rgb_batch`` of one shape):
+    prologue, AUSE slice sums, packing and the device->host copy are one graph launch instead of ~16 kernel
+    launches with their Python / ctypes overhead -- what makes the small, latency-bound configurations
+    (one 800x800 image per call) fast.  ``launch()`` returns a ``metrics.PendingScores``."""
+
+    def __init__(self, rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb_std_for_nll: float = 3e-2,
+                 pool=None, stream: Optional["torch.cuda.Stream"] = None):
+        self.inputs = (rgb_pred, rgb_gt, rgb_std)
+        dev = rgb_pred.device
+        self.stream = stream
+        metrics.score_rgb_batch(rgb_pred, rgb_gt, rgb_std, min_rgb_std_for_nll)   # warm: lazy loads, cached tables
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        kw = {} if pool is None else {"pool": pool}
+        with torch.cuda.graph(self.graph, **kw):
+            self.packed_dev, self.b, self.n, self.c, self.cuts_one = metrics._score_rgb_device(
+                rgb_pred, rgb_gt, rgb_std, min_rgb_std_for_nll)
+            self.packed_host = torch.empty(self.packed_dev.shape, dtype=self.packed_dev.dtype, pin_memory=True)
+            self.packed_host.copy_(self.packed_dev, non_blocking=True)
+        self.done = torch.cuda.Event()
+        self._last: Optional[metrics.PendingScores] = None
+
+    def launch(self) -> "metrics.PendingScores":
+        if self._last is not None:
+            self._last.finish()                     # the pinned result buffer is about to be overwritten
+        self.graph.replay()
+        self.done.record()
+        self._last = metrics.PendingScores(self.packed_host, self.packed_dev, self.done, self.b, self.n, self.c,
+                                           self.cuts_one)
+        return self._last
+
+
+class _GraphSlot:
+    """One of the two buffer sets of a member set in ``GraphedViews``: the compositing graph (main stream) and the
+    reduce + score + read-back graph (side stream) with their static outputs."""
+
+    def __init__(self, members, gt_shape, h, w, chunk, min_std, pool, side):
+        dev = members[0]["density"].device
+        self.gt = torch.empty(gt_shape, device=dev)
+        self.comp, self.post = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.comp, pool=pool):
+            outs = render_members(members, h, w, chunk)
+        self.outs = outs
+        with torch.cuda.graph(self.post, pool=pool, stream=side):
+            red = mo.ensemble_reduce(outs) if len(outs) > 1 else outs[0]
+            self.packed_dev, self.b, self.n, self.c, self.cuts_one = metrics._score_rgb_device(
+                red["rgb"], self.gt, red["rgb_std"], min_std)
+            self.packed_host = torch.empty(self.packed_dev.shape, dtype=self.packed_dev.dtype, pin_memory=True)
+            self.packed_host.copy_(self.packed_dev, non_blocking=True)
+        self.red = red
+        self.comp_done, self.post_done = torch.cuda.Event(), torch.cuda.Event()
+        self.pending: Optional[metrics.PendingScores] = None
+
+
+class GraphedViews:
+    """``evaluate_view_async`` as CUDA-graph replays.  The device work of a view with fixed input tensors never
+    changes (all segment / cut tables live on the device), so it is captured once per member set: one graph for the
+    batched compositing call (main stream) and one for member reduce + scoring + the packed device->host copy (side
+    stream, so that it runs underneath the next view's persistent compositing kernels).  Two buffer sets per member
+    set alternate, so view i+1 never overwrites what the scoring of view i still reads; all graphs of a buffer
+    set index share one memory pool.  Per view the host issues two graph launches and four event operations
+    (~0.03 ms) instead of ~25 kernel launches through ctypes (~0.7 ms).  The ground truth is copied into the slot's
+    static buffer (13 MB, device to device) so that views sharing ray samples but not ground truth share graphs."""
+
+    def __init__(self, height: int, width: int, rays_per_chunk: int = 1 << 15, min_rgb_std_for_nll: float = 3e-2):
+        self.h, self.w, self.chunk, self.min_std = height, width, rays_per_chunk, min_rgb_std_for_nll
+        self._slots: Dict[tuple, _GraphSlot] = {}          # (member tensors, buffer set) -> graphs
+        self._count = 0
+        self._pools = None
+        self._side: Optional["torch.cuda.Stream"] = None
+        self._last_post: List[Optional["torch.cuda.Event"]] = [None, None]
+        self._warm = False
+
+    @staticmethod
+    def _key(members) -> tuple:
+        return tuple(m[k].data_ptr() for m in members for k in RAY_KEYS)
+
+    def launch(self, members: Sequence[Dict[str, Tensor]], rgb_gt: Tensor, timers: Optional[list] = None) -> PendingView:
+        dev = rgb_gt.device
+        turn = self._count & 1                     # consecutive views alternate between the two buffer sets
+        self._count += 1
+        key = (self._key(members), turn)
+        slot = self._slots.get(key)
+        if slot is None:
+            if self._pools is None:
+                self._pools = (torch.cuda.graph_pool_handle(), torch.cuda.graph_pool_handle())
+                self._side = _score_stream(dev)
+            if not self._warm:                     # eager once: lazy module loading, cached segment / cut tables
+                evaluate_view_async(members, rgb_gt, self.h, self.w, self.chunk, self.min_std).finish()
+                self._warm = True
+            torch.cuda.synchronize(dev)
+            slot = self._slots[key] = _GraphSlot(members, rgb_gt.shape, self.h, self.w, self.chunk, self.min_std,
+                                                 self._pools[turn], self._side)
+            torch.cuda.synchronize(dev)
+        if slot.pending is not None:
+            slot.pending.finish()                  # its pinned result buffer is about to be overwritten
+        main, side = torch.cuda.current_stream(dev), self._side
+        if self._last_post[turn] is not None:      # the previous user of this buffer set has finished reading it
+            main.wait_event(self._last_post[turn])
+        if timers is not None:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(main)
+        slot.comp.replay()
+        if timers is not None:
+            t1.record(main)
+            timers.append((t0, t1, len(members)))
+        slot.comp_done.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(slot.comp_done)
+            slot.gt.copy_(rgb_gt, non_blocking=True)
+            slot.post.replay()
+            slot.post_done.record(side)
+        self._last_post[turn] = slot.post_done
+        rgb_gt.record_stream(side)
+        slot.pending = metrics.PendingScores(slot.packed_host, slot.packed_dev, slot.post_done, slot.b, slot.n, slot.c,
+                                             slot.cuts_one)
+        return PendingView(slot.pending)
+
+
 class HostViewEvaluator:
     """End-to-end entry: the caller holds one view's member ray samples and ground truth in *pinned host*
     memory; every call copies them to the device on a copy stream (member m+1 uploads while member m
@@ -233,29 +368,57 @@ class HostViewEvaluator:
         return d
 
 
-def pack_record(view_id: int, d: Dict[str, object]) -> np.ndarray:
-    """Fixed-size float64 record of one view: 6 AUSE curves, 5 AUCE curves, 10 scalars, view id."""
-    parts = [np.asarray(d[k], dtype=np.float64).reshape(100) for k in CURVE_KEYS_100]
-    parts += [np.asarray(d[k], dtype=np.float64).reshape(99) for k in CURVE_KEYS_99]
-    parts.append(np.array([float(d[k]) for k in SCALAR_KEYS] + [float(view_id)], dtype=np.float64))
-    rec = np.concatenate(parts)
-    assert rec.shape == (RECORD_LEN,)
+def pack_record(view_id: int, d: Optional[Dict[str, object]], depth: Optional[Dict[str, object]] = None,
+                extra: Optional[Dict[str, float]] = None) -> np.ndarray:
+    """Fixed-size float64 record of one view.  ``d``: the rgb entries (``get_unc_metrics_rgb`` curves + the
+    ``rgb_*`` scalars of ``metrics.per_image_rgb_scalars``) or None (``eval_rgb = False``); ``depth``: the same
+    for the depth modality (curves under their plain names + ``depth_*`` scalars, ``metrics.per_image_depth_scalars``);
+    ``extra``: ``psnr / ssim / lpips`` from the model layer and ``num_rays_per_sec / fps``."""
+    rec = np.zeros(RECORD_LEN, dtype=np.float64)
+    o = 0
+    for src in (d, depth):
+        for k in CURVE_KEYS_100:
+            if src is not None:
+                rec[o:o + 100] = np.asarray(src[k], dtype=np.float64).reshape(100)
+            o += 100
+        for k in CURVE_KEYS_99:
+            if src is not None:
+                rec[o:o + 99] = np.asarray(src[k], dtype=np.float64).reshape(99)
+            o += 99
+    extra = extra or {}
+    for k in ALL_SCALAR_KEYS:
+        src = d if k in SCALAR_KEYS else depth if k in DEPTH_SCALAR_KEYS else extra
+        if src is not None and k in src:
+            rec[o] = float(src[k])
+        o += 1
+    rec[o:o + 3] = (d is not None, depth is not None, all(k in extra for k in IMAGE_KEYS))
+    rec[-1] = float(view_id)
     return rec
 
 
 def unpack_record(rec: np.ndarray) -> Tuple[int, Dict[str, object]]:
+    """Inverse of ``pack_record``: ``(view id, entries)``; rgb curves under their plain names, depth curves
+    with a ``depth_`` prefix, only the groups whose flag is set."""
+    flags = rec[-1 - len(_FLAGS):-1]
+    has_rgb, has_depth, has_img = (bool(v) for v in flags)
     d: Dict[str, object] = {}
     o = 0
-    for k in CURVE_KEYS_100:
-        d[k] = rec[o:o + 100]
-        o += 100
-    for k in CURVE_KEYS_99:
-        d[k] = rec[o:o + 99]
-        o += 99
-    for k in SCALAR_KEYS:
-        d[k] = float(rec[o])
+    for present, prefix in ((has_rgb, ""), (has_depth, "depth_")):
+        for k in CURVE_KEYS_100:
+            if present:
+                d[prefix + k] = rec[o:o + 100]
+            o += 100
+        for k in CURVE_KEYS_99:
+            if present:
+                d[prefix + k] = rec[o:o + 99]
+            o += 99
+    for k in ALL_SCALAR_KEYS:
+        present = has_rgb if k in SCALAR_KEYS else has_depth if k in DEPTH_SCALAR_KEYS else \
+            has_img if k in IMAGE_KEYS else True
+        if present:
+            d[k] = float(rec[o])
         o += 1
-    return int(rec[o]), d
+    return int(rec[-1]), d
 
 
 def bind_host_thread_to_gpu(local_rank: int) -> bool:
@@ -281,41 +444,86 @@ def bind_host_thread_to_gpu(local_rank: int) -> bool:
         return False
 
 
-def gather_records(local: np.ndarray, device=None) -> np.ndarray:
-    """All-gather the ``[views_per_rank, RECORD_LEN]`` float64 records of every rank (the only collective on
-    the path; NCCL all_gather_into_tensor over NVLink when ``device`` is CUDA, gloo on CPU) and return them
-    ordered by view id."""
+_PINNED: Dict[tuple, Tensor] = {}
+
+
+def _pinned(shape, dtype) -> Tensor:
+    key = (tuple(shape), dtype)
+    t = _PINNED.get(key)
+    if t is None:
+        if len(_PINNED) > 8:
+            _PINNED.clear()
+        t = _PINNED[key] = torch.empty(shape, dtype=dtype, pin_memory=True)
+    return t
+
+
+def gather_records(local: np.ndarray, device=None, rows_per_rank: Optional[int] = None) -> np.ndarray:
+    """All-gather the ``[local_views, RECORD_LEN]`` float64 records of every rank -- the only collective on the
+    path (NCCL ``all_gather_into_tensor`` over NVLink when ``device`` is CUDA, gloo on CPU) -- and return them
+    ordered by view id.  Ranks may hold different numbers of views (``shard_views`` gives the last ranks short or
+    empty blocks when ``num_views % world_size != 0``): every block is padded to a common row count with rows
+    marked view id -1, which are stripped after the exchange.  ``rows_per_rank`` (e.g. ``ceil(num_views / world)``)
+    fixes that row count up front; without it the per-rank counts are exchanged first."""
     import torch.distributed as dist
 
-    t = torch.from_numpy(np.ascontiguousarray(local))
+    local = np.ascontiguousarray(local, dtype=np.float64).reshape(-1, RECORD_LEN)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        allrec = t
+        allrec = local
     else:
-        if device is not None:
-            t = t.to(device)
-        out = torch.empty((dist.get_world_size() * t.shape[0], t.shape[1]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t)
-        allrec = out.cpu()
-    allrec = allrec.numpy()
+        world = dist.get_world_size()
+        on_gpu = device is not None and torch.device(device).type == "cuda"
+        if rows_per_rank is None:
+            cnt = torch.tensor([local.shape[0]], dtype=torch.int64)
+            cnt = cnt.to(device) if on_gpu else cnt
+            counts = torch.empty(world, dtype=torch.int64, device=cnt.device)
+            dist.all_gather_into_tensor(counts, cnt)
+            rows_per_rank = int(counts.max().item())
+        if local.shape[0] > rows_per_rank:
+            raise ValueError(f"{local.shape[0]} local records exceed rows_per_rank = {rows_per_rank}")
+        rows = max(1, int(rows_per_rank))
+        if on_gpu:
+            stage = _pinned((rows, RECORD_LEN), torch.float64)
+            stage.zero_()
+            stage[:, -1] = -1.0
+            stage[:local.shape[0]] = torch.from_numpy(local)
+            t = stage.to(device, non_blocking=True)
+            out = torch.empty((world * rows, RECORD_LEN), dtype=torch.float64, device=device)
+            dist.all_gather_into_tensor(out, t)
+            host = _pinned((world * rows, RECORD_LEN), torch.float64)
+            host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
+            allrec = host.numpy().copy()
+        else:
+            t = torch.zeros((rows, RECORD_LEN), dtype=torch.float64)
+            t[:, -1] = -1.0
+            t[:local.shape[0]] = torch.from_numpy(local)
+            out = torch.empty((world * rows, RECORD_LEN), dtype=torch.float64)
+            dist.all_gather_into_tensor(out, t)
+            allrec = out.numpy()
+        allrec = allrec[allrec[:, -1] >= 0]
     order = np.argsort(allrec[:, -1], kind="stable")
     return allrec[order]
 
 
 def aggregate_records(records: np.ndarray) -> Dict[str, object]:
-    """The reference's test-set aggregation (eval_uncertainty.py:920-946, 957-1067, 1070-1077) in view
-    order: float64 running sums of the curves / num_images, float32 ``torch.mean`` of the scalars."""
+    """The reference's test-set aggregation (eval_uncertainty.py:920-946, 957-1067, 1070-1077) in view order:
+    float64 running sums of the curves / num_images, float32 ``torch.mean`` of the per-image python floats.
+    Scalars come back in the reference's ``metrics.json`` order; rows with a negative view id (padding) are ignored."""
+    records = records[records[:, -1] >= 0]
     n = records.shape[0]
     curves: Dict[str, np.ndarray] = {}
-    scal: Dict[str, list] = {k: [] for k in SCALAR_KEYS}
+    scal: Dict[str, list] = {}
     for rec in records:
         _, d = unpack_record(rec)
-        for k in CURVE_KEYS_100 + CURVE_KEYS_99:
-            curves[k] = curves.get(k, np.zeros(len(d[k]))) + d[k]
-        for k in SCALAR_KEYS:
-            scal[k].append(d[k])
+        for k, v in d.items():
+            if isinstance(v, float):
+                scal.setdefault(k, []).append(v)
+            else:
+                curves[k] = curves.get(k, np.zeros(len(v))) + v
     out: Dict[str, object] = {k: v / n for k, v in curves.items()}
-    for k in SCALAR_KEYS:
-        out[k] = float(torch.mean(torch.tensor(scal[k])))
+    for k in ALL_SCALAR_KEYS:
+        if k in scal and len(scal[k]) == n:
+            out[k] = float(torch.mean(torch.tensor(scal[k])))
     return out
 
 
