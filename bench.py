@@ -94,7 +94,7 @@ class ClockSampler:
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, device_index: int, period_s: float = float(os.environ.get("UB_CLOCK_PERIOD_MS", "10")) * 1e-3):
+    def __init__(self, device_index: int, period_s: float = float(os.environ.get("UB_CLOCK_PERIOD_MS", "4")) * 1e-3):
         self.samples, self.reasons, self.power = [], set(), []
         self.period = period_s
         self._stop = threading.Event()
@@ -687,6 +687,7 @@ def sweep_summary(ctx, run, h, w, m):
             "gather_ms_per_rank_minmax": [min(run["gather_ms_per_rank"]), max(run["gather_ms_per_rank"])],
             "resident_pool": f"{run['pool']} distinct member sets ({run['pool'] * m * h * w * 1536 / 1e9:.0f} GB), view v uses set v % {run['pool']}; "
                              f"ground truth drawn per view",
+            "composite_ms_per_launch": (sum(run["comp_ms"]) / len(run["comp_ms"])) if run.get("comp_ms") else None,
             "records_sha256": records_digest(run["records"]) if ctx.rank == 0 else None,
             "records_sha256_note": "identical at N = 1, 2, 4, 8 <=> the sharded run is bit-identical to the single-GPU run",
             "check": {k: agg.get(k) for k in ("rgb_ause_rmse", "rgb_nll", "rgb_auc_abs_error")},

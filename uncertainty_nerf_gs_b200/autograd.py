@@ -26,6 +26,9 @@ class _CompositeRaysFn(torch.autograd.Function):
                                  rays_per_chunk=rays_per_chunk, eval_mode=False, return_weights=True)
         ctx.background = background
         ctx.rays_per_chunk = rays_per_chunk
+        # outputs the loss does not use must arrive as None, not as zeros: a zero gradient pushed through the sqrt of
+        # rgb_std / depth_std is 0 / 0 = NaN wherever the variance is 0 (torch never runs that backward either)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(density, deltas, starts, ends, rgb, beta, out["depth"], out["_workspace"])
         ctx.mark_non_differentiable(out["depth"])
         return tuple(out[k] for k in _OUT_KEYS) + (out["depth"],)
@@ -92,6 +95,7 @@ class _CompositeTilesFn(torch.autograd.Function):
         outs, alpha, _ = ops.composite_tiles_planes(xys, conics, opacities, planes, gaussian_ids, tile_bins,
                                                     height, width, background)
         ctx.height, ctx.width, ctx.background = height, width, background
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(xys, conics, opacities, gaussian_ids, tile_bins, *planes)
         return (*outs, alpha)
 

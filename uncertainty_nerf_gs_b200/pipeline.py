@@ -215,20 +215,28 @@ class GraphedScore:
         self.stream = stream
         metrics.score_rgb_batch(rgb_pred, rgb_gt, rgb_std, min_rgb_std_for_nll)   # warm: lazy loads, cached tables
         torch.cuda.synchronize(dev)
+        from . import ops
+
         self.graph = torch.cuda.CUDAGraph()
         kw = {} if pool is None else {"pool": pool}
+        count0 = ops.LAUNCH_COUNT
         with torch.cuda.graph(self.graph, **kw):
             self.packed_dev, self.b, self.n, self.c, self.cuts_one = metrics._score_rgb_device(
                 rgb_pred, rgb_gt, rgb_std, min_rgb_std_for_nll)
             self.packed_host = torch.empty(self.packed_dev.shape, dtype=self.packed_dev.dtype, pin_memory=True)
             self.packed_host.copy_(self.packed_dev, non_blocking=True)
+        self.kernels = ops.LAUNCH_COUNT - count0
+        ops._count(-self.kernels)
         self.done = torch.cuda.Event()
         self._last: Optional[metrics.PendingScores] = None
 
     def launch(self) -> "metrics.PendingScores":
         if self._last is not None:
             self._last.finish()                     # the pinned result buffer is about to be overwritten
+        from . import ops
+
         self.graph.replay()
+        ops._count(self.kernels)
         self.done.record()
         self._last = metrics.PendingScores(self.packed_host, self.packed_dev, self.done, self.b, self.n, self.c,
                                            self.cuts_one)
@@ -241,8 +249,11 @@ class _GraphSlot:
 
     def __init__(self, members, gt_shape, h, w, chunk, min_std, pool, side):
         dev = members[0]["density"].device
+        from . import ops
+
         self.gt = torch.empty(gt_shape, device=dev)
         self.comp, self.post = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        count0 = ops.LAUNCH_COUNT
         with torch.cuda.graph(self.comp, pool=pool):
             outs = render_members(members, h, w, chunk)
         self.outs = outs
@@ -253,6 +264,8 @@ class _GraphSlot:
             self.packed_host = torch.empty(self.packed_dev.shape, dtype=self.packed_dev.dtype, pin_memory=True)
             self.packed_host.copy_(self.packed_dev, non_blocking=True)
         self.red = red
+        self.kernels = ops.LAUNCH_COUNT - count0        # kernels of ours inside the two graphs (one replay launches them all)
+        ops._count(-self.kernels)                       # capturing launched nothing
         self.comp_done, self.post_done = torch.cuda.Event(), torch.cuda.Event()
         self.pending: Optional[metrics.PendingScores] = None
 
@@ -281,11 +294,13 @@ class GraphedViews:
         return tuple(m[k].data_ptr() for m in members for k in RAY_KEYS)
 
     def launch(self, members: Sequence[Dict[str, Tensor]], rgb_gt: Tensor, timers: Optional[list] = None) -> PendingView:
+        from . import ops
+
         dev = rgb_gt.device
         turn = self._count & 1                     # consecutive views alternate between the two buffer sets
         self._count += 1
-        key = (self._key(members), turn)
-        slot = self._slots.get(key)
+        mkey = self._key(members)
+        slot = self._slots.get((mkey, turn))
         if slot is None:
             if self._pools is None:
                 self._pools = (torch.cuda.graph_pool_handle(), torch.cuda.graph_pool_handle())
@@ -294,9 +309,11 @@ class GraphedViews:
                 evaluate_view_async(members, rgb_gt, self.h, self.w, self.chunk, self.min_std).finish()
                 self._warm = True
             torch.cuda.synchronize(dev)
-            slot = self._slots[key] = _GraphSlot(members, rgb_gt.shape, self.h, self.w, self.chunk, self.min_std,
-                                                 self._pools[turn], self._side)
+            for t in (0, 1):                       # both buffer sets at first sight: no capture later, whatever the phase
+                self._slots[(mkey, t)] = _GraphSlot(members, rgb_gt.shape, self.h, self.w, self.chunk, self.min_std,
+                                                    self._pools[t], self._side)
             torch.cuda.synchronize(dev)
+            slot = self._slots[(mkey, turn)]
         if slot.pending is not None:
             slot.pending.finish()                  # its pinned result buffer is about to be overwritten
         main, side = torch.cuda.current_stream(dev), self._side
@@ -316,6 +333,7 @@ class GraphedViews:
             slot.post.replay()
             slot.post_done.record(side)
         self._last_post[turn] = slot.post_done
+        ops._count(slot.kernels)
         rgb_gt.record_stream(side)
         slot.pending = metrics.PendingScores(slot.packed_host, slot.packed_dev, slot.post_done, slot.b, slot.n, slot.c,
                                              slot.cuts_one)
