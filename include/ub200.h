@@ -355,6 +355,16 @@ int ub_composite_tiles_planes(const float* xys, const float* conics, const float
                               float* const* outs_host, float* out_alpha, uint32_t* channel_max_keys,
                               void* stream);
 
+/* Diagnostic (parity tests): sigma and alpha = min(0.999, opacity * __expf(-sigma)) of the list entries
+ * gaussian_ids[first .. first + count) for the 256 pixel centres of tile (tile_x, tile_y), exactly as the compositing
+ * kernels evaluate them (same device function, rounding pinned).  out_sigma / out_alpha: DEVICE [count, 16, 16],
+ * row-major inside the tile.  Lets a host oracle replay gsplat's threshold decisions (sigma < 0, alpha < 1/255,
+ * T (1 - alpha) <= 1e-4; gsplat 0.1.11 rasterize_forward, reached from activesplatfacto_model.py:260-355) in the
+ * same float32 arithmetic. */
+int ub_tile_alpha_probe(const float* xys, const float* conics, const float* opacities,
+                        const int32_t* gaussian_ids, int32_t first, int32_t count, int32_t tile_x,
+                        int32_t tile_y, float* out_sigma, float* out_alpha, void* stream);
+
 /* In-place post-processing of one output plane [num_pixels, channels]:
  *   clamp_max_one   : image = min(image, 1)                       activesplatfacto_model.py:275
  *   divide_by_alpha : image = alpha > 0 ? image / alpha : max     activesplatfacto_model.py:319, 356

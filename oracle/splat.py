@@ -6,8 +6,10 @@ the published algorithm of gsplat 0.1.11 ``rasterize_forward`` (the version
 ``/root/reference/README.md:30`` pins; not vendored, not installable here); the pass structure and the
 post-processing follow the reference's call sites,
 ``nerfuncertainty/models/activesplatfacto/activesplatfacto_model.py:260-367``.
-One deliberate difference to gsplat's CUDA kernel: ``exp`` is the accurate float32 exponential, not
-the fast ``__expf`` intrinsic.
+``exp``: gsplat's CUDA kernel (and ours) uses the fast ``__expf`` intrinsic, which a CPU cannot reproduce;
+``rasterize`` therefore takes the per-(splat, pixel) ``sigma`` / ``alpha`` values from the device through its ``probe``
+argument when exact agreement of the threshold decisions is wanted (tests/test_gpu_splat_exact.py), and falls back to
+torch's accurate float32 ``exp`` otherwise (decisions can then differ where a value sits within an ulp of a threshold).
 """
 from __future__ import annotations
 
@@ -152,18 +154,33 @@ def spherical_harmonics(degrees_to_use: int, viewdirs: Tensor, coeffs: Tensor) -
 
 
 def rasterize(xys: Tensor, conics: Tensor, opacities: Tensor, colors: Tensor, gaussian_ids: Tensor,
-              tile_bins: Tensor, height: int, width: int, background: Tensor) -> Tuple[Tensor, Tensor]:
+              tile_bins: Tensor, height: int, width: int, background: Tensor, tiles=None, probe=None,
+              want_counts: bool = False):
     """``out [H, W, C] = sum_i c_i alpha_i T_i + T_final * background``, ``alpha [H, W] = 1 - T_final``.
-    Vectorised over the pixels of a tile, sequential over the tile's depth-sorted Gaussian list."""
+    Vectorised over the pixels of a tile, sequential over the tile's depth-sorted Gaussian list.
+
+    ``tiles``: iterable of tile indices to rasterise (default: all; other pixels keep background / alpha 0).
+    ``probe(tile_index, lo, hi) -> (sigma, alpha) [hi - lo, 16, 16]``: take the per-(splat, pixel) ``sigma`` and
+    ``alpha = min(0.999, opacity * exp(-sigma))`` from there instead of computing them with torch's ``exp`` -- the
+    CUDA kernels use the fast ``__expf`` intrinsic like gsplat's own kernel, which no CPU can reproduce; with the
+    device's values every threshold decision below is the same float32 comparison the kernel makes, so the set of
+    contributing splats of every pixel (and with it the alpha image) is reproduced exactly.
+    ``want_counts``: also return the number of contributing splats per pixel ``[H, W]`` (int64)."""
     ch = colors.shape[1]
     out = torch.zeros(height, width, ch)
     final_t = torch.ones(height, width)
+    counts = torch.zeros(height, width, dtype=torch.int64)
     tiles_x = (width + TILE - 1) // TILE
     tiles_y = (height + TILE - 1) // TILE
     opac = opacities.reshape(-1)
+    chosen = None if tiles is None else set(int(t) for t in tiles)
     for ty in range(tiles_y):
         for tx in range(tiles_x):
+            if chosen is not None and ty * tiles_x + tx not in chosen:
+                out[ty * TILE:(ty + 1) * TILE, tx * TILE:(tx + 1) * TILE] = background
+                continue
             lo, hi = (int(v) for v in tile_bins[ty * tiles_x + tx])
+            probed = probe(ty * tiles_x + tx, lo, hi) if probe is not None and hi > lo else None
             i0, j0 = ty * TILE, tx * TILE
             i1, j1 = min(i0 + TILE, height), min(j0 + TILE, width)
             ii, jj = torch.meshgrid(torch.arange(i0, i1), torch.arange(j0, j1), indexing="ij")
@@ -172,14 +189,19 @@ def rasterize(xys: Tensor, conics: Tensor, opacities: Tensor, colors: Tensor, ga
             T = torch.ones_like(px)
             acc = torch.zeros(*px.shape, ch)
             done = torch.zeros_like(px, dtype=torch.bool)
+            cnt = torch.zeros_like(px, dtype=torch.int64)
             for idx in range(lo, hi):
                 if bool(done.all()):
                     break
                 g = int(gaussian_ids[idx])
-                dx = xys[g, 0] - px
-                dy = xys[g, 1] - py
-                sigma = 0.5 * (conics[g, 0] * dx * dx + conics[g, 2] * dy * dy) + conics[g, 1] * dx * dy
-                alpha = torch.clamp(opac[g] * torch.exp(-sigma), max=0.999)
+                if probed is not None:
+                    sigma = probed[0][idx - lo, :i1 - i0, :j1 - j0]
+                    alpha = probed[1][idx - lo, :i1 - i0, :j1 - j0]
+                else:
+                    dx = xys[g, 0] - px
+                    dy = xys[g, 1] - py
+                    sigma = 0.5 * (conics[g, 0] * dx * dx + conics[g, 2] * dy * dy) + conics[g, 1] * dx * dy
+                    alpha = torch.clamp(opac[g] * torch.exp(-sigma), max=0.999)
                 skip = (sigma < 0) | (alpha < 1.0 / 255.0)
                 next_t = T * (1.0 - alpha)
                 stop = (~done) & (~skip) & (next_t <= 1e-4)
@@ -188,31 +210,38 @@ def rasterize(xys: Tensor, conics: Tensor, opacities: Tensor, colors: Tensor, ga
                 vis = alpha * T
                 acc = torch.where(take[..., None], acc + colors[g] * vis[..., None], acc)
                 T = torch.where(take, next_t, T)
+                cnt = cnt + take.long()
             out[i0:i1, j0:j1] = acc + T[..., None] * background
             final_t[i0:i1, j0:j1] = T
+            counts[i0:i1, j0:j1] = cnt
+    if want_counts:
+        return out, 1.0 - final_t, counts
     return out, 1.0 - final_t
 
 
 def active_splatfacto_outputs(xys: Tensor, depths: Tensor, conics: Tensor, opacities: Tensor, rgbs: Tensor,
                               betas: Tensor, gaussian_ids: Tensor, tile_bins: Tensor, height: int, width: int,
-                              background: Tensor) -> Dict[str, Tensor]:
+                              background: Tensor, probe=None, depth_image_override: Tensor = None) -> Dict[str, Tensor]:
     """The rasterisation block of ``ActiveSplatfactoModel.get_outputs``
-    (``activesplatfacto_model.py:260-367``) as four separate 3-channel passes, like the reference."""
+    (``activesplatfacto_model.py:260-367``) as four separate 3-channel passes, like the reference.
+    ``probe``: see ``rasterize``.  ``depth_image_override``: use this depth image for the per-Gaussian residuals of
+    the depth-variance pass (tests isolate that pass from the rounding of the depth pass with it)."""
     args = (gaussian_ids, tile_bins, height, width)
     zeros3 = torch.zeros(3)
-    rgb, alpha = rasterize(xys, conics, opacities, rgbs, *args, background)
+    kw = {"probe": probe}
+    rgb, alpha = rasterize(xys, conics, opacities, rgbs, *args, background, **kw)
     alpha = alpha[..., None]
     rgb = torch.clamp(rgb, max=1.0)
-    unc_im = rasterize(xys, conics, opacities, betas.reshape(-1, 1).repeat(1, 3), *args, zeros3)[0][..., 0:1]
-    depth_im = rasterize(xys, conics, opacities, depths[:, None].repeat(1, 3), *args, zeros3)[0][..., 0:1]
+    unc_im = rasterize(xys, conics, opacities, betas.reshape(-1, 1).repeat(1, 3), *args, zeros3, **kw)[0][..., 0:1]
+    depth_im = rasterize(xys, conics, opacities, depths[:, None].repeat(1, 3), *args, zeros3, **kw)[0][..., 0:1]
     depth_im = torch.where(alpha > 0, depth_im / alpha, depth_im.detach().max())
     xy_to_pix = torch.floor(xys).long()
     valid = (xy_to_pix[:, 0] > 0) & (xy_to_pix[:, 0] < width) & (xy_to_pix[:, 1] > 0) & (xy_to_pix[:, 1] < height)
     pv = xy_to_pix[valid]
-    fetched = depth_im[pv[:, 1], pv[:, 0], 0]
+    fetched = (depth_im if depth_image_override is None else depth_image_override)[pv[:, 1], pv[:, 0], 0]
     resid = depths.clone()
     resid[valid] -= fetched
-    dvar_im = rasterize(xys, conics, opacities, (resid[:, None] ** 2).repeat(1, 3), *args, zeros3)[0][..., 0:1]
+    dvar_im = rasterize(xys, conics, opacities, (resid[:, None] ** 2).repeat(1, 3), *args, zeros3, **kw)[0][..., 0:1]
     dvar_im = torch.where(alpha > 0, dvar_im / alpha, dvar_im.detach().max())
     return {
         "rgb": rgb, "depth": depth_im, "accumulation": alpha, "background": background,

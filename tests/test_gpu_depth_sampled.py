@@ -99,7 +99,7 @@ def test_philox_draws_are_statistically_sane(built_library):
 
 
 def test_depth_prepare_is_the_reference_torch_lines(built_library):
-    """ub_depth_prepare against the reference's own per-view torch lines (scale, clamp, minimum, boolean mask),
+    """ub_depth_prepare against the reference's own per-view torch lines (scale, masked-assignment clamps, boolean mask),
     bit for bit: ragged views, a view without any valid pixel, a NaN in a ground truth, sizes that are not a
     multiple of the block, pixel order preserved."""
     from uncertainty_nerf_gs_b200 import ops
@@ -111,7 +111,7 @@ def test_depth_prepare_is_the_reference_torch_lines(built_library):
         gt[torch.rand(b, n, generator=g) < 0.4] = 0.0
         gt[1] = 0.0                                             # a view with nothing to score
         if n > 10:
-            gt[2, 7] = float("nan")                             # torch: max() and minimum() propagate it
+            gt[2, 7] = float("nan")                             # MAX_DEPTH = NaN: `depth > NaN` is false, nothing is clamped above
             gt[3, 3] = -2.0
         depth = torch.randn(b, n, generator=g) * 3
         depth[0, 0] = float("nan")
@@ -124,7 +124,9 @@ def test_depth_prepare_is_the_reference_torch_lines(built_library):
             max_d = gt[i].max().float()
             d = scales[i] * depth[i]
             mask = gt[i] > 0
-            dm = torch.minimum(torch.clamp(d[mask], min=1e-3), max_d)
+            dm = d[mask]                                        # eval_uncertainty.py:552-560, the reference's own lines:
+            dm[dm < 1e-3] = 1e-3                                #   depth[depth < MIN_DEPTH] = MIN_DEPTH
+            dm[dm > max_d] = max_d                              #   depth[depth > MAX_DEPTH] = MAX_DEPTH
             want_p.append(dm); want_s.append((scales[i] * std[i])[mask]); want_g.append(gt[i][mask]); want_l.append(int(mask.sum()))
         assert lens == want_l
         for got, want in ((pred, want_p), (sd, want_s), (gg, want_g)):

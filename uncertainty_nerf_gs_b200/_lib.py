@@ -119,6 +119,7 @@ SIGNATURES = {
     "ub_composite_tiles_planes_backward": (C.c_int, [fp, fp, fp, C.POINTER(fp), C.POINTER(C.c_int32), C.c_int32, fp,
                                                      fp, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(fp),
                                                      fp, C.c_int64, fp, fp, fp, C.POINTER(fp), fp]),
+    "ub_tile_alpha_probe": (C.c_int, [fp, fp, fp, fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, fp, fp, fp]),
     "ub_splat_normalize": (C.c_int, [fp, C.c_int32, fp, C.c_int64, C.c_int32, C.c_int32, fp, fp, fp, fp]),
     "ub_splat_depth_residual": (C.c_int, [fp, fp, fp, C.c_int32, C.c_int32, C.c_int64, fp, fp]),
     "ub_composite_tiles": (C.c_int, [fp, fp, fp, fp, C.c_int32, fp, fp, C.c_int32, C.c_int32,

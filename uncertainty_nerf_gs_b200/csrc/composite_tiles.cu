@@ -8,10 +8,13 @@
 //   models/activesplatfacto/activesplatfacto_model.py:325-341   per-Gaussian (depth - depth_im[centre pixel])^2
 //   models/activesplatfacto/activesplatfacto_model.py:343-356   depth-variance image, / alpha else max
 // each rasterisation being one gsplat 0.1.11 `rasterize_gaussians` launch with 3-channel colours.  The
-// per-pixel loop restates gsplat's published `rasterize_forward` (not vendored in the reference: parity
-// unpinned): pixel centre (j+0.5, i+0.5); sigma = 0.5(a dx^2 + c dy^2) + b dx dy;
-// alpha = min(0.999, opac * exp(-sigma)); skip if sigma < 0 or alpha < 1/255; stop *before* a Gaussian
-// that would bring T to <= 1e-4; out += colour * alpha * T.
+// per-pixel loop restates gsplat's published `rasterize_forward` (not vendored in the reference):
+// pixel centre (j+0.5, i+0.5); sigma = 0.5(a dx^2 + c dy^2) + b dx dy; alpha = min(0.999, opac * __expf(-sigma))
+// (the fast intrinsic, as in gsplat's kernel); skip if sigma < 0 or alpha < 1/255; stop *before* a Gaussian that
+// would bring T to <= 1e-4; out += colour * alpha * T; T *= 1 - alpha.  The rounding of sigma / alpha / T is pinned
+// (ub_common.cuh: splat_sigma, splat_alpha), and `ub_tile_alpha_probe` hands the (sigma, alpha) values of any tile to
+// the host, so that the CPU oracle replays every threshold decision in the same float32 arithmetic: the set of
+// contributing splats of every pixel -- hence the alpha image -- is reproduced bit for bit (tests/test_gpu_splat_exact.py).
 //
 // Here all channels that share the geometry (rgb, beta, depth = 5) go through ONE pass.  A CTA owns a
 // tile and stages 256 splats at a time in shared memory, packed as float4 records
@@ -130,15 +133,15 @@ __global__ void __launch_bounds__(kTileThreads) composite_tiles_kernel(const Til
       const float4 ga = s_geo[t];
       const float4 gb = s_rec[0][t];
       const float dx = ga.x - px, dy = ga.y - py;
-      const float sigma = 0.5f * (ga.w * dx * dx + gb.y * dy * dy) + gb.x * dx * dy;
-      const float alpha = fminf(0.999f, ga.z * expf(-sigma));
+      const float sigma = splat_sigma(ga.w, gb.x, gb.y, dx, dy);
+      const float alpha = splat_alpha(ga.z, sigma);
       if (sigma < 0.0f || alpha < 1.0f / 255.0f) continue;
-      const float next_T = T * (1.0f - alpha);
+      const float next_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
       if (next_T <= 1e-4f) {
         done = true;
         break;
       }
-      const float vis = alpha * T;
+      const float vis = __fmul_rn(alpha, T);
       acc[0] += gb.z * vis;
       if (CH > 1) acc[1] += gb.w * vis;
 #pragma unroll
@@ -186,6 +189,20 @@ __global__ void __launch_bounds__(kTileThreads) composite_tiles_kernel(const Til
       if (m > -INFINITY) atomicMax(&p.channel_max_keys[threadIdx.x], order_key(m));
     }
   }
+}
+
+// Diagnostic: (sigma, alpha) of `count` consecutive entries of a tile's list for the 256 pixels of the tile, exactly as
+// composite_tiles_kernel evaluates them.  One block per list entry, thread = pixel (row-major inside the tile).
+__global__ void __launch_bounds__(kTileThreads)
+tile_alpha_probe_kernel(const float* xys, const float* conics, const float* opacities, const int32_t* gaussian_ids,
+                        int first, int tile_x, int tile_y, float* out_sigma, float* out_alpha) {
+  const int g = gaussian_ids[first + blockIdx.x];
+  const int ti = threadIdx.x / UB_TILE, tj = threadIdx.x % UB_TILE;
+  const float px = (float)(tile_x * UB_TILE + tj) + 0.5f, py = (float)(tile_y * UB_TILE + ti) + 0.5f;
+  const float dx = xys[2 * (size_t)g] - px, dy = xys[2 * (size_t)g + 1] - py;
+  const float sigma = splat_sigma(conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2], dx, dy);
+  out_sigma[(size_t)blockIdx.x * kTileThreads + threadIdx.x] = sigma;
+  out_alpha[(size_t)blockIdx.x * kTileThreads + threadIdx.x] = splat_alpha(opacities[g], sigma);
 }
 
 static int launch_tiles(TileParams p, int channels, int img_height, cudaStream_t stream) {
@@ -306,6 +323,19 @@ int ub_composite_tiles(const float* xys, const float* conics, const float* opaci
   float* outs[1] = {out};
   return ub_composite_tiles_planes(xys, conics, opacities, planes, chs, 1, gaussian_ids, tile_bins, img_height,
                                    img_width, background_host, outs, out_alpha, nullptr, stream_v);
+}
+
+int ub_tile_alpha_probe(const float* xys, const float* conics, const float* opacities, const int32_t* gaussian_ids,
+                        int32_t first, int32_t count, int32_t tile_x, int32_t tile_y, float* out_sigma,
+                        float* out_alpha, void* stream_v) {
+  using namespace ub;
+  UB_REQUIRE(xys && conics && opacities && gaussian_ids && out_sigma && out_alpha, UB_ERR_BAD_ARG,
+             "tile_alpha_probe: NULL pointer");
+  UB_REQUIRE(first >= 0 && count >= 0 && tile_x >= 0 && tile_y >= 0, UB_ERR_BAD_ARG, "tile_alpha_probe: bad range");
+  if (count == 0) return UB_OK;
+  tile_alpha_probe_kernel<<<(unsigned)count, kTileThreads, 0, static_cast<cudaStream_t>(stream_v)>>>(
+      xys, conics, opacities, gaussian_ids, first, tile_x, tile_y, out_sigma, out_alpha);
+  return check_launch("tile_alpha_probe");
 }
 
 int ub_splat_normalize(float* image, int32_t channels, const float* alpha, int64_t num_pixels,

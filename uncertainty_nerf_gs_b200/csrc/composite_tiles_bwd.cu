@@ -166,10 +166,10 @@ __global__ void __launch_bounds__(kBwdThreads) composite_tiles_bwd_kernel(const 
         const float4 ga = s_geo[t];
         const float4 gb = s_rec[0][t];
         const float dx = ga.x - px, dy = ga.y - py;
-        const float sigma = 0.5f * (ga.w * dx * dx + gb.y * dy * dy) + gb.x * dx * dy;
-        const float alpha = fminf(0.999f, ga.z * expf(-sigma));
+        const float sigma = splat_sigma(ga.w, gb.x, gb.y, dx, dy);
+        const float alpha = splat_alpha(ga.z, sigma);
         if (sigma < 0.0f || alpha < 1.0f / 255.0f) continue;
-        const float next_T = T * (1.0f - alpha);
+        const float next_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
         if (next_T <= 1e-4f) {
           done = true;
           break;
@@ -237,9 +237,9 @@ __global__ void __launch_bounds__(kBwdThreads) composite_tiles_bwd_kernel(const 
         const float4 ga = s_geo[t];
         const float4 gb = s_rec[0][t];
         const float dx = ga.x - px, dy = ga.y - py;
-        const float sigma = 0.5f * (ga.w * dx * dx + gb.y * dy * dy) + gb.x * dx * dy;
-        const float vis = expf(-sigma);
-        const float raw = ga.z * vis;
+        const float sigma = splat_sigma(ga.w, gb.x, gb.y, dx, dy);
+        const float vis = splat_falloff(sigma);
+        const float raw = __fmul_rn(ga.z, vis);
         const float alpha = fminf(0.999f, raw);
         valid = !(sigma < 0.0f || alpha < 1.0f / 255.0f);
         if (valid) {

@@ -2,14 +2,16 @@
 //
 // Reference arithmetic (file:line under /root/reference/nerfuncertainty/scripts/eval_uncertainty.py):
 //   :461-462   depth = a * depth;  depth_std = a * depth_std          (a = per-dataset scale)
-//   :511-513   max_depth = depth_gt.max();  depth = clamp(depth, min=1e-3);  depth = minimum(depth, max_depth)
+//   :455-456   MIN_DEPTH = 1e-3;  MAX_DEPTH = depth_gt.max()
+//   :558-560   depth[depth < MIN_DEPTH] = MIN_DEPTH;  depth[depth > MAX_DEPTH] = MAX_DEPTH   (masked assignments)
 //   :552-560   mask = depth_gt > 0;  depth[mask], depth_std[mask], depth_gt[mask]
 // The masked selections keep row-major pixel order (it decides the ties of the stable ranking downstream), so
 // this is a *stable* stream compaction per view: block counts -> per-view exclusive scan -> scatter.  Views
 // become ragged segments of one flat array; `out_offsets` (device int64 [B+1]) is what the caller reads back
 // to size the scoring launches -- the only host synchronisation of the depth path.
-// NaN semantics follow torch: clamp keeps a NaN depth, minimum / max propagate NaN (a NaN anywhere in a view's
-// ground truth makes every clamped depth of that view NaN), NaN > 0 is false.
+// NaN semantics follow those masked assignments: a NaN depth fails both comparisons and stays NaN; torch's max()
+// propagates NaN, so a NaN anywhere in a view's ground truth makes MAX_DEPTH NaN, `depth > NaN` is false everywhere
+// and the view's depths are left unclamped above (not turned into NaN); NaN > 0 is false in the mask.
 #include "ub_common.cuh"
 
 namespace ub {
@@ -152,8 +154,8 @@ __global__ void __launch_bounds__(kDepthThreads) depth_scatter_kernel(const Dept
     if (keep) {
       const long long dst = out + before + __popc(m & ((1u << lane) - 1u));
       float d = __fmul_rn(scale, p.depth[voff + i]);
-      d = d != d ? d : fmaxf(d, 1e-3f);                    // torch.clamp(min=1e-3) keeps NaN
-      d = (d != d || max_d != max_d) ? NAN : fminf(d, max_d);  // torch.minimum propagates NaN
+      if (d < 1e-3f) d = 1e-3f;    // depth[depth < MIN_DEPTH] = MIN_DEPTH: false for a NaN depth
+      if (d > max_d) d = max_d;    // depth[depth > MAX_DEPTH] = MAX_DEPTH: false for a NaN depth or a NaN MAX_DEPTH
       p.out_pred[dst] = d;
       p.out_std[dst] = __fmul_rn(scale, p.depth_std[voff + i]);
       p.out_gt[dst] = g;

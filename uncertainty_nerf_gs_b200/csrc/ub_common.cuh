@@ -159,6 +159,21 @@ __device__ __forceinline__ float4 splat_reach_box(float x, float y, float opac, 
   return make_float4(x - hx, x + hx, y - hy, y + hy);
 }
 
+// The per-(pixel, splat) test of gsplat 0.1.11's `rasterize_forward` with the rounding of every operation pinned,
+// so that the forward kernel, its backward and the diagnostic probe (ub_tile_alpha_probe) agree bit for bit:
+//   sigma = 0.5 (A dx^2 + C dy^2) + B dx dy        as  fma(B dx, dy, 0.5 * fma(C dy, dy, (A dx) dx))
+//   alpha = min(0.999, opacity * __expf(-sigma))   __expf = ex2.approx(x log2 e), the intrinsic gsplat's kernel uses
+// Decisions downstream (sigma < 0, alpha < 1/255, T (1 - alpha) <= 1e-4) are plain IEEE comparisons of these values.
+__device__ __forceinline__ float splat_sigma(float ca, float cb, float cc, float dx, float dy) {
+  const float a = __fmul_rn(__fmul_rn(ca, dx), dx);
+  const float c = __fmaf_rn(__fmul_rn(cc, dy), dy, a);
+  return __fmaf_rn(__fmul_rn(cb, dx), dy, __fmul_rn(0.5f, c));
+}
+__device__ __forceinline__ float splat_falloff(float sigma) { return __expf(-sigma); }
+__device__ __forceinline__ float splat_alpha(float opac, float sigma) {
+  return fminf(0.999f, __fmul_rn(opac, splat_falloff(sigma)));
+}
+
 // thread -> pixel of a 16 x 16 tile: warp w owns the 8 x 4 block at column 8 (w & 1), row 4 (w >> 1)
 __device__ __forceinline__ void tile_pixel_of_thread(int tid, int& ti, int& tj) {
   const int w = tid >> 5, l = tid & 31;

@@ -715,6 +715,28 @@ def composite_tiles_planes_backward(xys: Tensor, conics: Tensor, opacities: Tens
     return v_xys, v_conics, v_opac, v_pl
 
 
+def tile_alpha_probe(xys: Tensor, conics: Tensor, opacities: Tensor, gaussian_ids: Tensor, first: int, count: int,
+                     tile_x: int, tile_y: int) -> Tuple[Tensor, Tensor]:
+    """Diagnostic: ``(sigma, alpha) [count, 16, 16]`` of ``gaussian_ids[first:first + count]`` at the pixel centres of
+    tile ``(tile_x, tile_y)``, evaluated by the device function the compositing kernels use (``ub_tile_alpha_probe``)."""
+    lib = _lib.load()
+    xys, conics = _dev_f32(xys, "xys"), _dev_f32(conics, "conics")
+    opacities = _dev_f32(opacities.reshape(-1), "opacities")
+    if gaussian_ids.dtype != torch.int32 or not gaussian_ids.is_cuda:
+        raise TypeError("gaussian_ids must be a CUDA int32 tensor")
+    if first < 0 or count < 0 or first + count > gaussian_ids.numel():
+        raise ValueError("probe range outside gaussian_ids")
+    dev = xys.device
+    sigma = torch.empty(count, _lib.UB_TILE, _lib.UB_TILE, device=dev)
+    alpha = torch.empty(count, _lib.UB_TILE, _lib.UB_TILE, device=dev)
+    with _guard(dev):
+        _lib.check(lib.ub_tile_alpha_probe(xys.data_ptr(), conics.data_ptr(), opacities.data_ptr(),
+                                           gaussian_ids.contiguous().data_ptr(), int(first), int(count), int(tile_x),
+                                           int(tile_y), sigma.data_ptr(), alpha.data_ptr(), _stream()))
+    _count(1 if count > 0 else 0)
+    return sigma, alpha
+
+
 def splat_normalize_(image: Tensor, alpha: Optional[Tensor] = None, max_key: Optional[Tensor] = None,
                      clamp_max_one: bool = False, want_square: bool = False, want_sqrt: bool = False):
     """In place: ``min(image, 1)`` and / or ``alpha > 0 ? image / alpha : max`` (activesplatfacto_model.py:275,319).
