@@ -95,6 +95,12 @@ typedef struct ub_composite_rays_args {
   float* out_weights;        /* [R,S] optional: the volume-rendering weights                 */
 } ub_composite_rays_args;
 
+/* Workspace = [per-chunk table, 16 B per chunk: clip bounds of the expected depth, beta-NaN flag]
+ *             [candidate counter, 16 B] [candidate list, 8 B per ray].
+ * The compositing kernel lists the rays that the chunk-wide values can change (expected depth outside the ray's own
+ * step range; non-finite sum w^2 beta) and the finalize launch visits only those.  A workspace that holds just the
+ * chunk table (+16 B) is accepted too: finalize then visits every ray.  The chunk table is what
+ * ub_composite_rays_backward reads as `chunk_workspace`. */
 size_t ub_composite_rays_workspace_bytes(int64_t num_rays, int64_t rays_per_chunk);
 int ub_composite_rays(const ub_composite_rays_args* args, void* workspace, size_t workspace_bytes,
                       void* stream);

@@ -24,7 +24,10 @@
 //
 // Chunk-wide reductions of the reference (clip bounds of expected depth = min/max of steps over
 // the eval chunk; the `isnan(beta).any()` guard) are accumulated per chunk in the workspace and
-// applied by a small finalize kernel.
+// applied by a small finalize kernel.  That kernel does not re-read every ray: the compositing kernel
+// appends the few rays the chunk-wide values can possibly change to a candidate list (expected depth
+// outside the ray's own step range: empty / near-empty rays; non-finite sum w^2 beta), and finalize only
+// visits those (a few microseconds and ~1 % of the rays instead of a 12 B/ray pass over the outputs).
 #include <stdlib.h>
 
 #include "ub_common.cuh"
@@ -57,6 +60,13 @@ struct CompositeParams {
   float* o_dstd;
   float* o_w;
   unsigned* chunk_ws;  // [num_chunks][4]: max key(steps), max ~key(steps), beta-has-NaN, pad
+  // Candidate list of the finalize pass (fast path): rays whose expected depth lies outside the [min, max] of their
+  // OWN steps -- a superset of the rays the chunk-wide clip can change, since the chunk's bounds enclose the ray's --
+  // and rays whose sum w^2 beta came out non-finite (the only ones the NaN-guard redo can change).  NULL: finalize
+  // visits every ray.
+  unsigned* cand_count;
+  unsigned* cand_list;
+  unsigned cand_cap;
 };
 
 constexpr int kLanesPerRay = 4;
@@ -261,10 +271,20 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
       }
     }
     bounds.enter(p.tiles_per_chunk > 0 ? tile / p.tiles_per_chunk : 0, p.chunk_ws);
-    if (active) {
+    float rmin = step[0], rmax = step[0];  // step range of the ray (fminf / fmaxf skip NaN, like the chunk bounds)
 #pragma unroll
-      for (int i = 0; i < P; ++i) bounds.add_step(step[i]);
+    for (int i = 1; i < P; ++i) {
+      rmin = fminf(rmin, step[i]);
+      rmax = fmaxf(rmax, step[i]);
     }
+    if (active) {
+      bounds.add_step(rmin);
+      bounds.add_step(rmax);
+    }
+    rmin = fminf(rmin, __shfl_xor_sync(FULL_MASK, rmin, 1));
+    rmax = fmaxf(rmax, __shfl_xor_sync(FULL_MASK, rmax, 1));
+    rmin = fminf(rmin, __shfl_xor_sync(FULL_MASK, rmin, 2));
+    rmax = fmaxf(rmax, __shfl_xor_sync(FULL_MASK, rmax, 2));
 
     // ---- cumulative weight in float64, first sample with (float)cw >= 0.5 ----
     run = 0.0;
@@ -391,10 +411,22 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
       } else if (q == 1) {
         if (p.o_acc) p.o_acc[ray] = acc;
         if (p.o_depth) p.o_depth[ray] = depth;
-        if (p.o_exp) p.o_exp[ray] = e_num / (acc + 1e-10f);
+        if (p.o_exp) {
+          const float e = e_num / (acc + 1e-10f);
+          p.o_exp[ray] = e;
+          // the chunk-wide clip can only change e if it lies outside the ray's own [min, max] of steps
+          if (p.cand_count && e == e && !(e >= rmin && e <= rmax)) {
+            const unsigned slot = atomicAdd(p.cand_count, 1u);
+            if (slot < p.cand_cap) p.cand_list[slot] = (unsigned)ray;
+          }
+        }
       } else if (q == 2) {
         if (p.o_rgb_var) p.o_rgb_var[ray] = var;
         if (p.o_rgb_std) p.o_rgb_std[ray] = sqrtf(var);
+        if (p.cand_count && has_beta && p.beta_mode == UB_BETA_NAN_GUARD && non_finite(var)) {
+          const unsigned slot = atomicAdd(p.cand_count, 1u);  // the NaN-guard redo only touches non-finite sums
+          if (slot < p.cand_cap) p.cand_list[slot] = (unsigned)ray;
+        }
       } else {
         if (p.o_dvar) p.o_dvar[ray] = dvar;
         if (p.o_dstd) p.o_dstd[ray] = sqrtf(dvar);
@@ -617,20 +649,29 @@ __device__ __forceinline__ void finalize_ray(const CompositeParams& p, long long
   }
 }
 
-__global__ void __launch_bounds__(256) composite_finalize(const CompositeParams p) {
-  const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ray < p.num_rays) finalize_ray(p, ray);
+// visits the candidate list when the batch has one (grid-stride), else every ray
+__device__ __forceinline__ void finalize_batch_rays(const CompositeParams& p) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p.cand_count) {
+    const long long n = min((long long)*p.cand_count, (long long)p.cand_cap);
+    for (long long i = t; i < n; i += stride) finalize_ray(p, (long long)p.cand_list[i]);
+  } else {
+    for (long long ray = t; ray < p.num_rays; ray += stride) finalize_ray(p, ray);
+  }
 }
+
+__global__ void __launch_bounds__(256) composite_finalize(const CompositeParams p) { finalize_batch_rays(p); }
 
 // the finalize passes of up to UB_MAX_COMPOSITE_BATCH independent ray batches in one launch (blockIdx.y = batch)
 struct FinalizeBatch {
   CompositeParams p[UB_MAX_COMPOSITE_BATCH];
 };
 __global__ void __launch_bounds__(256) composite_finalize_batch(const __grid_constant__ FinalizeBatch b) {
-  const CompositeParams& p = b.p[blockIdx.y];
-  const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ray < p.num_rays) finalize_ray(p, ray);
+  finalize_batch_rays(b.p[blockIdx.y]);
 }
+
+constexpr unsigned kCandidateBlocks = 32;  // finalize grid when every batch has a candidate list
 
 static size_t chunk_ws_bytes(long long num_rays, long long rays_per_chunk) {
   long long chunks = 1;
@@ -669,16 +710,34 @@ static bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr
 
 extern "C" {
 
+// workspace of one ray batch: [chunk table | candidate counter (16 B) | candidate list, 2 entries per ray]
+static size_t composite_head_bytes(int64_t num_rays, int64_t rays_per_chunk) {
+  return ub::align_up(ub::chunk_ws_bytes(num_rays, rays_per_chunk), 16) + 16;
+}
+static size_t composite_list_bytes(int64_t num_rays) { return ub::align_up((size_t)(num_rays > 0 ? num_rays : 0) * 2 * 4, 16); }
+
 size_t ub_composite_rays_workspace_bytes(int64_t num_rays, int64_t rays_per_chunk) {
-  return ub::chunk_ws_bytes(num_rays, rays_per_chunk);
+  return composite_head_bytes(num_rays, rays_per_chunk) + composite_list_bytes(num_rays);
 }
 size_t ub_render_weights_workspace_bytes(int64_t num_rays, int64_t rays_per_chunk) {
   return ub::chunk_ws_bytes(num_rays, rays_per_chunk);
 }
 
+static bool composite_fast_path(const ub_composite_rays_args* a) {
+  using namespace ub;
+  const bool chunk_ok = (a->rays_per_chunk <= 0 || a->rays_per_chunk % kRaysPerTile == 0) &&
+                        a->num_rays < (1LL << 30);
+  const bool align_ok = aligned16(a->density) && aligned16(a->deltas) && aligned16(a->starts) &&
+                        aligned16(a->ends) && aligned16(a->rgb) &&
+                        (a->beta == nullptr || aligned16(a->beta)) &&
+                        (a->out_weights == nullptr || aligned16(a->out_weights));
+  const int s = a->num_samples;
+  return chunk_ok && align_ok && (s == 32 || s == 48 || s == 64 || s == 96);
+}
+
 // validation + parameter block of one ray batch (no launches)
 static int composite_prepare(const ub_composite_rays_args* a, void* workspace, size_t workspace_bytes,
-                             ub::CompositeParams& p) {
+                             void* cand_list, ub::CompositeParams& p) {
   using namespace ub;
   UB_REQUIRE(a != nullptr, UB_ERR_BAD_ARG, "composite_rays: args is NULL");
   UB_REQUIRE(a->num_rays >= 0 && a->num_samples >= 1, UB_ERR_BAD_ARG,
@@ -692,7 +751,7 @@ static int composite_prepare(const ub_composite_rays_args* a, void* workspace, s
              "composite_rays: bad beta_mode %d", a->beta_mode);
   UB_REQUIRE((a->out_rgb_var == nullptr && a->out_rgb_std == nullptr) || a->beta != nullptr,
              UB_ERR_BAD_ARG, "composite_rays: rgb_var/rgb_std requested without beta");
-  const size_t need = chunk_ws_bytes(a->num_rays, a->rays_per_chunk);
+  const size_t need = composite_head_bytes(a->num_rays, a->rays_per_chunk);
   UB_REQUIRE(workspace != nullptr && workspace_bytes >= need, UB_ERR_WORKSPACE,
              "composite_rays: workspace %zu B < required %zu B", workspace_bytes, need);
   p = CompositeParams{};
@@ -723,20 +782,19 @@ static int composite_prepare(const ub_composite_rays_args* a, void* workspace, s
   p.o_w = a->out_weights;
   p.chunk_ws = static_cast<unsigned*>(workspace);
   p.tiles_per_chunk = a->rays_per_chunk > 0 ? (int)(a->rays_per_chunk / kRaysPerTile) : 0;
+  if (cand_list != nullptr && composite_fast_path(a)) {  // the generic kernel keeps the visit-every-ray finalize
+    p.cand_count = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + need - 16);
+    p.cand_list = static_cast<unsigned*>(cand_list);
+    p.cand_cap = (unsigned)(2 * a->num_rays);
+  }
   return UB_OK;
 }
 
 // the compositing kernel of one prepared batch (the chunk workspace must already be zero)
 static int composite_launch_main(const ub_composite_rays_args* a, const ub::CompositeParams& p, cudaStream_t stream) {
   using namespace ub;
-  const bool chunk_ok = (a->rays_per_chunk <= 0 || a->rays_per_chunk % kRaysPerTile == 0) &&
-                        a->num_rays < (1LL << 31) - 64;
-  const bool align_ok = aligned16(a->density) && aligned16(a->deltas) && aligned16(a->starts) &&
-                        aligned16(a->ends) && aligned16(a->rgb) &&
-                        (a->beta == nullptr || aligned16(a->beta)) &&
-                        (a->out_weights == nullptr || aligned16(a->out_weights));
   int rc = UB_OK;
-  bool fast = chunk_ok && align_ok;
+  bool fast = composite_fast_path(a);
   if (fast) {
     switch (a->num_samples) {
       case 32: rc = launch_tma<32, 8, 16>(p, stream); break;
@@ -771,26 +829,34 @@ int ub_composite_rays(const ub_composite_rays_args* a, void* workspace, size_t w
                       void* stream_v) {
   using namespace ub;
   CompositeParams p{};
-  int rc = composite_prepare(a, workspace, workspace_bytes, p);
+  // a workspace that only holds the chunk table (the size this call needed before the candidate list existed) still
+  // works: finalize then visits every ray
+  const bool has_shape = a != nullptr && a->num_rays > 0;
+  const size_t head = has_shape ? composite_head_bytes(a->num_rays, a->rays_per_chunk) : 0;
+  const bool room = has_shape && workspace != nullptr &&
+                    workspace_bytes >= ub_composite_rays_workspace_bytes(a->num_rays, a->rays_per_chunk);
+  int rc = composite_prepare(a, workspace, workspace_bytes, room ? static_cast<char*>(workspace) + head : nullptr, p);
   if (rc != UB_OK || a->num_rays == 0) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const size_t need = chunk_ws_bytes(a->num_rays, a->rays_per_chunk);
-  if (cudaMemsetAsync(workspace, 0, need, stream) != cudaSuccess) return check_launch("composite_rays memset");
+  if (cudaMemsetAsync(workspace, 0, head, stream) != cudaSuccess) return check_launch("composite_rays memset");
   rc = composite_launch_main(a, p, stream);
   if (rc != UB_OK) return rc;
-  const unsigned fblocks = (unsigned)((a->num_rays + 255) / 256);
+  const unsigned fblocks = p.cand_count ? kCandidateBlocks : (unsigned)min((long long)65535, (long long)((a->num_rays + 255) / 256));
   composite_finalize<<<fblocks, 256, 0, stream>>>(p);
   return check_launch("composite_finalize");
 }
 
-static size_t batch_ws_slice(const ub_composite_rays_args& a) {
-  return ub::align_up(ub::chunk_ws_bytes(a.num_rays, a.rays_per_chunk), 16);
+// batch workspace: the heads (chunk table + candidate counter) of all batches first -- one memset --, then the lists
+static size_t batch_heads_bytes(const ub_composite_rays_args* args, int32_t num_batches) {
+  size_t total = 0;
+  for (int i = 0; i < num_batches; ++i) total += composite_head_bytes(args[i].num_rays, args[i].rays_per_chunk);
+  return total;
 }
 
 size_t ub_composite_rays_batch_workspace_bytes(const ub_composite_rays_args* args, int32_t num_batches) {
-  size_t total = 0;
   if (args == nullptr) return 16;
-  for (int i = 0; i < num_batches; ++i) total += batch_ws_slice(args[i]);
+  size_t total = batch_heads_bytes(args, num_batches);
+  for (int i = 0; i < num_batches; ++i) total += composite_list_bytes(args[i].num_rays);
   return total > 0 ? total : 16;
 }
 
@@ -807,30 +873,33 @@ int ub_composite_rays_batch(const ub_composite_rays_args* args, int32_t num_batc
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   FinalizeBatch fb{};
   char* ws = static_cast<char*>(workspace);
-  long long max_rays = 0;
+  const size_t heads = batch_heads_bytes(args, num_batches);
+  char* lists = ws + heads;
+  long long full_rays = 0;  // largest batch that finalize must visit ray by ray (generic path)
   int live = 0;
   const ub_composite_rays_args* live_args[UB_MAX_COMPOSITE_BATCH];
   for (int i = 0; i < num_batches; ++i) {
-    const size_t slice = batch_ws_slice(args[i]);
+    const size_t head = composite_head_bytes(args[i].num_rays, args[i].rays_per_chunk);
     CompositeParams p{};
-    int rc = composite_prepare(&args[i], ws, slice, p);
-    ws += slice;
+    int rc = composite_prepare(&args[i], ws, head, lists, p);
+    ws += head;
+    lists += composite_list_bytes(args[i].num_rays);
     if (rc != UB_OK) return rc;
     if (args[i].num_rays == 0) continue;
     fb.p[live] = p;
     live_args[live] = &args[i];
     ++live;
-    if (args[i].num_rays > max_rays) max_rays = args[i].num_rays;
+    if (!p.cand_count && args[i].num_rays > full_rays) full_rays = args[i].num_rays;
   }
   if (live == 0) return UB_OK;
-  // one memset, the compositing kernels back to back, one finalize launch for all batches
-  if (cudaMemsetAsync(workspace, 0, need, stream) != cudaSuccess) return check_launch("composite_rays_batch memset");
+  // one memset (heads only), the compositing kernels back to back, one finalize launch for all batches
+  if (cudaMemsetAsync(workspace, 0, heads, stream) != cudaSuccess) return check_launch("composite_rays_batch memset");
   for (int i = 0; i < live; ++i) {
     int rc = composite_launch_main(live_args[i], fb.p[i], stream);
     if (rc != UB_OK) return rc;
   }
-  dim3 grid((unsigned)((max_rays + 255) / 256), (unsigned)live);
-  composite_finalize_batch<<<grid, 256, 0, stream>>>(fb);
+  const unsigned gx = full_rays > 0 ? (unsigned)min((long long)65535, (long long)((full_rays + 255) / 256)) : kCandidateBlocks;
+  composite_finalize_batch<<<dim3(gx, (unsigned)live), 256, 0, stream>>>(fb);
   return check_launch("composite_finalize_batch");
 }
 
@@ -869,7 +938,7 @@ int ub_render_weights(const ub_render_weights_args* a, void* workspace, size_t w
   int rc = check_launch("render_weights");
   if (rc != UB_OK) return rc;
   if (a->out_expected_depth) {
-    const unsigned fblocks = (unsigned)((a->num_rays + 255) / 256);
+    const unsigned fblocks = (unsigned)min((long long)65535, (long long)((a->num_rays + 255) / 256));
     composite_finalize<<<fblocks, 256, 0, stream>>>(p);
     rc = check_launch("render_weights finalize");
   }
