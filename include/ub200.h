@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define UB_ABI_VERSION 1
+#define UB_ABI_VERSION 2
 
 typedef enum ub_status {
   UB_OK = 0,
@@ -96,10 +96,10 @@ typedef struct ub_composite_rays_args {
 } ub_composite_rays_args;
 
 /* Workspace = [per-chunk table, 16 B per chunk: clip bounds of the expected depth, beta-NaN flag]
- *             [candidate counter, 16 B] [candidate list, 8 B per ray].
- * The compositing kernel lists the rays that the chunk-wide values can change (expected depth outside the ray's own
+ *             [candidate flags, 8 B per 8-ray tile].
+ * The compositing kernel flags the rays that the chunk-wide values can change (expected depth outside the ray's own
  * step range; non-finite sum w^2 beta) and the finalize launch visits only those.  A workspace that holds just the
- * chunk table (+16 B) is accepted too: finalize then visits every ray.  The chunk table is what
+ * chunk table is accepted too: finalize then visits every ray.  The chunk table is what
  * ub_composite_rays_backward reads as `chunk_workspace`. */
 size_t ub_composite_rays_workspace_bytes(int64_t num_rays, int64_t rays_per_chunk);
 int ub_composite_rays(const ub_composite_rays_args* args, void* workspace, size_t workspace_bytes,
@@ -253,6 +253,9 @@ typedef struct ub_score_prologue_args {
   float* out_var;
   double* out_sums;
   int64_t* out_hist;
+  uint32_t* out_coarse_hist;      /* optional DEVICE [3, num_segments, 4096]: histograms of the top 12 bits of the     *
+                                   * order-preserving keys of out_var / out_abs_err / out_sq_err (in this order), the   *
+                                   * `coarse_hist` input of ub_cut_select_sums_ex; needs the three vectors; NULL: skip   */
 } ub_score_prologue_args;
 
 /* max_segment_len: length of the longest segment (workspace scales with it, not with the total). */
@@ -308,6 +311,15 @@ int ub_cut_select_sums(const float* const* keys_host, const float* const* pay0_h
                        const int64_t* seg_offsets, int64_t total, int64_t max_segment_len, const int64_t* cuts,
                        int32_t num_cuts, double* out_sums, void* workspace, size_t workspace_bytes,
                        void* stream);
+/* Same, with the coarse key histograms supplied by the caller: coarse_hist DEVICE [num_families, num_views, 4096]
+ * uint32, entry [f][v][b] = number of keys of family f in segment v whose order-preserving key (float32 bits made
+ * monotone: -0.0 == +0.0, NaN last) has top 12 bits b -- what ub_score_prologue writes to out_coarse_hist for the
+ * families (var, abs err, sq err).  Saves the first pass over the keys.  NULL: computed here. */
+int ub_cut_select_sums_ex(const float* const* keys_host, const float* const* pay0_host,
+                          const float* const* pay1_host, int32_t num_families, int32_t num_views,
+                          const int64_t* seg_offsets, int64_t total, int64_t max_segment_len, const int64_t* cuts,
+                          int32_t num_cuts, const uint32_t* coarse_hist, double* out_sums, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (A3) Last-layer diagonal-Laplace MC moments.

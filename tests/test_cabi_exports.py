@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built_library):
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} declared in ub200.h but not exported"
     assert sorted(_lib.SIGNATURES.keys()) == declared_symbols(), "ctypes table out of sync with the header"
-    assert _lib.load().ub_abi_version() == 1
+    assert _lib.load().ub_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(built_library, tmp_path):
@@ -64,8 +64,8 @@ def test_argument_validation_returns_codes_without_a_device(built_library):
     assert lib.ub_laplace_ll_moments(None, 10, 32, 3, None, 100, 1, None, None, None, None) == -2
     assert b"hidden must be 64" in lib.ub_last_error()
     assert lib.ub_segmented_sort(None, 1, None, 0, 0, None, None, None, 0, None) == -1  # no segment table
-    # chunk table (32 chunks x 16 B) + candidate counter (16 B) + candidate list (2 entries of 4 B per ray)
-    assert lib.ub_composite_rays_workspace_bytes(1 << 20, 1 << 15) == 32 * 16 + 16 + 2 * 4 * (1 << 20)
+    # chunk table (32 chunks x 16 B) + candidate flags (8 B per 8-ray tile)
+    assert lib.ub_composite_rays_workspace_bytes(1 << 20, 1 << 15) == 32 * 16 + 8 * (1 << 17)
     assert lib.ub_render_weights_workspace_bytes(1 << 20, 1 << 15) == 32 * 16
     with pytest.raises(_lib.UBError):
         _lib.check(-3)

@@ -12,6 +12,7 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libub200.so"
 
 UB_OK = 0
+ABI_VERSION = 2
 STATUS_NAMES = {0: "UB_OK", -1: "UB_ERR_BAD_ARG", -2: "UB_ERR_UNSUPPORTED", -3: "UB_ERR_WORKSPACE", -4: "UB_ERR_LAUNCH"}
 
 UB_BG_LAST_SAMPLE, UB_BG_NONE, UB_BG_FIXED = 0, 1, 2
@@ -74,6 +75,7 @@ class ScorePrologueArgs(C.Structure):
         ("nll_min_std", C.c_float), ("sigma_from_var", C.c_int32),
         ("z_values", fp), ("num_z", C.c_int32),
         ("out_sq_err", fp), ("out_abs_err", fp), ("out_var", fp), ("out_sums", fp), ("out_hist", fp),
+        ("out_coarse_hist", fp),
     ]
 
 
@@ -102,6 +104,8 @@ SIGNATURES = {
     "ub_cut_select_sums_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32]),
     "ub_cut_select_sums": (C.c_int, [C.POINTER(fp), C.POINTER(fp), C.POINTER(fp), C.c_int32, C.c_int32, fp,
                                      C.c_int64, C.c_int64, fp, C.c_int32, fp, fp, C.c_size_t, fp]),
+    "ub_cut_select_sums_ex": (C.c_int, [C.POINTER(fp), C.POINTER(fp), C.POINTER(fp), C.c_int32, C.c_int32, fp,
+                                        C.c_int64, C.c_int64, fp, C.c_int32, fp, fp, fp, C.c_size_t, fp]),
     "ub_laplace_ll_moments": (C.c_int, [fp, C.c_int64, C.c_int32, C.c_int32, fp, C.c_int32, C.c_int32,
                                         fp, fp, fp, fp]),
     "ub_depth_prepare_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
@@ -154,8 +158,8 @@ def load() -> C.CDLL:
         fn.restype = restype
         fn.argtypes = argtypes
     got = lib.ub_abi_version()
-    if got != 1:
-        raise ImportError(f"libub200.so ABI version {got} != 1 expected by this package; rebuild")
+    if got != ABI_VERSION:
+        raise ImportError(f"libub200.so ABI version {got} != {ABI_VERSION} expected by this package; rebuild")
     _lib = lib
     return lib
 

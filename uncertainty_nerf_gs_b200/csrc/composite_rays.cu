@@ -25,9 +25,9 @@
 // Chunk-wide reductions of the reference (clip bounds of expected depth = min/max of steps over
 // the eval chunk; the `isnan(beta).any()` guard) are accumulated per chunk in the workspace and
 // applied by a small finalize kernel.  That kernel does not re-read every ray: the compositing kernel
-// appends the few rays the chunk-wide values can possibly change to a candidate list (expected depth
-// outside the ray's own step range: empty / near-empty rays; non-finite sum w^2 beta), and finalize only
-// visits those (a few microseconds and ~1 % of the rays instead of a 12 B/ray pass over the outputs).
+// flags, per 8-ray tile, the few rays the chunk-wide values can possibly change (expected depth outside
+// the ray's own step range: empty / near-empty rays; non-finite sum w^2 beta), and finalize reads one
+// 8-byte word per tile and only visits flagged rays (1 B/ray instead of a 12 B/ray pass over the outputs).
 #include <stdlib.h>
 
 #include "ub_common.cuh"
@@ -60,13 +60,12 @@ struct CompositeParams {
   float* o_dstd;
   float* o_w;
   unsigned* chunk_ws;  // [num_chunks][4]: max key(steps), max ~key(steps), beta-has-NaN, pad
-  // Candidate list of the finalize pass (fast path): rays whose expected depth lies outside the [min, max] of their
-  // OWN steps -- a superset of the rays the chunk-wide clip can change, since the chunk's bounds enclose the ray's --
-  // and rays whose sum w^2 beta came out non-finite (the only ones the NaN-guard redo can change).  NULL: finalize
-  // visits every ray.
-  unsigned* cand_count;
-  unsigned* cand_list;
-  unsigned cand_cap;
+  // Candidate flags of the finalize pass (fast path), one 64-bit word per 8-ray tile, written unconditionally by the
+  // tile's warp (no atomics, no memset): low half = ballot of the rays whose expected depth lies outside the [min, max]
+  // of their OWN steps -- a superset of the rays the chunk-wide clip can change, since the chunk's bounds enclose the
+  // ray's --, high half = ballot of the rays whose sum w^2 beta came out non-finite (the only ones the NaN-guard redo
+  // can change).  NULL: finalize visits every ray.
+  unsigned long long* cand_flags;
 };
 
 constexpr int kLanesPerRay = 4;
@@ -400,6 +399,16 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
       cb = clamp01_keep_nan(cb);
     }
 
+    // ---- candidates of the finalize pass: the chunk-wide clip can only change an expected depth that lies outside
+    // the ray's own [min, max] of steps; the NaN-guard redo only touches non-finite sums ----
+    const float e_exp = e_num / (acc + 1e-10f);
+    if (p.cand_flags) {
+      const unsigned clip_m = __ballot_sync(FULL_MASK, active && q == 0 && e_exp == e_exp && !(e_exp >= rmin && e_exp <= rmax));
+      const unsigned var_m = __ballot_sync(FULL_MASK, active && q == 0 && has_beta && p.beta_mode == UB_BETA_NAN_GUARD &&
+                                                          non_finite(var));
+      if (lane == 0) p.cand_flags[tile] = ((unsigned long long)var_m << 32) | clip_m;   // bit 4 r <-> ray r of the tile
+    }
+
     // ---- outputs: the 4 lanes of a ray split the stores ----
     if (active) {
       if (q == 0) {
@@ -411,22 +420,10 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
       } else if (q == 1) {
         if (p.o_acc) p.o_acc[ray] = acc;
         if (p.o_depth) p.o_depth[ray] = depth;
-        if (p.o_exp) {
-          const float e = e_num / (acc + 1e-10f);
-          p.o_exp[ray] = e;
-          // the chunk-wide clip can only change e if it lies outside the ray's own [min, max] of steps
-          if (p.cand_count && e == e && !(e >= rmin && e <= rmax)) {
-            const unsigned slot = atomicAdd(p.cand_count, 1u);
-            if (slot < p.cand_cap) p.cand_list[slot] = (unsigned)ray;
-          }
-        }
+        if (p.o_exp) p.o_exp[ray] = e_exp;
       } else if (q == 2) {
         if (p.o_rgb_var) p.o_rgb_var[ray] = var;
         if (p.o_rgb_std) p.o_rgb_std[ray] = sqrtf(var);
-        if (p.cand_count && has_beta && p.beta_mode == UB_BETA_NAN_GUARD && non_finite(var)) {
-          const unsigned slot = atomicAdd(p.cand_count, 1u);  // the NaN-guard redo only touches non-finite sums
-          if (slot < p.cand_cap) p.cand_list[slot] = (unsigned)ray;
-        }
       } else {
         if (p.o_dvar) p.o_dvar[ray] = dvar;
         if (p.o_dstd) p.o_dstd[ray] = sqrtf(dvar);
@@ -649,13 +646,21 @@ __device__ __forceinline__ void finalize_ray(const CompositeParams& p, long long
   }
 }
 
-// visits the candidate list when the batch has one (grid-stride), else every ray
+// visits the flagged rays when the batch has candidate flags (one thread per tile, grid-stride), else every ray
 __device__ __forceinline__ void finalize_batch_rays(const CompositeParams& p) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p.cand_count) {
-    const long long n = min((long long)*p.cand_count, (long long)p.cand_cap);
-    for (long long i = t; i < n; i += stride) finalize_ray(p, (long long)p.cand_list[i]);
+  if (p.cand_flags) {
+    const long long tiles = (p.num_rays + kRaysPerTile - 1) / kRaysPerTile;
+    for (long long tile = t; tile < tiles; tile += stride) {
+      const unsigned long long f = p.cand_flags[tile];
+      unsigned m = (unsigned)f | (unsigned)(f >> 32);
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        finalize_ray(p, tile * kRaysPerTile + (bit >> 2));
+      }
+    }
   } else {
     for (long long ray = t; ray < p.num_rays; ray += stride) finalize_ray(p, ray);
   }
@@ -671,7 +676,6 @@ __global__ void __launch_bounds__(256) composite_finalize_batch(const __grid_con
   finalize_batch_rays(b.p[blockIdx.y]);
 }
 
-constexpr unsigned kCandidateBlocks = 32;  // finalize grid when every batch has a candidate list
 
 static size_t chunk_ws_bytes(long long num_rays, long long rays_per_chunk) {
   long long chunks = 1;
@@ -710,11 +714,13 @@ static bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr
 
 extern "C" {
 
-// workspace of one ray batch: [chunk table | candidate counter (16 B) | candidate list, 2 entries per ray]
+// workspace of one ray batch: [chunk table (zeroed by the call) | candidate flags, 8 B per 8-ray tile]
 static size_t composite_head_bytes(int64_t num_rays, int64_t rays_per_chunk) {
-  return ub::align_up(ub::chunk_ws_bytes(num_rays, rays_per_chunk), 16) + 16;
+  return ub::align_up(ub::chunk_ws_bytes(num_rays, rays_per_chunk), 16);
 }
-static size_t composite_list_bytes(int64_t num_rays) { return ub::align_up((size_t)(num_rays > 0 ? num_rays : 0) * 2 * 4, 16); }
+static size_t composite_list_bytes(int64_t num_rays) {
+  return (size_t)((num_rays > 0 ? num_rays : 0) + ub::kRaysPerTile - 1) / ub::kRaysPerTile * 8;
+}
 
 size_t ub_composite_rays_workspace_bytes(int64_t num_rays, int64_t rays_per_chunk) {
   return composite_head_bytes(num_rays, rays_per_chunk) + composite_list_bytes(num_rays);
@@ -782,11 +788,8 @@ static int composite_prepare(const ub_composite_rays_args* a, void* workspace, s
   p.o_w = a->out_weights;
   p.chunk_ws = static_cast<unsigned*>(workspace);
   p.tiles_per_chunk = a->rays_per_chunk > 0 ? (int)(a->rays_per_chunk / kRaysPerTile) : 0;
-  if (cand_list != nullptr && composite_fast_path(a)) {  // the generic kernel keeps the visit-every-ray finalize
-    p.cand_count = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + need - 16);
-    p.cand_list = static_cast<unsigned*>(cand_list);
-    p.cand_cap = (unsigned)(2 * a->num_rays);
-  }
+  if (cand_list != nullptr && composite_fast_path(a))  // the generic kernel keeps the visit-every-ray finalize
+    p.cand_flags = static_cast<unsigned long long*>(cand_list);
   return UB_OK;
 }
 
@@ -841,7 +844,8 @@ int ub_composite_rays(const ub_composite_rays_args* a, void* workspace, size_t w
   if (cudaMemsetAsync(workspace, 0, head, stream) != cudaSuccess) return check_launch("composite_rays memset");
   rc = composite_launch_main(a, p, stream);
   if (rc != UB_OK) return rc;
-  const unsigned fblocks = p.cand_count ? kCandidateBlocks : (unsigned)min((long long)65535, (long long)((a->num_rays + 255) / 256));
+  const long long fwork = p.cand_flags ? (a->num_rays + kRaysPerTile - 1) / kRaysPerTile : a->num_rays;
+  const unsigned fblocks = (unsigned)min((long long)65535, (long long)((fwork + 255) / 256));
   composite_finalize<<<fblocks, 256, 0, stream>>>(p);
   return check_launch("composite_finalize");
 }
@@ -875,7 +879,7 @@ int ub_composite_rays_batch(const ub_composite_rays_args* args, int32_t num_batc
   char* ws = static_cast<char*>(workspace);
   const size_t heads = batch_heads_bytes(args, num_batches);
   char* lists = ws + heads;
-  long long full_rays = 0;  // largest batch that finalize must visit ray by ray (generic path)
+  long long full_rays = 0;  // finalize work items of the largest batch: tiles (candidate flags) or rays (generic path)
   int live = 0;
   const ub_composite_rays_args* live_args[UB_MAX_COMPOSITE_BATCH];
   for (int i = 0; i < num_batches; ++i) {
@@ -889,7 +893,8 @@ int ub_composite_rays_batch(const ub_composite_rays_args* args, int32_t num_batc
     fb.p[live] = p;
     live_args[live] = &args[i];
     ++live;
-    if (!p.cand_count && args[i].num_rays > full_rays) full_rays = args[i].num_rays;
+    const long long work = p.cand_flags ? (args[i].num_rays + kRaysPerTile - 1) / kRaysPerTile : args[i].num_rays;
+    if (work > full_rays) full_rays = work;
   }
   if (live == 0) return UB_OK;
   // one memset (heads only), the compositing kernels back to back, one finalize launch for all batches
@@ -898,7 +903,7 @@ int ub_composite_rays_batch(const ub_composite_rays_args* args, int32_t num_batc
     int rc = composite_launch_main(live_args[i], fb.p[i], stream);
     if (rc != UB_OK) return rc;
   }
-  const unsigned gx = full_rays > 0 ? (unsigned)min((long long)65535, (long long)((full_rays + 255) / 256)) : kCandidateBlocks;
+  const unsigned gx = (unsigned)min((long long)65535, (long long)((full_rays + 255) / 256));
   composite_finalize_batch<<<dim3(gx, (unsigned)live), 256, 0, stream>>>(fb);
   return check_launch("composite_finalize_batch");
 }

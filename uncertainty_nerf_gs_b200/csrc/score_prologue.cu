@@ -20,8 +20,15 @@
 //   2. A bin with exactly one threshold k in the band: c = k + [exact float64 predicate for z_k].
 //   3. Anything else (NaN / negative ratio, tiny sigma, several thresholds per bin): the float32
 //      binary search + float64 verification + exact float64 binary search of coverage_count().
-// The counts are therefore bit-exact whatever the estimate does.
+// The counts are therefore bit-exact whatever the estimate does.  Tier 2 is evaluated inline for the whole warp
+// whenever any lane needs it (a call per lane ran with one thread active and cost a quarter of the kernel's
+// instructions: profiles/r1_select_ncu_summary.txt -> r2).
 // Sums are accumulated in float64 per block and combined in a fixed order (deterministic).
+// NLL: d^2 / (2 s^2) and log s use the fast division / logarithm (relative error ~1e-7 per element, far inside the
+// 1e-5 contract of the mean); everything that feeds an integer result (the coverage counts) stays exact.
+// Optionally the kernel also counts, per segment, the top 12 bits of the order-preserving keys of the three vectors
+// it writes (var, abs err, sq err): the coarse histograms ub_cut_select_sums would otherwise rebuild with a pass of
+// its own over the vectors it has just been handed (-12 B/pixel, -1 launch).
 #include "ub_common.cuh"
 
 namespace ub {
@@ -32,7 +39,7 @@ constexpr int kPixPerChunk = kPrologueThreads * kPixPerThread;
 constexpr int kChunksPerBlock = 4;  // amortises the table build
 constexpr int kPixPerBlock = kPixPerChunk * kChunksPerBlock;
 constexpr int kMaxZ = 127;
-constexpr int kLutBins = 8192;            // uniform bins of r over [0, 1.001 z_0)
+constexpr int kLutBins = 16384;           // uniform bins of r over [0, 1.001 z_0)
 constexpr float kLutGuard = 1e-5f;        // relative guard band around every bin (float32 estimate error)
 constexpr double kLutGuardAbs = 1e-9;     // absolute guard band (float64 rounding of m -+ z sigma)
 constexpr float kSigmaGuard = 1e6f;       // tiers 1/2 need sigma >= 1e-6 |m|: 2^-52 (|m|/sigma + z) << 1e-9
@@ -58,7 +65,11 @@ struct PrologueParams {
   unsigned long long* hist;  // [num_segments][num_z + 1]
   const unsigned char* lut;  // [kLutBins + 16] ratio table (workspace)
   int vec_ok;
+  unsigned* coarse;          // [3][num_segments][kCoarseBins] or NULL: top-12-bit key histograms of var / ae / se
 };
+
+constexpr int kCoarseBins = 4096;
+constexpr int kCoarseShift = 20;
 
 __device__ __forceinline__ bool interval_holds(double z, float m, float s, float t) {
   const double zs = __dmul_rn(z, (double)s);
@@ -123,53 +134,45 @@ __global__ void __launch_bounds__(256) prologue_lut_kernel(const double* __restr
                        : (inside == 1 ? (unsigned char)(kLutOneThreshold + above) : (unsigned char)kLutGeneric);
 }
 
-// tiers 2 and 3 (rare): one exact check, or the fully general search
-__device__ __noinline__ int coverage_count_slow(unsigned e, const double* __restrict__ zs_d,
-                                                const float* __restrict__ zs_f, int nz, float m, float s,
-                                                float t) {
-  if (e != kLutGeneric) {
-    const int k = (int)(e - kLutOneThreshold);
-    return k + (interval_holds(zs_d[k], m, s, t) ? 1 : 0);
-  }
-  return coverage_count(zs_d, zs_f, nz, m, s, t);
-}
-
-template <int C>
+template <int C, bool COARSE>
 __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const PrologueParams p) {
   __shared__ double z_d[kMaxZ + 1];
   __shared__ float z_f[kMaxZ + 1];
   __shared__ unsigned int hist_s[kPrologueThreads / 32][kMaxZ + 1];
   __shared__ double red[kPrologueThreads / 32][UB_PROLOGUE_NSUMS];
   __shared__ __align__(16) unsigned char lut[kLutBins + 16];
+  // coarse key histograms of the block, two 16-bit counters per word (a block holds 4096 pixels < 2^16)
+  __shared__ unsigned int coarse_s[COARSE ? 3 : 1][COARSE ? kCoarseBins / 2 : 1];
 
   const int seg = blockIdx.y;
   const long long seg_lo = p.seg_offsets[seg], seg_hi = p.seg_offsets[seg + 1];
   const long long blk_lo = seg_lo + (long long)blockIdx.x * kPixPerBlock;
+  if (blk_lo >= seg_hi && blockIdx.x > 0) return;  // ragged batches: nothing in this block (block 0 writes the zero partials)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nz = p.num_z;
 
-  for (int i = threadIdx.x; i < nz; i += blockDim.x) {
-    z_d[i] = p.z[i];
-    z_f[i] = (float)p.z[i];
+  for (int i = threadIdx.x; i <= kMaxZ; i += blockDim.x) {
+    z_d[i] = i < nz ? p.z[i] : 0.0;
+    z_f[i] = i < nz ? (float)p.z[i] : 0.f;
   }
   for (int i = threadIdx.x; i < (kPrologueThreads / 32) * (kMaxZ + 1); i += blockDim.x)
     (&hist_s[0][0])[i] = 0u;
-  __syncthreads();
-
-  const float inv_w = (float)((double)kLutBins / fmax(z_d[0] * 1.001, 1e-30));
+  if (COARSE)
+    for (int i = threadIdx.x; i < 3 * (kCoarseBins / 2); i += blockDim.x) (&coarse_s[0][0])[i] = 0u;
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.lut);
     uint4* dst = reinterpret_cast<uint4*>(lut);
     for (int i = threadIdx.x; i < (kLutBins + 16) / 16; i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
+  const float inv_w = (float)((double)kLutBins / fmax(z_d[0] * 1.001, 1e-30));
 
   double sums[UB_PROLOGUE_NSUMS] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
   for (int chunk = 0; chunk < kChunksPerBlock; ++chunk) {
     const long long pix0 = blk_lo + (long long)chunk * kPixPerChunk + (long long)threadIdx.x * kPixPerThread;
     const int npix = (int)max(0LL, min((long long)kPixPerThread, seg_hi - pix0));
-    if (npix <= 0) continue;
+    if (__syncthreads_count(npix > 0) == 0) break;  // the whole block is past the segment's end
     float pr[kPixPerThread * C], tg[kPixPerThread * C], sd[kPixPerThread];
     const bool vec = p.vec_ok && npix == kPixPerThread && (pix0 & 3) == 0;  // 16-byte aligned rows
     if (vec) {
@@ -193,20 +196,21 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
 #pragma unroll
       for (int i = 0; i < kPixPerThread; ++i) sd[i] = i < npix ? p.std[pix0 + i] : 1.f;
     }
+    // every lane runs every pixel slot (dummy data past the end), so the warp votes below are convergent
     float se[kPixPerThread], ae[kPixPerThread], vr[kPixPerThread];
 #pragma unroll
     for (int px = 0; px < kPixPerThread; ++px) {
+      const bool valid = px < npix;
       const float sdv = sd[px];
       const float var = __fmul_rn(sdv, sdv);
       const float sigma = p.sigma_from_var ? sqrtf(var) : sdv;
       const float nll_s = fmaxf(sdv, p.nll_min_std);  // torch.maximum propagates NaN:
       const float s_nll = sdv != sdv ? sdv : nll_s;
-      const float two_var = 2.0f * __fmul_rn(s_nll, s_nll);
-      const float log_s = logf(s_nll);
+      const float inv_two_var = __fdividef(0.5f, __fmul_rn(s_nll, s_nll));
+      const float log_s = __logf(s_nll) + 0.91893853320467274178f;
       const float inv_sigma = __fdividef(1.0f, sigma);
       const float sigma_guard = (sigma > 1e-30f && sigma < 1e30f) ? sigma * kSigmaGuard : -1.f;
-      float se_px = 0.f, ae_px = 0.f;
-      double nll_px = 0.0;
+      float se_px = 0.f, ae_px = 0.f, nll_px = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const float m = pr[px * C + c], t = tg[px * C + c];
@@ -214,28 +218,41 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
         const float d2 = __fmul_rn(d, d);
         se_px = c == 0 ? d2 : __fadd_rn(se_px, d2);
         ae_px = c == 0 ? fabsf(d) : __fadd_rn(ae_px, fabsf(d));
-        if (px < npix) {
-          const float nll = __fadd_rn(__fadd_rn(__fdiv_rn(d2, two_var), log_s), 0.91893853320467274178f);
-          nll_px += (double)nll;
-          // coverage count, tiers 1-3
-          const float r = fabsf(d) * inv_sigma;
-          const unsigned bin = min((unsigned)__float2int_rz(r * inv_w), (unsigned)kLutBins);
-          const unsigned looked_up = lut[bin];
-          const unsigned e = (r >= 0.f && sigma_guard >= fabsf(m)) ? looked_up : kLutGeneric;
-          int cnt = (int)e;
-          if (e >= kLutOneThreshold) cnt = coverage_count_slow(e, z_d, z_f, nz, m, sigma, t);
-          atomicAdd(&hist_s[warp][cnt], 1u);
+        nll_px += fmaf(d2, inv_two_var, log_s);
+        // coverage count, tiers 1-3
+        const float r = fabsf(d) * inv_sigma;
+        const unsigned bin = min((unsigned)__float2int_rz(r * inv_w), (unsigned)kLutBins);
+        const unsigned looked_up = lut[bin];
+        const unsigned e = (r >= 0.f && sigma_guard >= fabsf(m)) ? looked_up : kLutGeneric;
+        int cnt = (int)e;
+        if (__any_sync(FULL_MASK, valid && e >= kLutOneThreshold)) {  // warp-uniform
+          // tier 2 for the whole warp, branch-free: one exact float64 predicate at threshold k
+          const int k = (int)(e & 127u);
+          const bool holds = interval_holds(z_d[k], m, sigma, t);
+          if (e != kLutGeneric && e >= kLutOneThreshold) cnt = k + (holds ? 1 : 0);
+          if (__any_sync(FULL_MASK, valid && e == kLutGeneric)) {  // tier 3: NaN / negative ratios, tiny sigma
+            if (valid && e == kLutGeneric) cnt = coverage_count(z_d, z_f, nz, m, sigma, t);
+          }
         }
+        if (valid) atomicAdd(&hist_s[warp][cnt], 1u);
       }
       se[px] = se_px;
       ae[px] = ae_px;
       vr[px] = var;
-      if (px < npix) {
+      if (valid) {
         sums[0] += (double)se_px;
         sums[1] += (double)ae_px;
         sums[2] += (double)var;
-        sums[3] += nll_px;
+        sums[3] += (double)nll_px;
         sums[4] += (double)sigma;
+        if (COARSE) {
+          const unsigned kv = sort_key_from_float(var) >> kCoarseShift;
+          const unsigned ka = sort_key_from_float(ae_px) >> kCoarseShift;
+          const unsigned ks = sort_key_from_float(se_px) >> kCoarseShift;
+          atomicAdd(&coarse_s[0][kv >> 1], 1u << (16 * (kv & 1u)));
+          atomicAdd(&coarse_s[1][ka >> 1], 1u << (16 * (ka & 1u)));
+          atomicAdd(&coarse_s[2][ks >> 1], 1u << (16 * (ks & 1u)));
+        }
       }
     }
     if (vec) {
@@ -271,6 +288,17 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
     unsigned int v = 0;
     for (int w = 0; w < kPrologueThreads / 32; ++w) v += hist_s[w][c];
     if (v) atomicAdd(&p.hist[(size_t)seg * (nz + 1) + c], (unsigned long long)v);
+  }
+  if (COARSE) {
+    for (int i = threadIdx.x; i < 3 * (kCoarseBins / 2); i += blockDim.x) {
+      const unsigned v = (&coarse_s[0][0])[i];
+      if (v) {
+        const int f = i / (kCoarseBins / 2), w2 = i - f * (kCoarseBins / 2);
+        unsigned* g = p.coarse + ((size_t)f * p.num_segments + seg) * kCoarseBins + 2 * w2;
+        if (v & 0xFFFFu) atomicAdd(g, v & 0xFFFFu);
+        if (v >> 16) atomicAdd(g + 1, v >> 16);
+      }
+    }
   }
 }
 
@@ -336,6 +364,17 @@ int ub_score_prologue(const ub_score_prologue_args* a, void* workspace, size_t w
   if (cudaMemsetAsync(a->out_hist, 0, (size_t)a->num_segments * (a->num_z + 1) * sizeof(int64_t),
                       stream) != cudaSuccess)
     return check_launch("score_prologue hist memset");
+  if (a->out_coarse_hist) {
+    UB_REQUIRE(a->out_sq_err && a->out_abs_err && a->out_var, UB_ERR_BAD_ARG,
+               "score_prologue: out_coarse_hist needs the three output vectors");
+    if (cudaMemsetAsync(a->out_coarse_hist, 0, (size_t)3 * a->num_segments * kCoarseBins * sizeof(uint32_t), stream) !=
+        cudaSuccess)
+      return check_launch("score_prologue coarse memset");
+  }
+  // blocks past the end of a short segment exit early: their partial sums must read as zero
+  if (cudaMemsetAsync(ws + lay.off_partial, 0,
+                      (size_t)a->num_segments * lay.blocks_per_seg * UB_PROLOGUE_NSUMS * sizeof(double), stream) != cudaSuccess)
+    return check_launch("score_prologue partial memset");
 
   PrologueParams p{};
   p.pred = a->pred;
@@ -361,12 +400,16 @@ int ub_score_prologue(const ub_score_prologue_args* a, void* workspace, size_t w
   bool vec_ok = al16(a->pred) && al16(a->target) && al16(a->std) && al16(a->out_sq_err) &&
                 al16(a->out_abs_err) && al16(a->out_var);
   p.vec_ok = vec_ok ? 1 : 0;  // the kernel additionally requires 4-pixel-aligned positions
+  p.coarse = a->out_coarse_hist;
 
   dim3 grid((unsigned)lay.blocks_per_seg, (unsigned)a->num_segments);
-  if (a->channels == 3)
-    score_prologue_kernel<3><<<grid, kPrologueThreads, 0, stream>>>(p);
-  else
-    score_prologue_kernel<1><<<grid, kPrologueThreads, 0, stream>>>(p);
+  if (a->channels == 3) {
+    if (p.coarse) score_prologue_kernel<3, true><<<grid, kPrologueThreads, 0, stream>>>(p);
+    else score_prologue_kernel<3, false><<<grid, kPrologueThreads, 0, stream>>>(p);
+  } else {
+    if (p.coarse) score_prologue_kernel<1, true><<<grid, kPrologueThreads, 0, stream>>>(p);
+    else score_prologue_kernel<1, false><<<grid, kPrologueThreads, 0, stream>>>(p);
+  }
   int rc = check_launch("score_prologue");
   if (rc != UB_OK) return rc;
   prologue_finalize_kernel<<<a->num_segments, 32 * UB_PROLOGUE_NSUMS, 0, stream>>>(p.partial, lay.blocks_per_seg, a->out_sums);

@@ -1158,6 +1158,15 @@ int ub_cut_select_sums(const float* const* keys_host, const float* const* pay0_h
                        const int64_t* seg_offsets, int64_t total, int64_t max_segment_len, const int64_t* cuts,
                        int32_t num_cuts, double* out_sums, void* workspace, size_t workspace_bytes,
                        void* stream_v) {
+  return ub_cut_select_sums_ex(keys_host, pay0_host, pay1_host, num_families, num_views, seg_offsets, total,
+                               max_segment_len, cuts, num_cuts, nullptr, out_sums, workspace, workspace_bytes, stream_v);
+}
+
+int ub_cut_select_sums_ex(const float* const* keys_host, const float* const* pay0_host,
+                          const float* const* pay1_host, int32_t num_families, int32_t num_views,
+                          const int64_t* seg_offsets, int64_t total, int64_t max_segment_len, const int64_t* cuts,
+                          int32_t num_cuts, const uint32_t* coarse_hist, double* out_sums, void* workspace,
+                          size_t workspace_bytes, void* stream_v) {
   using namespace ub;
   UB_REQUIRE(num_families >= 1 && num_families <= kSelMaxFamilies && keys_host && pay0_host, UB_ERR_BAD_ARG,
              "cut_select_sums: num_families must be in [1, %d]", kSelMaxFamilies);
@@ -1232,7 +1241,10 @@ int ub_cut_select_sums(const float* const* keys_host, const float* const* pay0_h
   dim3 grid_chunks(chunks < 1 ? 1 : chunks, (unsigned)G);
   dim3 grid_blocks((unsigned)lay.max_blocks, (unsigned)G);
   dim3 grid_cells((unsigned)num_cuts, (unsigned)G);
-  sel_coarse_hist<<<grid_chunks, kSelThreads, 0, stream>>>(p);
+  if (coarse_hist != nullptr)
+    p.hist_c = const_cast<uint32_t*>(coarse_hist);  // read-only from here on (sel_alloc)
+  else
+    sel_coarse_hist<<<grid_chunks, kSelThreads, 0, stream>>>(p);
   sel_alloc<<<G, kSelThreads, 0, stream>>>(p);
   sel_fine_hist<<<grid_chunks, kSelThreads, 0, stream>>>(p);
   sel_locate<<<G, kSelLocThreads, 0, stream>>>(p);

@@ -153,12 +153,13 @@ def _use_select(max_len: int) -> bool:
     return os.environ.get("UB_AUSE_SORT", "0") != "1" and max_len <= _SELECT_MAX_LEN
 
 
-def _ause_sums(vec: Tensor, lens, cuts: np.ndarray) -> Tensor:
+def _ause_sums(vec: Tensor, lens, cuts: np.ndarray, coarse: Optional[Tensor] = None) -> Tensor:
     """``[B, 4, ncuts]`` float64: payload sums under every cut for (abs err by var, sq err by var, abs err
-    ascending, sq err ascending) from the prologue's ``[3, total]`` buffer (var, abs err, sq err)."""
+    ascending, sq err ascending) from the prologue's ``[3, total]`` buffer (var, abs err, sq err); ``coarse``: the
+    prologue's key histograms of those three vectors, in that order."""
     ae, se = vec[1], vec[2]
     if _use_select(max(lens) if len(lens) else 0):
-        return ops.cut_select_sums([(vec[0], ae, se), (ae, ae, None), (se, se, None)], lens, cuts)
+        return ops.cut_select_sums([(vec[0], ae, se), (ae, ae, None), (se, se, None)], lens, cuts, coarse=coarse)
     total = vec.shape[1]
     sorted_all, perm_all = ops.segmented_sort(vec.reshape(-1), list(lens) * 3, want_perm=True, want_keys=True)
     perm_var = perm_all[:total]
@@ -273,12 +274,14 @@ def _score_rgb_device(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb
     n = h * w
     lens = [n] * b
     z = _z_table(rgb_pred.device)
+    select = _use_select(n)
     pro = ops.score_prologue(rgb_pred.reshape(-1, c), rgb_gt.reshape(-1, c), rgb_std.reshape(-1), lens, z,
-                             nll_min_std=min_rgb_std_for_nll, sigma_from_var=True, want_vectors=True)
+                             nll_min_std=min_rgb_std_for_nll, sigma_from_var=True, want_vectors=True,
+                             want_coarse=select)
     vec = pro["vectors"]                                   # [3, total]: var, abs err, sq err
     cuts_one = ause_cut_counts(n)
     cuts = _tiled_cuts(n, b)
-    sums = _ause_sums(vec, lens, cuts)                                                # [B, 4, 100]
+    sums = _ause_sums(vec, lens, cuts, pro.get("coarse"))                             # [B, 4, 100]
     packed_dev = torch.cat([sums.reshape(b, -1), pro["sums"], pro["hist"].to(torch.float64)], dim=1)
     return packed_dev, b, n, c, cuts_one
 
@@ -413,11 +416,12 @@ def score_depth_batch(depth: Tensor, depth_std: Tensor, depth_gt: Tensor, scales
     pred, gt = pred.reshape(-1, 1), gt.reshape(-1, 1)
     total = pred.shape[0]
     z = _z_table(dev)
+    select = _use_select(max(lens) if len(lens) else 0)
     pro = ops.score_prologue(pred, gt, std, lens, z, nll_min_std=min_depth_std_for_nll, sigma_from_var=False,
-                             want_vectors=True)
+                             want_vectors=True, want_coarse=select)
     vec = pro["vectors"]
     cuts = np.stack([ause_cut_counts(n) for n in lens])
-    sums = _ause_sums(vec, lens, cuts)
+    sums = _ause_sums(vec, lens, cuts, pro.get("coarse"))
     packed = torch.cat([sums.reshape(b, -1), pro["sums"], pro["hist"].to(torch.float64)], dim=1).cpu().numpy()
     zh = z_values_host()
     results = []

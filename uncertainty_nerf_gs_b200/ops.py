@@ -445,10 +445,12 @@ class Segments:
 
 
 def score_prologue(pred: Tensor, target: Tensor, std: Tensor, seg_lengths: Sequence[int], z_values: Tensor,
-                   nll_min_std: float, sigma_from_var: bool = True, want_vectors: bool = True
-                   ) -> Dict[str, Tensor]:
+                   nll_min_std: float, sigma_from_var: bool = True, want_vectors: bool = True,
+                   want_coarse: bool = False) -> Dict[str, Tensor]:
     """se / ae / var vectors, float64 sums and the AUCE interval histogram for a batch of images.
-    ``pred, target [N, C]``, ``std [N]``; images are consecutive segments of ``seg_lengths`` pixels."""
+    ``pred, target [N, C]``, ``std [N]``; images are consecutive segments of ``seg_lengths`` pixels.
+    ``want_coarse``: also ``coarse [3, nseg, 4096]`` uint32 (as int32 storage), the top-12-bit key histograms of the
+    three vectors that ``cut_select_sums(..., coarse=...)`` would otherwise compute with a pass of its own."""
     lib = _lib.load()
     pred = _dev_f32(pred, "pred")
     target = _dev_f32(target, "target")
@@ -482,6 +484,11 @@ def score_prologue(pred: Tensor, target: Tensor, std: Tensor, seg_lengths: Seque
     args.out_sq_err, args.out_abs_err = _ptr(out.get("squared_error")), _ptr(out.get("absolute_error"))
     args.out_var = _ptr(out.get("var"))
     args.out_sums, args.out_hist = out["sums"].data_ptr(), out["hist"].data_ptr()
+    if want_coarse:
+        if not want_vectors:
+            raise ValueError("want_coarse needs want_vectors")
+        out["coarse"] = torch.empty(3, nseg, 4096, dtype=torch.int32, device=dev)
+        args.out_coarse_hist = out["coarse"].data_ptr()
     ws = _workspace(lib.ub_score_prologue_workspace_bytes(nseg, seg.max_len, nz), dev)
     with _guard(dev):
         _lib.check(lib.ub_score_prologue(C.byref(args), ws.data_ptr(), ws.numel(), _stream()))
@@ -545,12 +552,14 @@ def cut_prefix_sums(values: Sequence[Tensor], perms: Union[None, Tensor, Sequenc
 
 
 def cut_select_sums(families: Sequence[Tuple[Tensor, Tensor, Optional[Tensor]]], seg_lengths: Sequence[int],
-                    cuts: np.ndarray) -> Tensor:
+                    cuts: np.ndarray, coarse: Optional[Tensor] = None) -> Tensor:
     """float64 sums of the payloads over the first ``cuts[s, c]`` elements of the stable ascending order of
     the keys, without sorting (``ub_cut_select_sums``): equal to ``segmented_sort`` + ``cut_prefix_sums`` up
     to float64 summation order.  ``families``: ``(keys, payload0, payload1 or None)`` triples of ``[total]``
     float32 tensors sharing the segmentation; ``payload0 is keys`` (same storage) sums the sorted keys.
-    Returns ``[nseg, V, ncuts]`` with one row per payload array in family order."""
+    Returns ``[nseg, V, ncuts]`` with one row per payload array in family order.
+    ``coarse [num_families, nseg, 4096]`` (int32 storage): the top-12-bit key histograms, when the producer of the
+    keys already has them (``score_prologue(want_coarse=True)``)."""
     lib = _lib.load()
     fams = []
     for i, (k, p0, p1) in enumerate(families):
@@ -571,12 +580,16 @@ def cut_select_sums(families: Sequence[Tuple[Tensor, Tensor, Optional[Tensor]]],
     kp = (C.c_void_p * nf)(*[k.data_ptr() for k, _, _ in fams])
     p0p = (C.c_void_p * nf)(*[p0.data_ptr() for _, p0, _ in fams])
     p1p = (C.c_void_p * nf)(*[_ptr(p1) for _, _, p1 in fams])
+    if coarse is not None:
+        if coarse.dtype != torch.int32 or not coarse.is_cuda or tuple(coarse.shape) != (nf, nseg, 4096):
+            raise ValueError(f"coarse must be a CUDA int32 tensor of shape {(nf, nseg, 4096)}")
+        coarse = coarse.contiguous()
     ws = _workspace(lib.ub_cut_select_sums_workspace_bytes(nf, nseg, total, seg.max_len, ncuts), dev)
     with _guard(dev):
-        _lib.check(lib.ub_cut_select_sums(kp, p0p, p1p, nf, nseg, seg.offsets.data_ptr(), total, seg.max_len,
-                                          cuts_dev.data_ptr(), ncuts, out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                          _stream()))
-    _count(9)
+        _lib.check(lib.ub_cut_select_sums_ex(kp, p0p, p1p, nf, nseg, seg.offsets.data_ptr(), total, seg.max_len,
+                                             cuts_dev.data_ptr(), ncuts, _ptr(coarse), out.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), _stream()))
+    _count(9 if coarse is None else 8)
     return out
 
 
