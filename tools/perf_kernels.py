@@ -90,18 +90,23 @@ def score():
         var = (std ** 2).reshape(-1)
         ts = timeit(lambda i: ops.segmented_sort(var, [n] * b, want_perm=True, want_keys=False))
         tk = timeit(lambda i: ops.segmented_sort(var, [n] * b, want_perm=False, want_keys=True))
-        vec = ops.score_prologue(pred.reshape(-1, 3), gt.reshape(-1, 3), std.reshape(-1), [n] * b, z, 0.03)["vectors"]
+        pro = ops.score_prologue(pred.reshape(-1, 3), gt.reshape(-1, 3), std.reshape(-1), [n] * b, z, 0.03, want_coarse=True)
+        vec = pro["vectors"]
+        tpc = timeit(lambda i: ops.score_prologue(pred.reshape(-1, 3), gt.reshape(-1, 3), std.reshape(-1), [n] * b, z, 0.03,
+                                                  want_coarse=True))
         cuts = np.tile(metrics.ause_cut_counts(n)[None, :], (b, 1))
         prev = os.environ.get("UB_AUSE_SORT")
         os.environ["UB_AUSE_SORT"] = "0"
         t_sel = timeit(lambda i: metrics._ause_sums(vec, [n] * b, cuts))
+        t_sel_c = timeit(lambda i: metrics._ause_sums(vec, [n] * b, cuts, pro["coarse"]))
         os.environ["UB_AUSE_SORT"] = "1"
         t_srt = timeit(lambda i: metrics._ause_sums(vec, [n] * b, cuts))
         if prev is None:
             os.environ.pop("UB_AUSE_SORT")
         else:
             os.environ["UB_AUSE_SORT"] = prev
-        print(json.dumps({"kernel": f"ause cut sums {w}x{h} x{b}", "ms_select": t_sel, "ms_sort_and_cut_sums": t_srt,
+        print(json.dumps({"kernel": f"ause cut sums {w}x{h} x{b}", "ms_select": t_sel, "ms_select_given_coarse_hist": t_sel_c,
+                          "ms_prologue_with_coarse_hist": tpc, "ms_sort_and_cut_sums": t_srt,
                           "Mkeys_s_select": 3 * n * b / t_sel / 1e3}))
         print(json.dumps({"kernel": f"score {w}x{h} x{b}", "ms_total": ms, "images_s": b / ms * 1e3, "ms_streamed": ms_stream, "images_s_streamed": b / ms_stream * 1e3, "ms_prologue": tp,
                           "prologue_GBs": 40 * n * b / tp / 1e6, "ms_sort_pairs": ts, "ms_sort_keys": tk,

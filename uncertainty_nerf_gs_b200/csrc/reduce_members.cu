@@ -33,24 +33,6 @@ struct ReduceBatch {
   int num_members;
 };
 
-// KMAX > 0: all members (K <= KMAX) are loaded before the first use -- up to KMAX * 48 bytes in flight per thread,
-// which is what hides the DRAM latency at the 2 CTAs / SM the float64 arithmetic allows -- and the two float64
-// sums of an element live only while that element is reduced.  KMAX == 0: any K, one member at a time.
-// The order of the float64 additions (members ascending) is the same in both, so the results are identical.
-// (float)sqrt(v) for a float64 v without the ~35-instruction DSQRT: float32 rsqrt estimate, one float64 Newton step
-// (relative error ~1e-14, far below the float32 rounding of the result); zero, subnormal-as-float, huge and NaN
-// arguments take the library sqrt.
-__device__ __forceinline__ float sqrt_to_float(double v) {
-  const float vf = (float)v;
-  if (vf > 1e-30f && vf < 1e30f) {
-    const double y = (double)rsqrtf(vf);
-    double s = v * y;
-    s = fma(0.5 * y, fma(-s, s, v), s);
-    return (float)s;
-  }
-  return (float)sqrt(v);
-}
-
 template <int C, int KMAX>
 __device__ __forceinline__ void reduce_pixels(const float* const* member, int K, const ReduceJob& jb,
                                               long long pix0, int npix, bool vec) {
@@ -73,50 +55,52 @@ __device__ __forceinline__ void reduce_pixels(const float* const* member, int K,
       for (int i = 0; i < E; ++i) dst[i] = i < ne ? m[e0 + i] : 0.f;
     }
   };
+  // member 0 is the shift; the others arrive in groups of KMAX whose loads are all issued before the first use (up to
+  // KMAX * 48 bytes in flight per thread: what hides the DRAM latency at the 2 CTAs / SM the accumulators allow), for
+  // any K.  The float64 additions run over the members in ascending order whatever the grouping.
   float x0[E];
   double s1[E], s2[E];
-  if constexpr (KMAX > 0) {
+  load(member[0], x0);
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    s1[i] = 0.0;
+    s2[i] = 0.0;
+  }
+  for (int k0 = 1; k0 < K; k0 += KMAX) {
     float x[KMAX][E];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) load(member[k < K ? k : 0], x[k]);
+    for (int u = 0; u < KMAX; ++u) {
+      if (k0 + u < K) {  // warp-uniform
+        load(member[k0 + u], x[u]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < E; ++i) x[u][i] = x0[i];  // d = 0: adds nothing
+      }
+    }
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-      x0[i] = x[0][i];
-      double a = 0.0, b2 = 0.0;
+      const double b0 = (double)x0[i];
+      double a = s1[i], b2 = s2[i];
 #pragma unroll
-      for (int k = 1; k < KMAX; ++k) {
-        if (k < K) {
-          const double d = (double)x[k][i] - (double)x0[i];
-          a += d;
-          b2 += d * d;
-        }
+      for (int u = 0; u < KMAX; ++u) {
+        const double d = (double)x[u][i] - b0;
+        a += d;
+        b2 = fma(d, d, b2);
       }
       s1[i] = a;
       s2[i] = b2;
     }
-  } else {
-    load(member[0], x0);
-#pragma unroll
-    for (int i = 0; i < E; ++i) {
-      s1[i] = 0.0;
-      s2[i] = 0.0;
-    }
-    for (int k = 1; k < K; ++k) {
-      float x[E];
-      load(member[k], x);
-#pragma unroll
-      for (int i = 0; i < E; ++i) {
-        const double d = (double)x[i] - (double)x0[i];
-        s1[i] += d;
-        s2[i] += d * d;
-      }
-    }
   }
+  // Only the cancellation-prone part stays in float64: the shifted sums and  s2 - s1^2 / K  (two float64 operations
+  // per element).  Everything downstream of that difference -- the 1 / (K - 1) scale, the square root, the mean
+  // x0 + s1 / K -- is float32 arithmetic on values that are already well conditioned (<= 3 ulp of a float in total,
+  // 1e-7 relative), which takes ~2/3 of the float64-pipe work (conversions included) out of the kernel.
   const double inv_k = 1.0 / (double)K;
-  const double inv_km1 = 1.0 / (double)(K - 1);
+  const float inv_kf = 1.0f / (float)K;
+  const float inv_km1 = 1.0f / (float)(K - 1);     // K == 1 -> inf: 0 * inf = NaN like torch's unbiased std of one sample
   float mean[E];
 #pragma unroll
-  for (int i = 0; i < E; ++i) mean[i] = (float)((double)x0[i] + s1[i] * inv_k);
+  for (int i = 0; i < E; ++i) mean[i] = fmaf((float)s1[i], inv_kf, x0[i]);
   if (jb.out_mean) {
     if (vec) {
       float4* dst = reinterpret_cast<float4*>(jb.out_mean + e0);
@@ -137,10 +121,9 @@ __device__ __forceinline__ void reduce_pixels(const float* const* member, int K,
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const int i = px * C + c;
-        // * 1/(K-1) instead of a float64 division (<= 1 ulp of a double apart); K == 1 -> 0 * inf = NaN like torch
-        double var = (s2[i] - s1[i] * s1[i] * inv_k) * inv_km1;
-        if (var < 0.0) var = 0.0;
-        const float v = jb.spread_mode == UB_SPREAD_STD ? sqrt_to_float(var) : (float)var;
+        float var = (float)fma(-s1[i] * inv_k, s1[i], s2[i]) * inv_km1;   // sum (d - mean d)^2 / (K - 1)
+        if (var < 0.0f) var = 0.0f;
+        const float v = jb.spread_mode == UB_SPREAD_STD ? sqrtf(var) : var;
         acc = c == 0 ? v : acc + v;
       }
       spread[px] = C == 1 ? acc : acc / (float)C;
@@ -251,11 +234,9 @@ __global__ void __launch_bounds__(256, FLAT ? 6 : 2) reduce_members_batched_kern
       const int npix = (int)min(4LL, jb.num_pixels - pix0);
       const bool vec = jb.vec_ok && npix == 4;
       if (jb.channels == 1) {
-        if (K <= 8) reduce_pixels<1, 8>(member, K, jb, pix0, npix, vec);
-        else reduce_pixels<1, 0>(member, K, jb, pix0, npix, vec);
+        reduce_pixels<1, 8>(member, K, jb, pix0, npix, vec);
       } else {
-        if (K <= 5) reduce_pixels<3, 5>(member, K, jb, pix0, npix, vec);
-        else reduce_pixels<3, 0>(member, K, jb, pix0, npix, vec);
+        reduce_pixels<3, 4>(member, K, jb, pix0, npix, vec);
       }
     }
   } else {

@@ -326,7 +326,7 @@ def patch_reference_models() -> List[str]:
                       "for elements that sit exactly on an interval boundary")
 
     def keep(cls, name):
-        if not hasattr(cls, "_ub_reference_" + name):
+        if "_ub_reference_" + name not in vars(cls):       # the class's own dict: idempotent, blind to inherited names
             setattr(cls, "_ub_reference_" + name, getattr(cls, name))
 
     keep(ActiveNerfactoModel, "get_outputs")
