@@ -33,7 +33,7 @@ struct ReduceBatch {
   int num_members;
 };
 
-template <int C, int KMAX>
+template <int C, int KMAX, bool GROUPED>
 __device__ __forceinline__ void reduce_pixels(const float* const* member, int K, const ReduceJob& jb,
                                               long long pix0, int npix, bool vec) {
   constexpr int E = 4 * C;  // elements per thread
@@ -55,40 +55,65 @@ __device__ __forceinline__ void reduce_pixels(const float* const* member, int K,
       for (int i = 0; i < E; ++i) dst[i] = i < ne ? m[e0 + i] : 0.f;
     }
   };
-  // member 0 is the shift; the others arrive in groups of KMAX whose loads are all issued before the first use (up to
-  // KMAX * 48 bytes in flight per thread: what hides the DRAM latency at the 2 CTAs / SM the accumulators allow), for
-  // any K.  The float64 additions run over the members in ascending order whatever the grouping.
+  // GROUPED == false (K <= KMAX): all members are loaded before the first use -- up to KMAX * 48 bytes in flight per
+  // thread, which is what hides the DRAM latency at the 2 CTAs / SM the accumulators allow -- and the two float64 sums
+  // of an element live only while that element is reduced.  GROUPED == true (any K): member 0 is the shift, the others
+  // arrive in groups of KMAX - 1 whose loads are issued together; the sums persist across the groups.  The float64
+  // additions run over the members in ascending order either way, so the results are identical.
   float x0[E];
   double s1[E], s2[E];
-  load(member[0], x0);
-#pragma unroll
-  for (int i = 0; i < E; ++i) {
-    s1[i] = 0.0;
-    s2[i] = 0.0;
-  }
-  for (int k0 = 1; k0 < K; k0 += KMAX) {
+  if constexpr (!GROUPED) {
     float x[KMAX][E];
 #pragma unroll
-    for (int u = 0; u < KMAX; ++u) {
-      if (k0 + u < K) {  // warp-uniform
-        load(member[k0 + u], x[u]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < E; ++i) x[u][i] = x0[i];  // d = 0: adds nothing
-      }
-    }
+    for (int k = 0; k < KMAX; ++k) load(member[k < K ? k : 0], x[k]);
 #pragma unroll
     for (int i = 0; i < E; ++i) {
+      x0[i] = x[0][i];
       const double b0 = (double)x0[i];
-      double a = s1[i], b2 = s2[i];
+      double a = 0.0, b2 = 0.0;
 #pragma unroll
-      for (int u = 0; u < KMAX; ++u) {
-        const double d = (double)x[u][i] - b0;
-        a += d;
-        b2 = fma(d, d, b2);
+      for (int k = 1; k < KMAX; ++k) {
+        if (k < K) {
+          const double d = (double)x[k][i] - b0;
+          a += d;
+          b2 = fma(d, d, b2);
+        }
       }
       s1[i] = a;
       s2[i] = b2;
+    }
+  } else {
+    constexpr int G = KMAX - 1;
+    load(member[0], x0);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      s1[i] = 0.0;
+      s2[i] = 0.0;
+    }
+    for (int k0 = 1; k0 < K; k0 += G) {
+      float x[G][E];
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        if (k0 + u < K) {  // warp-uniform
+          load(member[k0 + u], x[u]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < E; ++i) x[u][i] = x0[i];  // d = 0: adds nothing
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const double b0 = (double)x0[i];
+        double a = s1[i], b2 = s2[i];
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+          const double d = (double)x[u][i] - b0;
+          a += d;
+          b2 = fma(d, d, b2);
+        }
+        s1[i] = a;
+        s2[i] = b2;
+      }
     }
   }
   // Only the cancellation-prone part stays in float64: the shifted sums and  s2 - s1^2 / K  (two float64 operations
@@ -234,9 +259,11 @@ __global__ void __launch_bounds__(256, FLAT ? 6 : 2) reduce_members_batched_kern
       const int npix = (int)min(4LL, jb.num_pixels - pix0);
       const bool vec = jb.vec_ok && npix == 4;
       if (jb.channels == 1) {
-        reduce_pixels<1, 8>(member, K, jb, pix0, npix, vec);
+        if (K <= 8) reduce_pixels<1, 8, false>(member, K, jb, pix0, npix, vec);
+        else reduce_pixels<1, 8, true>(member, K, jb, pix0, npix, vec);
       } else {
-        reduce_pixels<3, 4>(member, K, jb, pix0, npix, vec);
+        if (K <= 5) reduce_pixels<3, 5, false>(member, K, jb, pix0, npix, vec);
+        else reduce_pixels<3, 5, true>(member, K, jb, pix0, npix, vec);
       }
     }
   } else {
