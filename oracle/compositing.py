@@ -1,10 +1,14 @@
 """Oracle: per-ray front-to-back compositing with the variance term (torch, CPU).
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PARITY UNPINNED at the
-nerfstudio boundary: the renderers below restate nerfstudio 1.1.0
-``model_components/renderers.py`` and ``cameras/rays.py:RaySamples.get_weights``
-(the version ``/root/reference/README.md:23`` installs; not vendored, not
-installable here).  The anchors inside the reference are cited per function.
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PINNED to the reference's own
+code: ``tests/test_oracle_pinned.py`` executes ``ComputeWeightsModule`` / ``SumModule``
+(``laplace_model.py:47-62,102-107``), ``ActiveNerfactoModel.get_outputs`` + the inherited chunk loop
+and ``NerfactoLaplaceModel.get_outputs_unc`` unmodified (``oracle/ref_exec.py``) and demands bit
+equality with the functions below (also against ``tests/golden/ref_composite.npz``).  The renderers
+themselves live in nerfstudio 1.1.0 (``model_components/renderers.py``,
+``cameras/rays.py:RaySamples.get_weights``; the version ``/root/reference/README.md:23`` installs; not
+vendored, not installable here): they are restated from the published code, in ``tests/stubs/site/nerfstudio``
+for the reference to call and here for the tests.  The anchors inside the reference are cited per function.
 
 Tensor conventions follow the reference: ``[R, S, C]`` with a trailing channel
 axis (``C = 1`` for density / deltas / starts / ends / beta, ``C = 3`` for rgb).

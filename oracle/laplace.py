@@ -4,7 +4,9 @@ TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Restates
 ``nerfuncertainty/models/laplace/laplace_field.py:528-568`` (``sample_laplace``) and the rgb-head
 post-processing at ``:478-484``.  The only change: the standard-normal draws are an argument instead of
 ``torch.randn`` on the global generator, so that the CUDA path can be fed identical samples.
-PARITY UNPINNED (no reference tests); the arithmetic is ``nn.Linear`` + activation + running sums.
+PINNED: ``tests/test_oracle_pinned.py::test_live_sample_laplace`` runs the reference's ``sample_laplace`` unmodified with the
+global generator seeded, so that its ``torch.randn`` returns the draws handed to the oracle, and demands bit equality
+(also ``tests/golden/ref_laplace.npz``).
 """
 from __future__ import annotations
 

@@ -6,7 +6,11 @@ TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).
 reference's own ``nerfuncertainty/metrics/ause.py:7-44`` and ``auce.py:10-57`` whenever
 ``/root/reference`` is mounted, and against golden vectors those functions produced
 (``tests/golden/make_golden.py``).  The remaining functions restate
-``nerfuncertainty/scripts/eval_uncertainty.py`` (cited per function).
+``nerfuncertainty/scripts/eval_uncertainty.py`` (cited per function) and are PINNED the same way:
+``tests/test_oracle_pinned.py::test_live_rgb_scoring_and_nll / test_live_depth_scoring /
+test_live_test_set_loop_and_npy_dumps`` execute ``get_unc_metrics_rgb``, ``get_unc_metrics_depth``,
+``negative_gaussian_loglikelihood``, ``get_image_metrics_and_images_unc`` and ``get_average_uncertainty_metrics``
+unmodified and demand bit equality (``tests/golden/ref_scoring.npz``).
 
 Two contract decisions (hard parts 1 and 5):
 

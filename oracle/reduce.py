@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Pure torch-CPU restatement of
 ``nerfuncertainty/models/mcdropout/mcdropout_models.py:121-126`` and
-``nerfuncertainty/models/ensemble/ensemble_pipeline.py:159-190``.  PARITY UNPINNED (the
-reference has no tests); the arithmetic is plain ``torch.stack / mean / std / var``.
+``nerfuncertainty/models/ensemble/ensemble_pipeline.py:159-190``.  PINNED: bit-equal to the reference's own
+methods executed unmodified (``tests/test_oracle_pinned.py::test_live_ensemble_reduce / test_live_mcdropout_reduce``
+through ``oracle/ref_exec.py``) and to ``tests/golden/ref_reduce.npz`` produced by them.
 """
 from __future__ import annotations
 

@@ -1,11 +1,14 @@
 """Oracle: tile-based front-to-back alpha compositing of 2-D Gaussians and the four
 active-splatfacto rasterisation passes (torch, CPU).
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PARITY UNPINNED: the per-pixel loop restates
-the published algorithm of gsplat 0.1.11 ``rasterize_forward`` (the version
-``/root/reference/README.md:30`` pins; not vendored, not installable here); the pass structure and the
-post-processing follow the reference's call sites,
-``nerfuncertainty/models/activesplatfacto/activesplatfacto_model.py:260-367``.
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Two layers.  The pass structure and the
+post-processing are the reference's (``nerfuncertainty/models/activesplatfacto/activesplatfacto_model.py:260-367``)
+and are PINNED: ``tests/test_oracle_pinned.py::test_live_active_splatfacto_get_outputs`` executes that method
+unmodified with this module standing in for gsplat and demands bit equality of every output key
+(``tests/golden/ref_splat.npz``).  The rasteriser underneath restates the published algorithm of gsplat 0.1.11
+``rasterize_forward`` / ``project_gaussians`` / ``spherical_harmonics`` (the version ``/root/reference/README.md:30``
+pins; a third-party CUDA dependency, not vendored, not installable here): that layer has no reference output to
+be pinned to.
 ``exp``: gsplat's CUDA kernel (and ours) uses the fast ``__expf`` intrinsic, which a CPU cannot reproduce;
 ``rasterize`` therefore takes the per-(splat, pixel) ``sigma`` / ``alpha`` values from the device through its ``probe``
 argument when exact agreement of the threshold decisions is wanted (tests/test_gpu_splat_exact.py), and falls back to

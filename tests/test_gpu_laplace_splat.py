@@ -2,7 +2,7 @@
 
 Laplace: ``sigma2 = E[y^2] - E[y]^2`` in float32 cancels catastrophically (SURVEY hard part 6), so parity is
 pinned on the two moments at 1e-5 relative and on sigma2 with an absolute floor of 1e-5 * E[y^2].
-Splat: parity unpinned against gsplat (not vendored); the oracle restates its published per-pixel loop.
+Splat: the pass structure is pinned to the reference (tests/test_oracle_pinned.py); the rasteriser under it restates gsplat 0.1.11 (not vendored).
 The alpha < 1/255 and T <= 1e-4 decisions are thresholds, so a pixel may take one Gaussian more or less
 when a 1-ulp exp difference crosses them: bounded count of outliers, tight tolerance elsewhere.
 """
