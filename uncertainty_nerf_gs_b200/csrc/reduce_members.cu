@@ -5,7 +5,8 @@
 //   models/ensemble/ensemble_pipeline.py:159-190   same, plus var(0).mean(-1) for the epistemic term
 //
 // One streaming pass: every member image is read exactly once through its own pointer (no
-// torch.stack copy), each thread owns 4 consecutive pixels (128-bit loads), and the K values of an
+// torch.stack copy), each thread owns 4 consecutive pixels of a one-channel key (128-bit loads) or 2 of a three-
+// channel key (64-bit loads: half the registers of 4 pixels, twice the resident warps), and the K values of an
 // element never leave registers.  All output keys of a view (rgb, depth, accumulation, ...) go
 // through ONE launch: blockIdx.y selects the key ("job").  The spread uses shifted sums in float64
 // (shift = first member), which is exact for identical members and has no mean^2/var
@@ -33,30 +34,37 @@ struct ReduceBatch {
   int num_members;
 };
 
-template <int C, int KMAX, bool GROUPED>
+template <int C, int P, int KMAX, bool GROUPED>
 __device__ __forceinline__ void reduce_pixels(const float* const* member, int K, const ReduceJob& jb,
                                               long long pix0, int npix, bool vec) {
-  constexpr int E = 4 * C;  // elements per thread
+  constexpr int E = P * C;  // elements per thread
+  static_assert((C == 1 && P == 4) || (C == 3 && P == 2), "vector widths below");
   const long long e0 = pix0 * C;
   const int ne = npix * C;
   auto load = [&](const float* m, float (&dst)[E]) {
     if (vec) {
-      const float4* src = reinterpret_cast<const float4*>(m + e0);
+      if constexpr (C == 1) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(m + e0));
+        dst[0] = v.x;
+        dst[1] = v.y;
+        dst[2] = v.z;
+        dst[3] = v.w;
+      } else {  // two pixels = 24 bytes at an 8-byte aligned offset (pix0 even, base 16-byte aligned)
+        const float2* src = reinterpret_cast<const float2*>(m + e0);
 #pragma unroll
-      for (int j = 0; j < C; ++j) {
-        const float4 v = __ldcs(src + j);
-        dst[4 * j + 0] = v.x;
-        dst[4 * j + 1] = v.y;
-        dst[4 * j + 2] = v.z;
-        dst[4 * j + 3] = v.w;
+        for (int j = 0; j < 3; ++j) {
+          const float2 v = __ldcs(src + j);
+          dst[2 * j] = v.x;
+          dst[2 * j + 1] = v.y;
+        }
       }
     } else {
 #pragma unroll
       for (int i = 0; i < E; ++i) dst[i] = i < ne ? m[e0 + i] : 0.f;
     }
   };
-  // GROUPED == false (K <= KMAX): all members are loaded before the first use -- up to KMAX * 48 bytes in flight per
-  // thread, which is what hides the DRAM latency at the 2 CTAs / SM the accumulators allow -- and the two float64 sums
+  // GROUPED == false (K <= KMAX): all members are loaded before the first use -- up to KMAX * 24 bytes in flight per
+  // thread, which together with 3-4 CTAs / SM is what hides the DRAM latency -- and the two float64 sums
   // of an element live only while that element is reduced.  GROUPED == true (any K): member 0 is the shift, the others
   // arrive in groups of KMAX - 1 whose loads are issued together; the sums persist across the groups.  The float64
   // additions run over the members in ascending order either way, so the results are identical.
@@ -128,10 +136,13 @@ __device__ __forceinline__ void reduce_pixels(const float* const* member, int K,
   for (int i = 0; i < E; ++i) mean[i] = fmaf((float)s1[i], inv_kf, x0[i]);
   if (jb.out_mean) {
     if (vec) {
-      float4* dst = reinterpret_cast<float4*>(jb.out_mean + e0);
+      if constexpr (C == 1) {
+        *reinterpret_cast<float4*>(jb.out_mean + e0) = make_float4(mean[0], mean[1], mean[2], mean[3]);
+      } else {
+        float2* dst = reinterpret_cast<float2*>(jb.out_mean + e0);
 #pragma unroll
-      for (int j = 0; j < C; ++j)
-        dst[j] = make_float4(mean[4 * j], mean[4 * j + 1], mean[4 * j + 2], mean[4 * j + 3]);
+        for (int j = 0; j < 3; ++j) dst[j] = make_float2(mean[2 * j], mean[2 * j + 1]);
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < E; ++i)
@@ -139,9 +150,9 @@ __device__ __forceinline__ void reduce_pixels(const float* const* member, int K,
     }
   }
   if (jb.spread_mode != UB_SPREAD_NONE && jb.out_spread) {
-    float spread[4];
+    float spread[P];
 #pragma unroll
-    for (int px = 0; px < 4; ++px) {
+    for (int px = 0; px < P; ++px) {
       float acc = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -154,11 +165,13 @@ __device__ __forceinline__ void reduce_pixels(const float* const* member, int K,
       spread[px] = C == 1 ? acc : acc / (float)C;
     }
     if (vec) {
-      *reinterpret_cast<float4*>(jb.out_spread + pix0) =
-          make_float4(spread[0], spread[1], spread[2], spread[3]);
+      if constexpr (P == 4)
+        *reinterpret_cast<float4*>(jb.out_spread + pix0) = make_float4(spread[0], spread[1], spread[2], spread[3]);
+      else
+        *reinterpret_cast<float2*>(jb.out_spread + pix0) = make_float2(spread[0], spread[1]);
     } else {
 #pragma unroll
-      for (int px = 0; px < 4; ++px)
+      for (int px = 0; px < P; ++px)
         if (px < npix) jb.out_spread[pix0 + px] = spread[px];
     }
   }
@@ -227,10 +240,10 @@ __device__ __forceinline__ void reduce_pixel_any_c(const float* const* member, i
 }
 
 // Two instantiations share the launch: FLAT = true carries only the mean-only float32 stream path (about 40
-// registers, full occupancy: most of a view's bytes go through it), FLAT = false the float64 spread paths (128
-// registers, 2 CTAs per SM).  One kernel for both left the streaming jobs at a quarter of the occupancy they need.
+// registers, full occupancy: most of a view's bytes go through it), FLAT = false the float64 spread paths (<= 80
+// registers, 3 CTAs per SM).  One kernel for both left the streaming jobs at a quarter of the occupancy they need.
 template <bool FLAT>
-__global__ void __launch_bounds__(256, FLAT ? 6 : 2) reduce_members_batched_kernel(const __grid_constant__ ReduceBatch b) {
+__global__ void __launch_bounds__(256, FLAT ? 6 : 3) reduce_members_batched_kernel(const __grid_constant__ ReduceBatch b) {
   const ReduceJob& jb = b.job[blockIdx.y];
   const float* const* member = b.member[blockIdx.y];
   const int K = b.num_members;
@@ -252,19 +265,23 @@ __global__ void __launch_bounds__(256, FLAT ? 6 : 2) reduce_members_batched_kern
     return;
   }
   if constexpr (!FLAT) {
-  if (jb.channels == 1 || jb.channels == 3) {
+  if (jb.channels == 1) {
     const long long groups = (jb.num_pixels + 3) / 4;
     for (long long g = tid; g < groups; g += stride) {
       const long long pix0 = g * 4;
       const int npix = (int)min(4LL, jb.num_pixels - pix0);
       const bool vec = jb.vec_ok && npix == 4;
-      if (jb.channels == 1) {
-        if (K <= 8) reduce_pixels<1, 8, false>(member, K, jb, pix0, npix, vec);
-        else reduce_pixels<1, 8, true>(member, K, jb, pix0, npix, vec);
-      } else {
-        if (K <= 5) reduce_pixels<3, 5, false>(member, K, jb, pix0, npix, vec);
-        else reduce_pixels<3, 5, true>(member, K, jb, pix0, npix, vec);
-      }
+      if (K <= 6) reduce_pixels<1, 4, 6, false>(member, K, jb, pix0, npix, vec);
+      else reduce_pixels<1, 4, 6, true>(member, K, jb, pix0, npix, vec);
+    }
+  } else if (jb.channels == 3) {
+    const long long groups = (jb.num_pixels + 1) / 2;
+    for (long long g = tid; g < groups; g += stride) {
+      const long long pix0 = g * 2;
+      const int npix = (int)min(2LL, jb.num_pixels - pix0);
+      const bool vec = jb.vec_ok && npix == 2;
+      if (K <= 5) reduce_pixels<3, 2, 5, false>(member, K, jb, pix0, npix, vec);
+      else reduce_pixels<3, 2, 5, true>(member, K, jb, pix0, npix, vec);
     }
   } else {
     for (long long px = tid; px < jb.num_pixels; px += stride) reduce_pixel_any_c(member, K, jb, px);
@@ -320,12 +337,13 @@ int ub_reduce_members_batched(const ub_reduce_job* jobs_host, int32_t num_jobs, 
     if (is_flat) {
       flat_threads = std::max(flat_threads, (long long)((in.num_pixels * in.channels + 7) / 8));
     } else {
-      const long long t = (in.channels == 1 || in.channels == 3) ? (in.num_pixels + 3) / 4 : in.num_pixels;
+      const long long t = in.channels == 1 ? (in.num_pixels + 3) / 4
+                          : in.channels == 3 ? (in.num_pixels + 1) / 2 : in.num_pixels;
       spread_threads = std::max(spread_threads, t);
     }
   }
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  const long long cap = (long long)sms * 8;
+  const long long cap = (long long)sms * 16;
   if (n_flat > 0 && flat_threads > 0) {
     dim3 grid((unsigned)std::min(cap, (flat_threads + 255) / 256), (unsigned)n_flat);
     reduce_members_batched_kernel<true><<<grid, 256, 0, stream>>>(flat);

@@ -36,8 +36,11 @@ namespace ub {
 constexpr int kPrologueThreads = 256;
 constexpr int kPixPerThread = 4;
 constexpr int kPixPerChunk = kPrologueThreads * kPixPerThread;
-constexpr int kChunksPerBlock = 4;  // amortises the table build
-constexpr int kPixPerBlock = kPixPerChunk * kChunksPerBlock;
+// chunks per block: amortise the table build and the flush of the block's histograms (4096 pixels per block; 8192 once
+// the batch is large enough to fill the device several times over anyway)
+__host__ __device__ inline int prologue_chunks_per_block(long long num_segments, long long max_len) {
+  return num_segments * max_len >= (4LL << 20) ? 8 : 4;
+}
 constexpr int kMaxZ = 127;
 constexpr int kLutBins = 16384;           // uniform bins of r over [0, 1.001 z_0)
 constexpr float kLutGuard = 1e-5f;        // relative guard band around every bin (float32 estimate error)
@@ -61,7 +64,10 @@ struct PrologueParams {
   float* o_ae;
   float* o_var;
   double* partial;  // [num_segments][blocks_per_seg][NSUMS]
+  unsigned* done;   // [num_segments] blocks of the segment that have written their partial sums (zeroed)
+  double* out_sums; // [num_segments][NSUMS]
   int blocks_per_seg;
+  int chunks_per_block;
   unsigned long long* hist;  // [num_segments][num_z + 1]
   const unsigned char* lut;  // [kLutBins + 16] ratio table (workspace)
   int vec_ok;
@@ -70,6 +76,12 @@ struct PrologueParams {
 
 constexpr int kCoarseBins = 4096;
 constexpr int kCoarseShift = 20;
+
+// sort_key_from_float(x) >> 20 for a value that is never negative (a square, a sum of magnitudes): the sign bit
+// of the key is set, NaN is the one largest key
+__device__ __forceinline__ unsigned coarse_bin_nonneg(float x) {
+  return x != x ? (unsigned)(kCoarseBins - 1) : (0x800u | (__float_as_uint(x) >> kCoarseShift));
+}
 
 __device__ __forceinline__ bool interval_holds(double z, float m, float s, float t) {
   const double zs = __dmul_rn(z, (double)s);
@@ -135,18 +147,18 @@ __global__ void __launch_bounds__(256) prologue_lut_kernel(const double* __restr
 }
 
 template <int C, bool COARSE>
-__global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const PrologueParams p) {
+__global__ void __launch_bounds__(kPrologueThreads, 3) score_prologue_kernel(const PrologueParams p) {
   __shared__ double z_d[kMaxZ + 1];
   __shared__ float z_f[kMaxZ + 1];
   __shared__ unsigned int hist_s[kPrologueThreads / 32][kMaxZ + 1];
   __shared__ double red[kPrologueThreads / 32][UB_PROLOGUE_NSUMS];
   __shared__ __align__(16) unsigned char lut[kLutBins + 16];
-  // coarse key histograms of the block, two 16-bit counters per word (a block holds 4096 pixels < 2^16)
+  // coarse key histograms of the block, two 16-bit counters per word (a block holds <= 8192 pixels < 2^16)
   __shared__ unsigned int coarse_s[COARSE ? 3 : 1][COARSE ? kCoarseBins / 2 : 1];
 
   const int seg = blockIdx.y;
   const long long seg_lo = p.seg_offsets[seg], seg_hi = p.seg_offsets[seg + 1];
-  const long long blk_lo = seg_lo + (long long)blockIdx.x * kPixPerBlock;
+  const long long blk_lo = seg_lo + (long long)blockIdx.x * (kPixPerChunk * p.chunks_per_block);
   if (blk_lo >= seg_hi && blockIdx.x > 0) return;  // ragged batches: nothing in this block (block 0 writes the zero partials)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nz = p.num_z;
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
 
   double sums[UB_PROLOGUE_NSUMS] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
-  for (int chunk = 0; chunk < kChunksPerBlock; ++chunk) {
+  for (int chunk = 0; chunk < p.chunks_per_block; ++chunk) {
     const long long pix0 = blk_lo + (long long)chunk * kPixPerChunk + (long long)threadIdx.x * kPixPerThread;
     const int npix = (int)max(0LL, min((long long)kPixPerThread, seg_hi - pix0));
     if (__syncthreads_count(npix > 0) == 0) break;  // the whole block is past the segment's end
@@ -209,7 +221,14 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
       const float inv_two_var = __fdividef(0.5f, __fmul_rn(s_nll, s_nll));
       const float log_s = __logf(s_nll) + 0.91893853320467274178f;
       const float inv_sigma = __fdividef(1.0f, sigma);
-      const float sigma_guard = (sigma > 1e-30f && sigma < 1e30f) ? sigma * kSigmaGuard : -1.f;
+      // tiers 1 / 2 need a positive, not-tiny sigma with sigma >= 1e-6 |m|; tested once per pixel against the largest
+      // |m| of its channels (conservative: a channel sent to tier 3 needlessly is still counted exactly) and folded into
+      // the ratio's multiplier, so that a failed guard shows up as a NaN ratio
+      float m_max = fabsf(pr[px * C]);
+#pragma unroll
+      for (int c = 1; c < C; ++c) m_max = fmaxf(m_max, fabsf(pr[px * C + c]));
+      const bool guard_ok = sigma > 1e-30f && sigma < 1e30f && sigma * kSigmaGuard >= m_max;
+      const float r_mul = guard_ok ? inv_sigma : __int_as_float(0x7FC00000);
       float se_px = 0.f, ae_px = 0.f, nll_px = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -220,10 +239,10 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
         ae_px = c == 0 ? fabsf(d) : __fadd_rn(ae_px, fabsf(d));
         nll_px += fmaf(d2, inv_two_var, log_s);
         // coverage count, tiers 1-3
-        const float r = fabsf(d) * inv_sigma;
+        const float r = fabsf(d) * r_mul;
         const unsigned bin = min((unsigned)__float2int_rz(r * inv_w), (unsigned)kLutBins);
         const unsigned looked_up = lut[bin];
-        const unsigned e = (r >= 0.f && sigma_guard >= fabsf(m)) ? looked_up : kLutGeneric;
+        const unsigned e = r >= 0.f ? looked_up : kLutGeneric;  // false for the NaN of a failed guard / NaN inputs
         int cnt = (int)e;
         if (__any_sync(FULL_MASK, valid && e >= kLutOneThreshold)) {  // warp-uniform
           // tier 2 for the whole warp, branch-free: one exact float64 predicate at threshold k
@@ -246,9 +265,9 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
         sums[3] += (double)nll_px;
         sums[4] += (double)sigma;
         if (COARSE) {
-          const unsigned kv = sort_key_from_float(var) >> kCoarseShift;
-          const unsigned ka = sort_key_from_float(ae_px) >> kCoarseShift;
-          const unsigned ks = sort_key_from_float(se_px) >> kCoarseShift;
+          const unsigned kv = coarse_bin_nonneg(var);
+          const unsigned ka = coarse_bin_nonneg(ae_px);
+          const unsigned ks = coarse_bin_nonneg(se_px);
           atomicAdd(&coarse_s[0][kv >> 1], 1u << (16 * (kv & 1u)));
           atomicAdd(&coarse_s[1][ka >> 1], 1u << (16 * (ka & 1u)));
           atomicAdd(&coarse_s[2][ks >> 1], 1u << (16 * (ks & 1u)));
@@ -283,6 +302,7 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
     double v = 0.0;
     for (int w = 0; w < kPrologueThreads / 32; ++w) v += red[w][threadIdx.x];
     p.partial[((size_t)seg * p.blocks_per_seg + blockIdx.x) * UB_PROLOGUE_NSUMS + threadIdx.x] = v;
+    __threadfence();
   }
   for (int c = threadIdx.x; c <= nz; c += blockDim.x) {
     unsigned int v = 0;
@@ -300,33 +320,43 @@ __global__ void __launch_bounds__(kPrologueThreads) score_prologue_kernel(const 
       }
     }
   }
-}
-
-// out_sums[seg][j] = sum over the segment's blocks in block order (deterministic)
-// one warp per sum: lanes stride over the blocks, then a fixed-order shuffle tree
-__global__ void prologue_finalize_kernel(const double* partial, int blocks_per_seg, double* out_sums) {
-  const int seg = blockIdx.x;
-  const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (j >= UB_PROLOGUE_NSUMS) return;
-  double v = 0.0;
-  for (int b = lane; b < blocks_per_seg; b += 32)
-    v += partial[((size_t)seg * blocks_per_seg + b) * UB_PROLOGUE_NSUMS + j];
+  // the last block of the segment to get here adds the partial sums of all of them, in block order (deterministic):
+  // one warp per sum, lanes stride over the blocks, then a fixed-order shuffle tree
+  __shared__ unsigned s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long pix_per_block = (long long)kPixPerChunk * p.chunks_per_block;
+    const unsigned nblk = (unsigned)max(1LL, (seg_hi - seg_lo + pix_per_block - 1) / pix_per_block);
+    s_last = atomicAdd(p.done + seg, 1u) == nblk - 1u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (warp < UB_PROLOGUE_NSUMS) {
+    double v = 0.0;
+    for (int b = lane; b < p.blocks_per_seg; b += 32)
+      v += __ldcg(p.partial + ((size_t)seg * p.blocks_per_seg + b) * UB_PROLOGUE_NSUMS + warp);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += shfl_xor_double(FULL_MASK, v, o);
-  if (lane == 0) out_sums[(size_t)seg * UB_PROLOGUE_NSUMS + j] = v;
+    for (int o = 16; o > 0; o >>= 1) v += shfl_xor_double(FULL_MASK, v, o);
+    if (lane == 0) p.out_sums[(size_t)seg * UB_PROLOGUE_NSUMS + warp] = v;
+  }
 }
 
 struct PrologueLayout {
-  size_t off_offsets, off_partial, off_lut, total;
-  int blocks_per_seg;
+  size_t off_offsets, off_partial, partial_bytes, off_done, off_lut, total;
+  int blocks_per_seg, chunks_per_block;
 };
 static PrologueLayout prologue_layout(int num_segments, long long max_len) {
   PrologueLayout l{};
-  l.blocks_per_seg = (int)((max_len + kPixPerBlock - 1) / kPixPerBlock);
+  l.chunks_per_block = prologue_chunks_per_block(num_segments, max_len);
+  const long long pix_per_block = (long long)kPixPerChunk * l.chunks_per_block;
+  l.blocks_per_seg = (int)((max_len + pix_per_block - 1) / pix_per_block);
   if (l.blocks_per_seg < 1) l.blocks_per_seg = 1;
   l.off_offsets = 0;
   l.off_partial = align_up((size_t)(num_segments + 1) * sizeof(long long), 256);
-  l.off_lut = align_up(l.off_partial + (size_t)num_segments * l.blocks_per_seg * UB_PROLOGUE_NSUMS * sizeof(double), 256);
+  l.partial_bytes = (size_t)num_segments * l.blocks_per_seg * UB_PROLOGUE_NSUMS * sizeof(double);
+  l.off_done = l.off_partial + l.partial_bytes;  // zeroed together with the partial sums
+  l.off_lut = align_up(l.off_done + (size_t)num_segments * sizeof(unsigned), 256);
   l.total = l.off_lut + kLutBins + 16;
   return l;
 }
@@ -372,8 +402,8 @@ int ub_score_prologue(const ub_score_prologue_args* a, void* workspace, size_t w
       return check_launch("score_prologue coarse memset");
   }
   // blocks past the end of a short segment exit early: their partial sums must read as zero
-  if (cudaMemsetAsync(ws + lay.off_partial, 0,
-                      (size_t)a->num_segments * lay.blocks_per_seg * UB_PROLOGUE_NSUMS * sizeof(double), stream) != cudaSuccess)
+  if (cudaMemsetAsync(ws + lay.off_partial, 0, lay.partial_bytes + (size_t)a->num_segments * sizeof(unsigned), stream) !=
+      cudaSuccess)
     return check_launch("score_prologue partial memset");
 
   PrologueParams p{};
@@ -391,7 +421,10 @@ int ub_score_prologue(const ub_score_prologue_args* a, void* workspace, size_t w
   p.o_ae = a->out_abs_err;
   p.o_var = a->out_var;
   p.partial = reinterpret_cast<double*>(ws + lay.off_partial);
+  p.done = reinterpret_cast<unsigned*>(ws + lay.off_done);
+  p.out_sums = a->out_sums;
   p.blocks_per_seg = lay.blocks_per_seg;
+  p.chunks_per_block = lay.chunks_per_block;
   p.hist = reinterpret_cast<unsigned long long*>(a->out_hist);
   unsigned char* lut = reinterpret_cast<unsigned char*>(ws + lay.off_lut);
   p.lut = lut;
@@ -410,10 +443,7 @@ int ub_score_prologue(const ub_score_prologue_args* a, void* workspace, size_t w
     if (p.coarse) score_prologue_kernel<1, true><<<grid, kPrologueThreads, 0, stream>>>(p);
     else score_prologue_kernel<1, false><<<grid, kPrologueThreads, 0, stream>>>(p);
   }
-  int rc = check_launch("score_prologue");
-  if (rc != UB_OK) return rc;
-  prologue_finalize_kernel<<<a->num_segments, 32 * UB_PROLOGUE_NSUMS, 0, stream>>>(p.partial, lay.blocks_per_seg, a->out_sums);
-  return check_launch("score_prologue finalize");
+  return check_launch("score_prologue");
 }
 
 }  // extern "C"

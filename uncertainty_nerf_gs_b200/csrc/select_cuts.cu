@@ -12,11 +12,10 @@
 //              per segment, each holding <= n/2048 keys unless the keys tie): an equal-frequency binning
 //              that needs neither the key range nor splitters; a sorted 1024-key sample finds the heavy
 //              tie values (a clamped uncertainty floor), each of which gets a bin of its own
-//   fine       histogram over the fine bins
+//   fine       histogram over the fine bins; per 2048-key tile counts of the heavy tie values
 //   locate     prefix over the fine bins; every cut falls into one bin (its "cell") at a residual rank r;
 //              a bin that holds no cut gets a class = number of cuts that exclude it
-//   ties       per 2048-key tile counts of the heavy tie values that hold a cut
-//   plan       a big cell whose keys are all equal (a tie group) is resolved by index: stable order inside
+//   (locate)   a big cell whose keys are all equal (a tie group) is resolved by index: stable order inside
 //              it is the element order, so the tile where the running count crosses r follows from the
 //              per-tile counts and only that tile's members stay undecided; other cells stay undecided whole
 //   classify   one pass over keys + payloads: decided elements add their payload to the sum of their class
@@ -69,10 +68,12 @@ struct RunDesc {        // what the resolve block of cut j works on
 struct SegPlan {
   int nfine, nbins, ncells, nheavy, ntiled;
   int emax;  // biased exponent of the largest finite |key| of the segment
-  int pad1, pad2;
+  int flags;  // bit 0: the segment holds negative keys, bit 1: it holds NaN keys (from the coarse histogram)
+  int pad2;
   uint32_t heavy[kSelMaxHeavy];      // heavy tie values (any order)
   uint32_t tkey[kSelMaxHeavy];       // tiled cells: tie groups that hold a cut and are resolved by tile
   int tcell[kSelMaxHeavy];
+  int theavy[kSelMaxHeavy];          // tiled cell -> index of its key among the heavy tie values (row of tilecounts)
   int cut_k[kSelMaxCuts];            // original index of the j-th smallest cut
   int cut_T[kSelMaxCuts];            // bins < T are under the cut
   int cut_cell[kSelMaxCuts];         // cell that holds the cut, -1 if the cut is a bin boundary
@@ -109,9 +110,12 @@ struct SelParams {
   uint32_t* table;        // [G][kSelCoarse]: (first fine bin << 5) | shift of the low 20 key bits
   SegPlan* plan;          // [G]
   uint16_t* binmap;       // [G][kSelBins]: class, or kSelCellFlag | cell
-  uint32_t* tilecounts;   // [G][kSelMaxHeavy][max_tiles]; after sel_plan_tiled: first record of (tiled cell, tile)
+  uint32_t* tilecounts;   // [G][kSelMaxHeavy][max_tiles] per heavy tie value; after sel_plan_tiled, rows of tiled cells:
+                          // first record of (tiled cell, tile)
   uint8_t* tilemode;      // [G][max_tiles][kSelMaxHeavy]: class of the tie group's members in the tile, or kSelCompact
   double* spart;          // [G][max_blocks][num_cuts + 1][2]
+  double* fpart;          // [G][kSelFinGroups][kSelFinStride] group totals of sel_finish
+  uint32_t* fcount;       // [G] sel_finish blocks that have arrived                       zeroed
   uint32_t* ckeys;        // [F * total] records: order-preserving key
   uint32_t* cidx;         // [F * total] records: index within the segment
 };
@@ -132,7 +136,8 @@ __device__ __forceinline__ int sel_bin(uint32_t u, uint32_t t, const uint32_t* h
   return bin;
 }
 
-// exclusive scan of one value per thread over a block of kSelThreads threads
+// exclusive scan of one value per thread over a block of 32 * WARPS threads
+template <int WARPS = kSelWarps>
 __device__ __forceinline__ uint32_t sel_block_excl_scan(uint32_t v, uint32_t* warp_tmp, uint32_t* total_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t incl = v;
@@ -145,7 +150,7 @@ __device__ __forceinline__ uint32_t sel_block_excl_scan(uint32_t v, uint32_t* wa
   __syncthreads();
   uint32_t base = 0, tot = 0;
 #pragma unroll
-  for (int w = 0; w < kSelWarps; ++w) {
+  for (int w = 0; w < WARPS; ++w) {
     const uint32_t t = warp_tmp[w];
     if (w < warp) base += t;
     tot += t;
@@ -186,20 +191,27 @@ __global__ void __launch_bounds__(kSelThreads) sel_coarse_hist(const SelParams p
   }
 }
 
-// ---- fine-bin allocation + heavy tie values: one block per segment ----------------------------------------
-__global__ void __launch_bounds__(kSelThreads) sel_alloc(const SelParams p) {
-  __shared__ uint32_t warp_tmp[kSelWarps];
+// ---- fine-bin allocation + heavy tie values: one block of 1024 threads per segment (a latency chain) ----------
+constexpr int kSelAllocThreads = 1024;
+__global__ void __launch_bounds__(kSelAllocThreads) sel_alloc(const SelParams p) {
+  constexpr int kWarps = kSelAllocThreads / 32;
+  static_assert(kSelSample == kSelAllocThreads, "one sample per thread");
+  __shared__ uint32_t warp_tmp[kWarps];
   __shared__ uint32_t s_sample[kSelSample];
   const int g = blockIdx.x, tid = threadIdx.x;
   int f, b;
   long long lo, len;
   sel_segment(p, g, f, b, lo, len);
   SegPlan& pl = p.plan[g];
+  // the sample first: its loads are the longest latency of the kernel
+  const int ns = (int)min((long long)kSelSample, len);
+  const float* k = p.keys[f] + lo;
+  uint32_t x = tid < ns ? sort_key_from_float(__ldg(k + (long long)tid * len / ns)) : 0xFFFFFFFFu;
   const uint32_t target = (uint32_t)max(1LL, (len + 2047) / 2048);
-  constexpr int per = kSelCoarse / kSelThreads;
+  constexpr int per = kSelCoarse / kSelAllocThreads;
   const uint32_t* gh = p.hist_c + (size_t)g * kSelCoarse;
   uint32_t nsub[per], lg[per], sum = 0;
-  int emax = 0;
+  int emax = 0, flags = 0;
 #pragma unroll
   for (int i = 0; i < per; ++i) {
     const uint32_t cnt = gh[tid * per + i];
@@ -207,6 +219,8 @@ __global__ void __launch_bounds__(kSelThreads) sel_alloc(const SelParams p) {
       const int c = tid * per + i;
       const int ex = ((c >= 2048 ? c : ~c) >> 3) & 0xFF;
       if (ex != 255) emax = max(emax, ex);
+      if (c < 2048) flags |= 1;              // negative keys (-0.0 counts as +0.0)
+      if (c == kSelCoarse - 1) flags |= 2;   // the NaN key 0xFFFFFFFE
     }
     uint32_t l = 0;
     if (cnt > target) {
@@ -218,7 +232,7 @@ __global__ void __launch_bounds__(kSelThreads) sel_alloc(const SelParams p) {
     sum += nsub[i];
   }
   uint32_t tot;
-  uint32_t run = sel_block_excl_scan(sum, warp_tmp, &tot);
+  uint32_t run = sel_block_excl_scan<kWarps>(sum, warp_tmp, &tot);
   uint32_t* tab = p.table + (size_t)g * kSelCoarse;
 #pragma unroll
   for (int i = 0; i < per; ++i) {
@@ -228,40 +242,43 @@ __global__ void __launch_bounds__(kSelThreads) sel_alloc(const SelParams p) {
   // heavy tie values from a sorted sample: a key that fills >= 8 of 1024 evenly spaced probes.  A tie group
   // next to other keys of the same fine bin would make its cell "large and not one tie group" (the slow
   // radix-select corner of sel_resolve); owning a bin makes it a tie-group cell, resolved by index.
-  const int ns = (int)min((long long)kSelSample, len);
-  const float* k = p.keys[f] + lo;
-  for (int i = tid; i < kSelSample; i += kSelThreads)
-    s_sample[i] = i < ns ? sort_key_from_float(__ldg(k + (long long)i * len / ns)) : 0xFFFFFFFFu;
-  __syncthreads();
-  for (int size = 2; size <= kSelSample; size <<= 1) {      // bitonic sort, ascending
+  // Bitonic sort, ascending, one key per thread: partners closer than a warp exchange by shuffle.
+  for (int size = 2; size <= kSelSample; size <<= 1) {
+    const bool up = (tid & size) == 0;
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < kSelSample / 2; i += kSelThreads) {
-        const int a = 2 * i - (i & (stride - 1)), c = a + stride;
-        const bool up = (a & size) == 0;
-        const uint32_t x = s_sample[a], y = s_sample[c];
-        if ((x > y) == up) {
-          s_sample[a] = y;
-          s_sample[c] = x;
-        }
+      uint32_t y;
+      if (stride >= 32) {
+        s_sample[tid] = x;
+        __syncthreads();
+        y = s_sample[tid ^ stride];
+        __syncthreads();
+      } else {
+        y = __shfl_xor_sync(FULL_MASK, x, stride);
       }
-      __syncthreads();
+      const bool low = (tid & stride) == 0;  // the lower index of the pair keeps the smaller key in an ascending run
+      x = (low == up) ? min(x, y) : max(x, y);
     }
   }
-  __shared__ int s_nh, s_emax;
+  s_sample[tid] = x;
+  __shared__ int s_nh, s_emax, s_flags;
   __shared__ uint32_t s_hv[kSelMaxHeavy];
-  if (tid == 0) s_emax = 0;
+  if (tid == 0) {
+    s_emax = 0;
+    s_flags = 0;
+  }
   __syncthreads();
   emax = __reduce_max_sync(FULL_MASK, emax);
+  flags = __reduce_or_sync(FULL_MASK, flags);
   if ((tid & 31) == 0 && emax) atomicMax(&s_emax, emax);
+  if ((tid & 31) == 0 && flags) atomicOr(&s_flags, flags);
   for (int thresh = kSelHeavyHits;; thresh *= 2) {  // at most kSelMaxHeavy values: raise the bar until they fit
     if (tid == 0) s_nh = 0;
     __syncthreads();
-    for (int i = tid; i < ns; i += kSelThreads) {
-      const uint32_t v = s_sample[i];
-      const bool first = i == 0 || s_sample[i - 1] != v;
-      if (first && i + thresh - 1 < ns && s_sample[i + thresh - 1] == v) {
+    if (tid < ns) {
+      const bool first = tid == 0 || s_sample[tid - 1] != x;
+      if (first && tid + thresh - 1 < ns && s_sample[tid + thresh - 1] == x) {
         const int slot = atomicAdd(&s_nh, 1);
-        if (slot < kSelMaxHeavy) s_hv[slot] = v;
+        if (slot < kSelMaxHeavy) s_hv[slot] = x;
       }
     }
     __syncthreads();
@@ -272,6 +289,7 @@ __global__ void __launch_bounds__(kSelThreads) sel_alloc(const SelParams p) {
   if (tid < kSelMaxHeavy) pl.heavy[tid] = tid < nh ? s_hv[tid] : 0xFFFFFFFFu;
   if (tid == 0) {
     pl.emax = s_emax;
+    pl.flags = s_flags;
     pl.nheavy = nh;
     pl.nfine = (int)tot;  // <= kSelFine: sum pow2ceil(cnt / target) <= 4096 + 2 n / target
     pl.nbins = (int)tot + 2 * nh;
@@ -279,6 +297,79 @@ __global__ void __launch_bounds__(kSelThreads) sel_alloc(const SelParams p) {
 }
 
 // ---- fine histogram --------------------------------------------------------------------------------------
+// Order-preserving key of a segment known (from its coarse histogram) to hold neither negative values nor NaN:
+// one OR instead of the general transform (-0.0 and +0.0 both map to 0x80000000, as in sort_key_from_float).
+template <bool NONNEG>
+__device__ __forceinline__ uint32_t sel_key(float f) {
+  return NONNEG ? (__float_as_uint(f) | 0x80000000u) : sort_key_from_float(f);
+}
+
+// bins of eight keys at once: the eight table loads are in flight together, and the heavy-value adjustment runs
+// value by value over all eight keys (one shared-memory load per heavy value instead of eight)
+// `tcnt` (fine histogram only): per heavy value, the number of its occurrences among these eight keys per thread --
+// one 2048-key tile per block-wide call -- is added to tcnt[h] (stable order inside a tie group is the element order,
+// so a tie group that turns out to hold a cut is resolved from these per-tile counts, see sel_plan_tiled)
+template <bool NONNEG, bool COUNT = false>
+__device__ __forceinline__ void sel_bins8(const float (&v)[8], const uint32_t* __restrict__ tab,
+                                          const uint32_t* heavy, int nh, uint32_t (&u)[8], int (&bin)[8],
+                                          uint32_t* tcnt = nullptr, uint32_t valid = 0xFFu) {
+  uint32_t t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    u[i] = sel_key<NONNEG>(v[i]);
+    t[i] = __ldg(tab + (u[i] >> kSelLowBits));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bin[i] = (int)(t[i] >> 5) + (int)((u[i] & kSelLowMask) >> (t[i] & 31u));
+  for (int h = 0; h < nh; ++h) {
+    const uint32_t hv = heavy[h];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bin[i] += (int)(hv < u[i]) + (int)(hv <= u[i]);
+    if (COUNT) {
+      uint32_t c = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c += (uint32_t)(hv == u[i]) & (valid >> i);
+      c = __reduce_add_sync(FULL_MASK, c);
+      if ((threadIdx.x & 31) == 0 && c) atomicAdd(tcnt + h, c);
+    }
+  }
+}
+
+template <bool NONNEG>
+__device__ __forceinline__ void sel_fine_hist_body(const float* __restrict__ k, int count,
+                                                   const uint32_t* __restrict__ tab, const uint32_t* s_heavy, int nh,
+                                                   uint32_t* h, uint32_t (*tcnt)[kSelMaxHeavy]) {
+  constexpr int per = kSelChunk / kSelThreads;
+  const int tid = threadIdx.x;
+  if (count == kSelChunk) {  // whole chunk: no clamps, no predicates
+    for (int base = 0; base < per; base += 8) {
+      float v[8];
+      uint32_t u[8];
+      int bin[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(k + (base + i) * kSelThreads + tid);
+      sel_bins8<NONNEG, true>(v, tab, s_heavy, nh, u, bin, tcnt[base / 8]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&h[bin[i]], 1u);
+    }
+  } else {
+    for (int base = 0; base < per; base += 8) {
+      float v[8];
+      uint32_t u[8];
+      int bin[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(k + min((base + i) * kSelThreads + tid, count - 1));
+      uint32_t valid = 0u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) valid |= (uint32_t)((base + i) * kSelThreads + tid < count) << i;
+      sel_bins8<NONNEG, true>(v, tab, s_heavy, nh, u, bin, tcnt[base / 8], valid);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if ((valid >> i) & 1u) atomicAdd(&h[bin[i]], 1u);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kSelThreads) sel_fine_hist(const SelParams p) {
   __shared__ uint32_t h[kSelBins];
   __shared__ uint32_t s_heavy[kSelMaxHeavy];
@@ -290,43 +381,107 @@ __global__ void __launch_bounds__(kSelThreads) sel_fine_hist(const SelParams p) 
   if (start >= len) return;
   const SegPlan& pl = p.plan[g];
   const int nb = pl.nbins, nh = pl.nheavy;
+  constexpr int kTilesPerChunk = kSelChunk / kSelTile;
+  static_assert(kSelTile == 8 * kSelThreads, "one sel_bins8 call of the block covers one tile");
+  __shared__ uint32_t s_tcnt[kTilesPerChunk][kSelMaxHeavy];
   for (int i = threadIdx.x; i < nb; i += kSelThreads) h[i] = 0u;
   if (threadIdx.x < kSelMaxHeavy) s_heavy[threadIdx.x] = pl.heavy[threadIdx.x];
+  if (threadIdx.x < kTilesPerChunk * kSelMaxHeavy) (&s_tcnt[0][0])[threadIdx.x] = 0u;
   __syncthreads();
   const int count = (int)min((long long)kSelChunk, len - start);
   const float* k = p.keys[f] + lo + start;
   const uint32_t* tab = p.table + (size_t)g * kSelCoarse;
-  constexpr int per = kSelChunk / kSelThreads;
-  if (count == kSelChunk) {  // whole chunk: no clamps, no predicates
-    for (int base = 0; base < per; base += 8) {
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = __ldg(k + (base + i) * kSelThreads + (int)threadIdx.x);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t u = sort_key_from_float(v[i]);
-        atomicAdd(&h[sel_bin(u, __ldg(tab + (u >> kSelLowBits)), s_heavy, nh)], 1u);
-      }
-    }
-  } else {
-    for (int base = 0; base < per; base += 8) {
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = __ldg(k + min((base + i) * kSelThreads + (int)threadIdx.x, count - 1));
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if ((base + i) * kSelThreads + (int)threadIdx.x < count) {
-          const uint32_t u = sort_key_from_float(v[i]);
-          atomicAdd(&h[sel_bin(u, __ldg(tab + (u >> kSelLowBits)), s_heavy, nh)], 1u);
-        }
-    }
-  }
+  if ((pl.flags & 3) == 0) sel_fine_hist_body<true>(k, count, tab, s_heavy, nh, h, s_tcnt);
+  else sel_fine_hist_body<false>(k, count, tab, s_heavy, nh, h, s_tcnt);
   __syncthreads();
+  if (threadIdx.x < kTilesPerChunk * kSelMaxHeavy) {  // per-tile counts of every heavy tie value
+    const int tl = threadIdx.x / kSelMaxHeavy, hh = threadIdx.x % kSelMaxHeavy;
+    const int tile = blockIdx.x * kTilesPerChunk + tl;
+    if (hh < nh && (long long)tile * kSelTile < len)
+      p.tilecounts[((size_t)g * kSelMaxHeavy + hh) * p.max_tiles + tile] = s_tcnt[tl][hh];
+  }
   uint32_t* gh = p.hist_f + (size_t)g * kSelBins;
   for (int i = threadIdx.x; i < nb; i += kSelThreads) {
     const uint32_t v = h[i];
     if (v) atomicAdd(gh + i, v);
   }
+}
+
+// ---- plan of one tie group that holds cuts (tiled cell h of segment g): called by every thread of sel_locate's block
+template <int WARPS>
+__device__ __forceinline__ void sel_plan_tiled_cell(const SelParams& p, int g, int h) {
+  constexpr int kThreads = WARPS * 32;
+  __shared__ uint32_t warp_tmp[WARPS];
+  __shared__ int s_tstar[kSelMaxCuts];
+  __shared__ uint32_t s_rho[kSelMaxCuts];
+  const int tid = threadIdx.x;
+  SegPlan& pl = p.plan[g];
+  const int cell = pl.tcell[h];
+  int f, b;
+  long long lo, len;
+  sel_segment(p, g, f, b, lo, len);
+  const int ntiles = (int)((len + kSelTile - 1) / kSelTile);
+  uint32_t* row = p.tilecounts + ((size_t)g * kSelMaxHeavy + pl.theavy[h]) * p.max_tiles;
+  uint32_t carry = 0;
+  for (int base = 0; base < ntiles; base += kThreads) {
+    const int i = base + tid;
+    const uint32_t v = i < ntiles ? row[i] : 0u;
+    uint32_t tot;
+    const uint32_t ex = sel_block_excl_scan<WARPS>(v, warp_tmp, &tot);
+    if (i < ntiles) row[i] = carry + ex;
+    carry += tot;
+  }
+  __syncthreads();
+  const uint32_t cell_count = carry;  // == pl.cell_count[cell]
+  const int j0 = pl.cell_j0[cell], nj = pl.cell_j1[cell] - j0;  // nj <= kSelMaxCuts <= kThreads
+  uint8_t* mode = p.tilemode + (size_t)g * p.max_tiles * kSelMaxHeavy + h;
+  if (tid < nj) {
+    const uint32_t r = pl.cut_r[j0 + tid];  // 1 <= r < cell_count
+    int l = 0, hi = ntiles - 1;             // largest tile with row[tile] < r
+    while (l < hi) {
+      const int mid = (l + hi + 1) >> 1;
+      if (row[mid] < r) l = mid; else hi = mid - 1;
+    }
+    s_tstar[tid] = l;
+    s_rho[tid] = r - row[l];
+  }
+  __syncthreads();
+  for (int t = tid; t < ntiles; t += kThreads) {
+    int l = 0, hi = nj;  // number of cuts whose tile lies before t
+    while (l < hi) {
+      const int mid = (l + hi) >> 1;
+      if (s_tstar[mid] < t) l = mid + 1; else hi = mid;
+    }
+    const bool star = l < nj && s_tstar[l] == t;
+    mode[(size_t)t * kSelMaxHeavy] = star ? kSelCompact : (uint8_t)(j0 + l);
+  }
+  // the undecided tiles, in ascending order, share the cell's slot of the side list: the first record of a tile is
+  // the number of members in the undecided tiles before it (a scan over the cuts, one thread per cut)
+  bool fresh = false;
+  uint32_t raw = 0u;
+  int t = 0;
+  if (tid < nj) {
+    t = s_tstar[tid];
+    fresh = tid == 0 || s_tstar[tid - 1] != t;
+    raw = (t + 1 < ntiles ? row[t + 1] : cell_count) - row[t];  // members of the cut's tile
+  }
+  uint32_t acc;
+  const uint32_t ex = sel_block_excl_scan<WARPS>(fresh ? raw : 0u, warp_tmp, &acc);  // syncs: every row[] read above is done
+  if (tid < nj) {
+    const uint32_t cur = fresh ? ex : ex - raw;  // a cut that shares its tile with its predecessor: the tile's start
+    if (fresh) row[t] = cur;  // first record of this tile inside the cell's slot (what sel_classify reads)
+    pl.cut_posoff[j0 + tid] = cur + s_rho[tid];
+    RunDesc rd{};
+    rd.leader = fresh;
+    rd.cell = cell;
+    rd.j0 = j0;
+    rd.nj = nj;
+    rd.start = cur;
+    rd.len = raw;
+    pl.run[j0 + tid] = rd;
+  }
+  if (tid == 0) pl.cell_comp[cell] = acc;
+  __syncthreads();  // the shared arrays are reused by the next tie group
 }
 
 // ---- locate: one block of 1024 threads per segment -----------------------------------------------------------
@@ -465,6 +620,7 @@ __global__ void __launch_bounds__(kSelLocThreads) sel_locate(const SelParams p) 
       for (int w = 0; w < warp; ++w) ti += s_wc2[w];
       pl.tkey[ti] = pl.heavy[s_celltiled[cell]];
       pl.tcell[ti] = cell;
+      pl.theavy[ti] = s_celltiled[cell];
     }
     s_celltiled[cell] = ti;
     pl.cell_bin[cell] = s_cellbin[cell];
@@ -496,7 +652,7 @@ __global__ void __launch_bounds__(kSelLocThreads) sel_locate(const SelParams p) 
       rd.start = 0u;
       rd.len = s_cellcount[cell];
     }
-    if (cell < 0 || s_celltiled[cell] < 0) pl.run[tid] = rd;  // tiled cells: sel_plan_tiled writes their runs
+    if (cell < 0 || s_celltiled[cell] < 0) pl.run[tid] = rd;  // tiled cells: sel_plan_tiled_cell writes their runs
   }
   uint16_t* map = p.binmap + (size_t)g * kSelBins;
   for (int bin = tid; bin < nb; bin += kSelLocThreads) {
@@ -514,123 +670,10 @@ __global__ void __launch_bounds__(kSelLocThreads) sel_locate(const SelParams p) 
     if (a < ncells && s_cellbin[a] == bin) v = (uint16_t)(kSelCellFlag | a);
     map[bin] = v;
   }
-}
-
-// ---- ties: per-tile counts of the tie groups that hold a cut --------------------------------------------------
-__global__ void __launch_bounds__(kSelThreads) sel_tie_counts(const SelParams p) {
-  __shared__ uint32_t s_cnt[kSelMaxHeavy];
-  __shared__ uint32_t s_key[kSelMaxHeavy];
-  const int g = blockIdx.y, tid = threadIdx.x;
-  const SegPlan& pl = p.plan[g];
-  const int nt = pl.ntiled;
-  if (nt == 0) return;
-  int f, b;
-  long long lo, len;
-  sel_segment(p, g, f, b, lo, len);
-  const int t0 = blockIdx.x * p.tiles_per_block;
-  if ((long long)t0 * kSelTile >= len) return;
-  if (tid < kSelMaxHeavy) {
-    s_cnt[tid] = 0u;
-    s_key[tid] = tid < nt ? pl.tkey[tid] : 0xFFFFFFFFu;
-  }
-  __syncthreads();
-  const float* k = p.keys[f] + lo;
-  for (int tt = 0; tt < p.tiles_per_block; ++tt) {
-    const int t = t0 + tt;
-    const long long tile_lo = (long long)t * kSelTile;
-    if (tile_lo >= len) break;
-    const int count = (int)min((long long)kSelTile, len - tile_lo);
-    float v[kSelItems];
-#pragma unroll
-    for (int i = 0; i < kSelItems; ++i) v[i] = __ldg(k + tile_lo + min(i * kSelThreads + tid, count - 1));
-    for (int h = 0; h < nt; ++h) {
-      const uint32_t want = s_key[h];
-      uint32_t c = 0;
-#pragma unroll
-      for (int i = 0; i < kSelItems; ++i)
-        c += (i * kSelThreads + tid < count) && sort_key_from_float(v[i]) == want;
-      c = __reduce_add_sync(FULL_MASK, c);
-      if ((tid & 31) == 0 && c) atomicAdd(&s_cnt[h], c);
-    }
-    __syncthreads();
-    if (tid < nt) {
-      p.tilecounts[((size_t)g * kSelMaxHeavy + tid) * p.max_tiles + t] = s_cnt[tid];
-      s_cnt[tid] = 0u;
-    }
-    __syncthreads();
-  }
-}
-
-// ---- plan of the tie groups: one block per (tiled cell, segment) ------------------------------------------------
-__global__ void __launch_bounds__(kSelThreads) sel_plan_tiled(const SelParams p) {
-  __shared__ uint32_t warp_tmp[kSelWarps];
-  __shared__ int s_tstar[kSelMaxCuts];
-  __shared__ uint32_t s_rho[kSelMaxCuts];
-  const int h = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
-  SegPlan& pl = p.plan[g];
-  if (h >= pl.ntiled) return;
-  const int cell = pl.tcell[h];
-  int f, b;
-  long long lo, len;
-  sel_segment(p, g, f, b, lo, len);
-  const int ntiles = (int)((len + kSelTile - 1) / kSelTile);
-  uint32_t* row = p.tilecounts + ((size_t)g * kSelMaxHeavy + h) * p.max_tiles;
-  uint32_t carry = 0;
-  for (int base = 0; base < ntiles; base += kSelThreads) {
-    const int i = base + tid;
-    const uint32_t v = i < ntiles ? row[i] : 0u;
-    uint32_t tot;
-    const uint32_t ex = sel_block_excl_scan(v, warp_tmp, &tot);
-    if (i < ntiles) row[i] = carry + ex;
-    carry += tot;
-  }
-  __syncthreads();
-  const uint32_t cell_count = carry;  // == pl.cell_count[cell]
-  const int j0 = pl.cell_j0[cell], nj = pl.cell_j1[cell] - j0;
-  uint8_t* mode = p.tilemode + (size_t)g * p.max_tiles * kSelMaxHeavy + h;
-  for (int jj = tid; jj < nj; jj += kSelThreads) {
-    const uint32_t r = pl.cut_r[j0 + jj];  // 1 <= r < cell_count
-    int l = 0, hi = ntiles - 1;            // largest tile with row[tile] < r
-    while (l < hi) {
-      const int mid = (l + hi + 1) >> 1;
-      if (row[mid] < r) l = mid; else hi = mid - 1;
-    }
-    s_tstar[jj] = l;
-    s_rho[jj] = r - row[l];
-  }
-  __syncthreads();
-  for (int t = tid; t < ntiles; t += kSelThreads) {
-    int l = 0, hi = nj;  // number of cuts whose tile lies before t
-    while (l < hi) {
-      const int mid = (l + hi) >> 1;
-      if (s_tstar[mid] < t) l = mid + 1; else hi = mid;
-    }
-    const bool star = l < nj && s_tstar[l] == t;
-    mode[(size_t)t * kSelMaxHeavy] = star ? kSelCompact : (uint8_t)(j0 + l);
-  }
-  if (tid == 0) {
-    uint32_t acc = 0, cur = 0, raw = 0;
-    for (int jj = 0; jj < nj; ++jj) {
-      const bool fresh = jj == 0 || s_tstar[jj] != s_tstar[jj - 1];
-      if (fresh) {
-        const int t = s_tstar[jj];
-        cur = acc;
-        raw = (t + 1 < ntiles ? row[t + 1] : cell_count) - row[t];
-        acc += raw;
-        row[t] = cur;  // first record of this tile inside the cell's slot (tiles ascend: row[t + 1] is still a prefix)
-      }
-      pl.cut_posoff[j0 + jj] = cur + s_rho[jj];
-      RunDesc rd{};
-      rd.leader = fresh;
-      rd.cell = cell;
-      rd.j0 = j0;
-      rd.nj = nj;
-      rd.start = cur;
-      rd.len = raw;
-      pl.run[j0 + jj] = rd;
-    }
-    pl.cell_comp[cell] = acc;
-  }
+  // the tie groups that hold cuts (their per-tile counts come from the fine histogram pass)
+  __syncthreads();  // the plan fields written above are read back by other threads
+  const int ntiled = pl.ntiled;
+  for (int h = 0; h < ntiled; ++h) sel_plan_tiled_cell<kLocWarps>(p, g, h);
 }
 
 // first record of every cell's slot within the segment's side list (s_base[ncells] = all records) and the
@@ -647,66 +690,92 @@ __device__ __forceinline__ void sel_cell_bases(const SegPlan& pl, uint32_t* s_ba
 }
 
 // ---- classify: class sums of the decided elements, records of the undecided ones ---------------------------
+// Class sums without 64-bit shared-memory atomics (those are compare-and-swap loops: ATOMS.CAST.SPIN.64) and without
+// bank conflicts.  Per segment (or block) and payload array the largest finite magnitude fixes a scale
+// 2^(E - 186) (E = its biased exponent); a value whose lowest mantissa bit is a multiple of that scale -- everything
+// within 2^36 of the maximum -- is an exact integer q < 2^60, added as three 20-bit limbs with native 32-bit integer
+// atomics (exact, order-independent; zero limbs are skipped: a 24-bit mantissa touches two limbs, sometimes three).
+// Every (payload, limb, class) owns kSelCols words and a lane adds to column lane % kSelCols: lanes of one warp never
+// hit the same word unless they share class and column, and two classes collide on a bank only for the lane pair
+// (l, l + 16) -- two wavefronts per atomic instead of ~6 with one word per class -- so a tie group's thousands of
+// equal-class members need no special path.  A word sees at most 2 x 16384 / kSelCols = 2048 adds of < 2^20 (a lane
+// adds its own 8 keys of a tile or, for the general path, up to 8 queued ones of its warp: at most 16).  The few
+// values below the window, denormals, NaN and inf take the float64 compare-and-swap add.
+constexpr int kSelCols = 16;
+constexpr int kSelLimbBits = 20;
+constexpr uint32_t kSelLimbMask = (1u << kSelLimbBits) - 1u;
+constexpr int kSelWindow = 36;  // q = mantissa << (be - (emax - kSelWindow)) < 2^(24 + 36)
+static_assert(2 * (kSelMaxTilesPerBlock * kSelTile / kSelCols) <= (1 << (31 - kSelLimbBits)), "limb words cannot overflow");
+
 struct ClassifyShared {
-  uint16_t map[kSelBins];           // bin -> class or cell; the coarse table is read through L1 (__ldg): six blocks per SM
+  uint16_t map[kSelBins];           // bin -> class or kSelCellFlag | cell (undecided: a record); the bins of the tie
+                                    // groups are rewritten per tile; the coarse table is read through L1
   uint32_t heavy[kSelMaxHeavy];
   double sum[kSelMaxCuts + 1][2];
   uint32_t base[kSelMaxCuts + 1];
   int8_t tiled[kSelMaxCuts];        // cell -> tiled index or -1
   uint32_t slot[kSelMaxHeavy];      // first record of (tiled cell, tile) within the segment's side list
   uint32_t cur[kSelMaxHeavy];
-  uint8_t mode[kSelMaxHeavy];
+  uint16_t tbin[kSelMaxHeavy];      // bin of every tie-group cell
   uint32_t warp_tmp[kSelWarps];
   uint32_t hot;
-  int limb[kSelMaxCuts + 1][2][3];  // per-tile fixed-point class sums (3 x 16 bits), native 32-bit atomics
-  uint32_t vmax[2];                 // bits of the largest finite |payload| of the tile
+  uint32_t vmax[2];                 // bits of the largest finite |payload| of the block
+  uint32_t vneg;                    // a payload of the block is negative
+  uint32_t rqn[kSelWarps];          // per warp: positions queued for the general path
+  uint16_t rq[kSelWarps][kSelTile / kSelWarps];
 };
+// dynamic shared memory: int limb[2 payloads][3 limbs][num_cuts + 1 classes][kSelCols]
+__host__ __device__ inline size_t sel_limb_words(int num_cuts) { return (size_t)2 * 3 * (num_cuts + 1) * kSelCols; }
 
-// Class sums without 64-bit shared-memory atomics (those are compare-and-swap loops: ATOMS.CAST.SPIN.64).  Per
-// segment (or block) and payload array the largest finite magnitude fixes a scale 2^(E - 174) (E = its biased exponent); a value
-// whose lowest mantissa bit is a multiple of that scale -- everything within 2^24 of the maximum -- is an exact
-// integer q < 2^49 and is added as three 16-bit limbs with native integer atomics (exact, order-independent);
-// the few values below that, denormals, NaN and inf take the float64 compare-and-swap add.
-__device__ __forceinline__ void sel_add_payload(ClassifyShared& sh, int cls, int pidx, float v, int emax) {
+struct SelScale {
+  int lo_e, width, sh_e;  // q exists iff (unsigned)(be - lo_e) <= width; q = mantissa << (be - sh_e)
+};
+__device__ __forceinline__ SelScale sel_scale(int emax) {
+  SelScale s;
+  s.lo_e = emax >= 1 ? max(emax - kSelWindow, 1) : 1000;
+  s.width = emax >= 1 ? emax - s.lo_e : 0;
+  s.sh_e = emax - kSelWindow;
+  return s;
+}
+// the three limbs of a finite value inside the window (negated when the value is negative); `slow`: outside the
+// window and not zero.  SIGNED = false: the caller knows that no payload is negative (-0.0 lands outside the window
+// and adds nothing, like +0.0).
+template <bool SIGNED>
+__device__ __forceinline__ void sel_split(float v, const SelScale& sc, int (&l)[3], bool& fast, bool& slow) {
   const uint32_t bits = __float_as_uint(v);
-  const int be = (int)((bits >> 23) & 0xFFu);
-  if ((bits << 1) == 0u) return;  // +-0 adds nothing
-  if (be != 0 && be != 255 && be + 24 >= emax && be <= emax) {
-    long long q = (long long)((bits & 0x7FFFFFu) | 0x800000u) << (be + 24 - emax);
-    if (bits >> 31) q = -q;
-    atomicAdd(&sh.limb[cls][pidx][0], (int)(q & 0xFFFF));
-    atomicAdd(&sh.limb[cls][pidx][1], (int)((q >> 16) & 0xFFFF));
-    atomicAdd(&sh.limb[cls][pidx][2], (int)(q >> 32));
-  } else {
-    atomicAdd(&sh.sum[cls][pidx], (double)v);
+  const uint32_t be = SIGNED ? ((bits >> 23) & 0xFFu) : (bits >> 23);
+  fast = (uint32_t)(be - (uint32_t)sc.lo_e) <= (uint32_t)sc.width;
+  const uint32_t mant = (bits & 0x7FFFFFu) | 0x800000u;
+  const uint32_t sft = (be - (uint32_t)sc.sh_e) & 63u;  // in [0, 36] when fast (unused otherwise)
+  const unsigned long long q = (unsigned long long)mant << sft;
+  const uint32_t qlo = (uint32_t)q, qhi = (uint32_t)(q >> 32);
+  l[0] = (int)(qlo & kSelLimbMask);
+  l[1] = (int)(__funnelshift_r(qlo, qhi, kSelLimbBits) & kSelLimbMask);
+  l[2] = (int)(qhi >> (2 * kSelLimbBits - 32));
+  if (SIGNED && (int)bits < 0) {
+    l[0] = -l[0];
+    l[1] = -l[1];
+    l[2] = -l[2];
   }
+  slow = !fast && (bits << 1) != 0u;
+}
+// `w`: the word of (payload, limb 0, class, this lane's column); `stride`: words between limbs
+__device__ __forceinline__ void sel_add_limbs(int* w, int stride, const int (&l)[3]) {
+  if (l[0]) atomicAdd(w, l[0]);
+  if (l[1]) atomicAdd(w + stride, l[1]);
+  if (l[2]) atomicAdd(w + 2 * stride, l[2]);
 }
 
-template <int NPAY, bool SELF>
-__device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifyShared& sh, int g, int f, int b,
-                                                  long long lo, long long len) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  SegPlan& pl = p.plan[g];
-  const int ncells = pl.ncells, nc = p.num_cuts, nh = pl.nheavy, nt = pl.ntiled;
-  const int t0 = blockIdx.x * p.tiles_per_block;
-  {
-    const uint16_t* map = p.binmap + (size_t)g * kSelBins;
-    const int nb = pl.nbins;
-    for (int i = tid; i < nb; i += kSelThreads) sh.map[i] = map[i];
-    if (tid < kSelMaxHeavy) sh.heavy[tid] = pl.heavy[tid];
-  }
+// NONNEG: neither the keys nor the payloads of the segment hold a negative value or (the keys) a NaN -- known from
+// the coarse histograms -- which shortens the key transform and the fixed-point split.
+template <int NPAY, bool SELF, bool NONNEG>
+__device__ __forceinline__ void sel_classify_tiles(const SelParams& p, ClassifyShared& sh, int* limb, int g, int f,
+                                                   long long lo, long long len, int t0, const SelScale sc0,
+                                                   const SelScale sc1) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const SegPlan& pl = p.plan[g];
+  const int nh = pl.nheavy, nt = pl.ntiled;
   const uint32_t* tab = p.table + (size_t)g * kSelCoarse;
-  for (int i = tid; i < (kSelMaxCuts + 1) * 2; i += kSelThreads) (&sh.sum[0][0])[i] = 0.0;
-  for (int i = tid; i < (kSelMaxCuts + 1) * 6; i += kSelThreads) (&sh.limb[0][0][0])[i] = 0;
-  if (tid < 2) sh.vmax[tid] = 0u;
-  if (tid < kSelMaxCuts) sh.tiled[tid] = tid < ncells ? (int8_t)pl.cell_tiled[tid] : (int8_t)-1;
-  sel_cell_bases(pl, sh.base, sh.warp_tmp, &sh.hot);
-  if (blockIdx.x == 0 && tid < nc) {  // the resolve blocks find their slot without redoing the scan
-    const int cell = pl.cut_cell[tid];
-    if (cell >= 0) pl.run[tid].base = sh.base[cell];
-  }
-  const int hot = sh.hot ? (int)(sh.hot & 127u) : -1;
-  const int hot_t = hot >= 0 ? (int)sh.tiled[hot] : -1;
   const float* k = p.keys[f] + lo;
   const float* q0 = SELF ? nullptr : p.pay0[f] + lo;
   const float* q1 = NPAY == 2 ? p.pay1[f] + lo : nullptr;
@@ -718,36 +787,10 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
   uint32_t* cursor = p.cursor + (size_t)g * kSelMaxCuts;
   const uint8_t* modes = p.tilemode + (size_t)g * p.max_tiles * kSelMaxHeavy;
   const uint32_t* rows = p.tilecounts + (size_t)g * kSelMaxHeavy * p.max_tiles;
-
-  // scale of the fixed-point class sums: exponent of the largest finite magnitude of each payload array over
-  // the segment -- known from the coarse histogram when the payload is the key array of a family (the AUSE
-  // call: the errors are the keys of the two error-sorted families), else the largest of this block's keys
-  int emax0 = p.pay_src[f][0] >= 0 ? p.plan[p.pay_src[f][0] * p.num_views + b].emax : -1;
-  int emax1 = NPAY == 2 ? (p.pay_src[f][1] >= 0 ? p.plan[p.pay_src[f][1] * p.num_views + b].emax : -1) : 0;
-  if (emax0 < 0 || emax1 < 0) {  // uniform over the block
-    uint32_t m0 = 0u, m1 = 0u;
-    const long long blk_lo = (long long)t0 * kSelTile;
-    const long long blk_hi = min(len, blk_lo + (long long)p.tiles_per_block * kSelTile);
-    for (long long i = blk_lo + tid; i < blk_hi; i += kSelThreads) {
-      if (emax0 < 0) {
-        const uint32_t b0 = __float_as_uint(SELF ? k[i] : q0[i]) & 0x7FFFFFFFu;
-        if (b0 < 0x7F800000u) m0 = max(m0, b0);
-      }
-      if (NPAY == 2 && emax1 < 0) {
-        const uint32_t b1 = __float_as_uint(q1[i]) & 0x7FFFFFFFu;
-        if (b1 < 0x7F800000u) m1 = max(m1, b1);
-      }
-    }
-    m0 = __reduce_max_sync(FULL_MASK, m0);
-    m1 = __reduce_max_sync(FULL_MASK, m1);
-    if (lane == 0) {
-      if (m0) atomicMax(&sh.vmax[0], m0);
-      if (m1) atomicMax(&sh.vmax[1], m1);
-    }
-    __syncthreads();
-    if (emax0 < 0) emax0 = (int)(sh.vmax[0] >> 23);
-    if (emax1 < 0) emax1 = (int)(sh.vmax[1] >> 23);
-  }
+  uint16_t* rq = sh.rq[warp];
+  const int lstride = (p.num_cuts + 1) * kSelCols;  // words between the limbs of a payload
+  int* const col0 = limb + (lane & (kSelCols - 1));  // this lane's column of payload 0
+  int* const col1 = col0 + 3 * lstride;
 
   for (int tt = 0; tt < p.tiles_per_block; ++tt) {
     const int t = t0 + tt;
@@ -757,13 +800,48 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
     if (nt > 0) {  // per-tile tables of the tie groups (uniform over the block)
       __syncthreads();
       if (tid < nt) {
-        sh.mode[tid] = modes[(size_t)t * kSelMaxHeavy + tid];
-        sh.slot[tid] = sh.base[pl.tcell[tid]] + rows[(size_t)tid * p.max_tiles + t];
+        const uint8_t md = modes[(size_t)t * kSelMaxHeavy + tid];
+        const int cell = pl.tcell[tid];
+        sh.slot[tid] = sh.base[cell] + rows[(size_t)pl.theavy[tid] * p.max_tiles + t];
         sh.cur[tid] = 0u;
+        sh.map[sh.tbin[tid]] = md == kSelCompact ? (uint16_t)(kSelCellFlag | cell) : (uint16_t)md;
       }
+      __syncthreads();
     }
-    float kf[kSelItems], a0[kSelItems], a1[kSelItems];
+
+    // everything the fast pass does not cover -- an undecided element (a record of its cell), a payload outside the
+    // fixed-point window, every element of the segment's last, partial tile -- goes through this
+    auto general = [&](int pos) {
+      const float kv = k[tile_lo + pos];
+      const float v0 = SELF ? kv : q0[tile_lo + pos];
+      const float v1 = NPAY == 2 ? q1[tile_lo + pos] : 0.f;
+      const uint32_t key = sort_key_from_float(kv);
+      const uint16_t m = sh.map[sel_bin(key, __ldg(tab + (key >> kSelLowBits)), sh.heavy, nh)];
+      if (m & kSelCellFlag) {  // (any order: records are ranked by (key, index) later)
+        const int cell = m & 0x7FFF;
+        const int ti = sh.tiled[cell];
+        const uint32_t d = ti >= 0 ? sh.slot[ti] + atomicAdd(&sh.cur[ti], 1u)
+                                   : sh.base[cell] + atomicAdd(cursor + cell, 1u);
+        ck[d] = key;
+        ci[d] = (uint32_t)(tile_lo + pos);
+        if (!SELF) c0[d] = v0;
+        if (NPAY == 2) c1[d] = v1;
+      } else {
+        int l[3];
+        bool fast, slow;
+        sel_split<true>(v0, sc0, l, fast, slow);
+        if (fast) sel_add_limbs(col0 + (int)m * kSelCols, lstride, l);
+        else if (slow) atomicAdd(&sh.sum[m][0], (double)v0);
+        if (NPAY == 2) {
+          sel_split<true>(v1, sc1, l, fast, slow);
+          if (fast) sel_add_limbs(col1 + (int)m * kSelCols, lstride, l);
+          else if (slow) atomicAdd(&sh.sum[m][1], (double)v1);
+        }
+      }
+    };
+
     if (count == kSelTile) {
+      float kf[kSelItems], a0[kSelItems], a1[kSelItems];
 #pragma unroll
       for (int i = 0; i < kSelItems; ++i) kf[i] = __ldcs(k + tile_lo + i * kSelThreads + tid);
       if (!SELF) {
@@ -774,85 +852,154 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
 #pragma unroll
         for (int i = 0; i < kSelItems; ++i) a1[i] = __ldcs(q1 + tile_lo + i * kSelThreads + tid);
       }
+      static_assert(kSelItems == 8, "sel_bins8");
+      uint32_t key[kSelItems];
+      int bin[kSelItems];
+      sel_bins8<NONNEG>(kf, tab, sh.heavy, nh, key, bin);
+      uint32_t m[kSelItems];
+#pragma unroll
+      for (int i = 0; i < kSelItems; ++i) m[i] = sh.map[bin[i]];
+      uint32_t rare = 0u;
+#pragma unroll
+      for (int i = 0; i < kSelItems; ++i) {
+        int l0[3], l1[3];
+        bool fast0, slow0, fast1 = false, slow1 = false;
+        sel_split<!NONNEG>(SELF ? kf[i] : a0[i], sc0, l0, fast0, slow0);
+        if (NPAY == 2) sel_split<!NONNEG>(a1[i], sc1, l1, fast1, slow1);
+        const bool ok = !(m[i] & kSelCellFlag) && !slow0 && !slow1;
+        rare |= ok ? 0u : (1u << i);
+        if (ok && fast0) sel_add_limbs(col0 + (int)m[i] * kSelCols, lstride, l0);
+        if (NPAY == 2 && ok && fast1) sel_add_limbs(col1 + (int)m[i] * kSelCols, lstride, l1);
+      }
+      // queue the rare positions per warp, then run them through the general path with every lane busy
+      while (rare) {
+        const int i = __ffs((int)rare) - 1;
+        rare &= rare - 1u;
+        rq[atomicAdd(&sh.rqn[warp], 1u)] = (uint16_t)(i * kSelThreads + tid);
+      }
+      __syncwarp();
+      const int nq = (int)sh.rqn[warp];
+      for (int e = lane; e < nq; e += 32) general((int)rq[e]);
+      __syncwarp();
+      if (lane == 0) sh.rqn[warp] = 0u;
     } else {
-#pragma unroll
-      for (int i = 0; i < kSelItems; ++i) kf[i] = __ldcs(k + tile_lo + min(i * kSelThreads + tid, count - 1));
-      if (!SELF) {
-#pragma unroll
-        for (int i = 0; i < kSelItems; ++i) a0[i] = __ldcs(q0 + tile_lo + min(i * kSelThreads + tid, count - 1));
-      }
-      if (NPAY == 2) {
-#pragma unroll
-        for (int i = 0; i < kSelItems; ++i) a1[i] = __ldcs(q1 + tile_lo + min(i * kSelThreads + tid, count - 1));
-      }
-    }
-    if (nt > 0) __syncthreads();  // per-tile tables visible
-    const int hot_cls = hot_t >= 0 ? (int)sh.mode[hot_t] : (int)kSelCompact;
-    double hot0 = 0.0, hot1 = 0.0;
-#pragma unroll
-    for (int i = 0; i < kSelItems; ++i) {
-      const int pos = i * kSelThreads + tid;
-      if (pos < count) {
-        const uint32_t key = sort_key_from_float(kf[i]);
-        const uint16_t m = sh.map[sel_bin(key, __ldg(tab + (key >> kSelLowBits)), sh.heavy, nh)];
-        if (m & kSelCellFlag) {
-          const int cell = m & 0x7FFF;
-          const int ti = sh.tiled[cell];
-          const int cls = ti >= 0 ? (int)sh.mode[ti] : (int)kSelCompact;
-          if (cls == (int)kSelCompact) {
-            // undecided: a record in the cell's slot (any order: records are ranked by (key, index) later)
-            const uint32_t d = ti >= 0 ? sh.slot[ti] + atomicAdd(&sh.cur[ti], 1u)
-                                       : sh.base[cell] + atomicAdd(cursor + cell, 1u);
-            ck[d] = key;
-            ci[d] = (uint32_t)(tile_lo + pos);
-            if (!SELF) c0[d] = a0[i];
-            if (NPAY == 2) c1[d] = a1[i];
-          } else if (cell == hot) {  // the big tie group: one class per tile, summed in registers
-            hot0 += (double)(SELF ? kf[i] : a0[i]);
-            if (NPAY == 2) hot1 += (double)a1[i];
-          } else {
-            sel_add_payload(sh, cls, 0, SELF ? kf[i] : a0[i], emax0);
-            if (NPAY == 2) sel_add_payload(sh, cls, 1, a1[i], emax1);
-          }
-        } else {
-          sel_add_payload(sh, (int)m, 0, SELF ? kf[i] : a0[i], emax0);
-          if (NPAY == 2) sel_add_payload(sh, (int)m, 1, a1[i], emax1);
-        }
-      }
-    }
-    if (hot_t >= 0 && hot_cls != (int)kSelCompact) {  // uniform over the block
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        hot0 += shfl_xor_double(FULL_MASK, hot0, o);
-        if (NPAY == 2) hot1 += shfl_xor_double(FULL_MASK, hot1, o);
-      }
-      if (lane == 0) {
-        atomicAdd(&sh.sum[hot_cls][0], hot0);
-        if (NPAY == 2) atomicAdd(&sh.sum[hot_cls][1], hot1);
-      }
+      for (int pos = tid; pos < count; pos += kSelThreads) general(pos);
     }
   }
-  __syncthreads();  // all adds of the block done: fold the limbs into the float64 sums
+}
+
+template <int NPAY, bool SELF>
+__device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifyShared& sh, int* limb, int g, int f,
+                                                  int b, long long lo, long long len) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  SegPlan& pl = p.plan[g];
+  const int ncells = pl.ncells, nc = p.num_cuts;
+  const int t0 = blockIdx.x * p.tiles_per_block;
+  {
+    const uint16_t* map = p.binmap + (size_t)g * kSelBins;
+    const int nb = pl.nbins;
+    for (int i = tid; i < nb; i += kSelThreads) sh.map[i] = map[i];
+    if (tid < kSelMaxHeavy) {
+      sh.heavy[tid] = pl.heavy[tid];
+      sh.tbin[tid] = tid < pl.ntiled ? (uint16_t)pl.cell_bin[pl.tcell[tid]] : (uint16_t)0;
+    }
+  }
+  const int lwords = (int)sel_limb_words(nc) / (NPAY == 2 ? 1 : 2);  // one payload: only its half is used
+  for (int i = tid; i < (kSelMaxCuts + 1) * 2; i += kSelThreads) (&sh.sum[0][0])[i] = 0.0;
+  for (int i = tid; i < lwords / 4; i += kSelThreads) reinterpret_cast<int4*>(limb)[i] = make_int4(0, 0, 0, 0);
+  if (tid < 2) sh.vmax[tid] = 0u;
+  if (tid == 2) sh.vneg = 0u;
+  if (tid < kSelWarps) sh.rqn[tid] = 0u;
+  if (tid < kSelMaxCuts) sh.tiled[tid] = tid < ncells ? (int8_t)pl.cell_tiled[tid] : (int8_t)-1;
+  sel_cell_bases(pl, sh.base, sh.warp_tmp, &sh.hot);
+  if (blockIdx.x == 0 && tid < nc) {  // the resolve blocks find their slot without redoing the scan
+    const int cell = pl.cut_cell[tid];
+    if (cell >= 0) pl.run[tid].base = sh.base[cell];
+  }
+
+  // scale of the fixed-point class sums: exponent of the largest finite magnitude of each payload array over
+  // the segment -- known from the coarse histogram when the payload is the key array of a family (the AUSE
+  // call: the errors are the keys of the two error-sorted families), else the largest of this block's values;
+  // likewise whether any payload is negative
+  const int src0 = p.pay_src[f][0], src1 = NPAY == 2 ? p.pay_src[f][1] : 0;
+  int emax0 = src0 >= 0 ? p.plan[src0 * p.num_views + b].emax : -1;
+  int emax1 = NPAY == 2 ? (src1 >= 0 ? p.plan[src1 * p.num_views + b].emax : -1) : 0;
+  int neg = (pl.flags & 3) | (src0 >= 0 ? (p.plan[src0 * p.num_views + b].flags & 1) : 0);
+  if (NPAY == 2 && src1 >= 0) neg |= p.plan[src1 * p.num_views + b].flags & 1;
+  if (emax0 < 0 || emax1 < 0) {  // uniform over the block
+    const float* k = p.keys[f] + lo;
+    const float* q0 = SELF ? nullptr : p.pay0[f] + lo;
+    const float* q1 = NPAY == 2 ? p.pay1[f] + lo : nullptr;
+    uint32_t m0 = 0u, m1 = 0u, sg = 0u;
+    const long long blk_lo = (long long)t0 * kSelTile;
+    const long long blk_hi = min(len, blk_lo + (long long)p.tiles_per_block * kSelTile);
+    for (long long i = blk_lo + tid; i < blk_hi; i += kSelThreads) {
+      if (emax0 < 0) {
+        const uint32_t w = __float_as_uint(SELF ? k[i] : q0[i]);
+        const uint32_t b0 = w & 0x7FFFFFFFu;
+        if (b0 < 0x7F800000u) m0 = max(m0, b0);
+        sg |= w;
+      }
+      if (NPAY == 2 && emax1 < 0) {
+        const uint32_t w = __float_as_uint(q1[i]);
+        const uint32_t b1 = w & 0x7FFFFFFFu;
+        if (b1 < 0x7F800000u) m1 = max(m1, b1);
+        sg |= w;
+      }
+    }
+    m0 = __reduce_max_sync(FULL_MASK, m0);
+    m1 = __reduce_max_sync(FULL_MASK, m1);
+    sg = __reduce_or_sync(FULL_MASK, sg);
+    if (lane == 0) {
+      if (m0) atomicMax(&sh.vmax[0], m0);
+      if (m1) atomicMax(&sh.vmax[1], m1);
+      if (sg >> 31) sh.vneg = 1u;
+    }
+    __syncthreads();
+    if (emax0 < 0) emax0 = (int)(sh.vmax[0] >> 23);
+    if (emax1 < 0) emax1 = (int)(sh.vmax[1] >> 23);
+    neg |= (int)sh.vneg;
+  }
+  const SelScale sc0 = sel_scale(emax0), sc1 = sel_scale(emax1);
+  if (neg == 0) sel_classify_tiles<NPAY, SELF, true>(p, sh, limb, g, f, lo, len, t0, sc0, sc1);
+  else sel_classify_tiles<NPAY, SELF, false>(p, sh, limb, g, f, lo, len, t0, sc0, sc1);
+
+  __syncthreads();  // all adds of the block done: fold the limb columns into the float64 sums
   double* sp = p.spart + ((size_t)g * p.max_blocks + blockIdx.x) * (size_t)(nc + 1) * 2;
+  const int lstride = (nc + 1) * kSelCols;
   for (int i = tid; i < (nc + 1) * 2; i += kSelThreads) {
-    const int* l = &sh.limb[0][0][0] + i * 3;
-    const long long tot = ((long long)l[2] << 32) + ((long long)l[1] << 16) + (long long)l[0];
+    const int cls = i >> 1, pidx = i & 1;
     double v = (&sh.sum[0][0])[i];
-    if (tot != 0) v += ldexp((double)tot, ((i & 1) ? emax1 : emax0) - 174);
+    if (pidx < NPAY) {
+      const int* w = limb + pidx * 3 * lstride + cls * kSelCols;
+      long long t0s = 0, t1s = 0, t2s = 0;
+#pragma unroll
+      for (int c = 0; c < kSelCols; ++c) {
+        const int cc = (c + tid) & (kSelCols - 1);  // threads start at different columns: no bank conflict
+        t0s += w[cc];
+        t1s += w[lstride + cc];
+        t2s += w[2 * lstride + cc];
+      }
+      // q total = t0 + t1 2^20 + t2 2^40 (|.| < 2^14 2^60 may exceed 64 bits: add as three exactly scaled doubles)
+      const int e = (pidx ? emax1 : emax0) - 150 - kSelWindow;
+      if (t0s | t1s | t2s)
+        v += ldexp((double)t0s, e) + ldexp((double)t1s, e + kSelLimbBits) + ldexp((double)t2s, e + 2 * kSelLimbBits);
+    }
     sp[i] = v;
   }
 }
 
-__global__ void __launch_bounds__(kSelThreads, 6) sel_classify(const SelParams p) {
+__global__ void __launch_bounds__(kSelThreads, 3) sel_classify(const SelParams p) {
   __shared__ ClassifyShared sh;
+  extern __shared__ __align__(16) int sel_limb_smem[];
   const int g = blockIdx.y;
   int f, b;
   long long lo, len;
   sel_segment(p, g, f, b, lo, len);
   if ((long long)blockIdx.x * p.tiles_per_block * kSelTile >= len) return;
-  if (p.self_payload[f]) sel_classify_body<1, true>(p, sh, g, f, b, lo, len);
-  else if (p.pay1[f]) sel_classify_body<2, false>(p, sh, g, f, b, lo, len);
-  else sel_classify_body<1, false>(p, sh, g, f, b, lo, len);
+  if (p.self_payload[f]) sel_classify_body<1, true>(p, sh, sel_limb_smem, g, f, b, lo, len);
+  else if (p.pay1[f]) sel_classify_body<2, false>(p, sh, sel_limb_smem, g, f, b, lo, len);
+  else sel_classify_body<1, false>(p, sh, sel_limb_smem, g, f, b, lo, len);
 }
 
 // ---- resolve: exact class of every record, one block per run of records ------------------------------------
@@ -1048,13 +1195,16 @@ __global__ void __launch_bounds__(kSelResThreads) sel_resolve(const SelParams p)
   }
 }
 
-// ---- finish: class sums -> sums under every cut, one block per segment ---------------------------------------
-constexpr int kSelFinThreads = 1024;
-__global__ void __launch_bounds__(kSelFinThreads) sel_finish(const SelParams p) {
-  constexpr int kSlices = kSelFinThreads / 256;
-  __shared__ double s_part[kSlices][(kSelMaxCuts + 1) * 2];
-  __shared__ double s_tot[(kSelMaxCuts + 1) * 2];
-  const int g = blockIdx.x, tid = threadIdx.x, nc = p.num_cuts;
+// ---- finish: class sums -> sums under every cut ------------------------------------------------------------------
+// kSelFinGroups blocks per segment each add a fixed share of the classify blocks' partial sums (block r: partials
+// r, r + kSelFinGroups, ..., eight loads in flight); the last of them to arrive adds the group totals and the
+// record sums in a fixed order and runs the prefix over the classes.  Deterministic: no sum depends on arrival order.
+constexpr int kSelFinGroups = 8;
+constexpr int kSelFinStride = (kSelMaxCuts + 1) * 2;
+__global__ void __launch_bounds__(kSelThreads) sel_finish(const SelParams p) {
+  __shared__ double s_tot[kSelFinStride];
+  __shared__ uint32_t s_last;
+  const int r = blockIdx.x, g = blockIdx.y, tid = threadIdx.x, nc = p.num_cuts;
   int f, b;
   long long lo, len;
   sel_segment(p, g, f, b, lo, len);
@@ -1062,43 +1212,58 @@ __global__ void __launch_bounds__(kSelFinThreads) sel_finish(const SelParams p) 
   const int nblk = (ntiles + p.tiles_per_block - 1) / p.tiles_per_block;
   const int stride = (nc + 1) * 2;
   const double* sp = p.spart + (size_t)g * p.max_blocks * stride;
-  const double* gs = p.ssum + (size_t)g * (kSelMaxCuts + 1) * 2;
-  const int slice = tid >> 8;
-  for (int i = tid & 255; i < stride; i += 256) {  // slice s adds blocks s, s + kSlices, ... (8 loads in flight)
+  double* fp = p.fpart + (size_t)g * kSelFinGroups * kSelFinStride;
+  for (int i = tid; i < stride; i += kSelThreads) {
     double s = 0.0;
-    for (int blk0 = slice; blk0 < nblk; blk0 += 8 * kSlices) {
+    for (int blk0 = r; blk0 < nblk; blk0 += 8 * kSelFinGroups) {
       double v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int blk = blk0 + u * kSlices;
+        const int blk = blk0 + u * kSelFinGroups;
         v[u] = blk < nblk ? sp[(size_t)blk * stride + i] : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) s += v[u];
     }
-    s_part[slice][i] = s;
+    fp[(size_t)r * kSelFinStride + i] = s;
   }
+  __threadfence();
   __syncthreads();
-  for (int i = tid; i < stride; i += kSelFinThreads) {
+  if (tid == 0) s_last = atomicAdd(p.fcount + g, 1u) == (uint32_t)(kSelFinGroups - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double* gs = p.ssum + (size_t)g * (kSelMaxCuts + 1) * 2;
+  for (int i = tid; i < stride; i += kSelThreads) {
     double s = gs[i];
 #pragma unroll
-    for (int q = 0; q < kSlices; ++q) s += s_part[q][i];
+    for (int q = 0; q < kSelFinGroups; ++q) s += __ldcg(fp + (size_t)q * kSelFinStride + i);
     s_tot[i] = s;
   }
   __syncthreads();
+  // prefix over the classes: warp w scans payload w (32 cuts per round, fixed shuffle order)
   const SegPlan& pl = p.plan[g];
-  if (tid < p.npay[f]) {
-    double run = 0.0;
-    double* out = p.out + ((size_t)b * p.num_values + p.row0[f] + tid) * nc;
-    for (int j = 0; j < nc; ++j) {
-      run += s_tot[j * 2 + tid];
-      out[pl.cut_k[j]] = run;
+  const int w = tid >> 5, lane = tid & 31;
+  if (w < p.npay[f]) {
+    double* out = p.out + ((size_t)b * p.num_values + p.row0[f] + w) * nc;
+    double carry = 0.0;
+    for (int j0 = 0; j0 < nc; j0 += 32) {
+      const int j = j0 + lane;
+      double v = j < nc ? s_tot[j * 2 + w] : 0.0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double u = shfl_up_double(FULL_MASK, v, o);
+        if (lane >= o) v += u;
+      }
+      v += carry;
+      if (j < nc) out[pl.cut_k[j]] = v;
+      carry = shfl_double(FULL_MASK, v, 31);
     }
   }
 }
 
 struct SelLayout {
-  size_t off_zero, zero_bytes, off_histc, off_histf, off_cursor, off_ssum;
+  size_t off_zero, zero_bytes, off_histc, off_histf, off_cursor, off_ssum, off_fcount, off_fpart;
   size_t off_table, off_plan, off_binmap, off_tilecounts, off_tilemode, off_spart, off_ckeys, off_cidx, off_cpay,
       total;
   int max_tiles, max_blocks, tiles_per_block, G;
@@ -1109,9 +1274,11 @@ static SelLayout sel_layout(int F, int B, int num_cuts, int num_side_arrays, lon
   l.G = F * B;
   l.max_tiles = (int)((max_len + kSelTile - 1) / kSelTile);
   if (l.max_tiles < 1) l.max_tiles = 1;
-  // blocks of the counting / classifying passes: enough of them to fill the device, each as long as that
-  // allows (a block stages 50 KB of binning tables)
-  long long tpb = (long long)l.max_tiles * l.G / 600;
+  // blocks of the classifying pass: as long as possible (a block stages, zeroes and folds ~60 KB of tables) while one
+  // wave of them -- three blocks per SM -- still covers the call; eight tiles each once the call is larger than that
+  const int sms = sm_count();
+  const long long slots = 3LL * (sms > 0 ? sms : 148);
+  long long tpb = ((long long)l.max_tiles * l.G + slots - 1) / slots;
   l.tiles_per_block = (int)(tpb < 1 ? 1 : tpb > kSelMaxTilesPerBlock ? kSelMaxTilesPerBlock : tpb);
   l.max_blocks = (l.max_tiles + l.tiles_per_block - 1) / l.tiles_per_block;
   const size_t G = (size_t)l.G;
@@ -1126,7 +1293,9 @@ static SelLayout sel_layout(int F, int B, int num_cuts, int num_side_arrays, lon
   l.off_histf = take(G * kSelBins * sizeof(uint32_t));
   l.off_cursor = take(G * kSelMaxCuts * sizeof(uint32_t));
   l.off_ssum = take(G * (kSelMaxCuts + 1) * 2 * sizeof(double));
+  l.off_fcount = take(G * sizeof(uint32_t));
   l.zero_bytes = o - l.off_zero;
+  l.off_fpart = take(G * (size_t)kSelFinGroups * kSelFinStride * sizeof(double));
   l.off_table = take(G * kSelCoarse * sizeof(uint32_t));
   l.off_plan = take(G * sizeof(SegPlan));
   l.off_binmap = take(G * kSelBins * sizeof(uint16_t));
@@ -1223,6 +1392,8 @@ int ub_cut_select_sums_ex(const float* const* keys_host, const float* const* pay
   p.tilecounts = reinterpret_cast<uint32_t*>(ws + lay.off_tilecounts);
   p.tilemode = reinterpret_cast<uint8_t*>(ws + lay.off_tilemode);
   p.spart = reinterpret_cast<double*>(ws + lay.off_spart);
+  p.fpart = reinterpret_cast<double*>(ws + lay.off_fpart);
+  p.fcount = reinterpret_cast<uint32_t*>(ws + lay.off_fcount);
   p.ckeys = reinterpret_cast<uint32_t*>(ws + lay.off_ckeys);
   p.cidx = reinterpret_cast<uint32_t*>(ws + lay.off_cidx);
   float* cpay = reinterpret_cast<float*>(ws + lay.off_cpay);
@@ -1245,14 +1416,25 @@ int ub_cut_select_sums_ex(const float* const* keys_host, const float* const* pay
     p.hist_c = const_cast<uint32_t*>(coarse_hist);  // read-only from here on (sel_alloc)
   else
     sel_coarse_hist<<<grid_chunks, kSelThreads, 0, stream>>>(p);
-  sel_alloc<<<G, kSelThreads, 0, stream>>>(p);
+  sel_alloc<<<G, kSelAllocThreads, 0, stream>>>(p);
   sel_fine_hist<<<grid_chunks, kSelThreads, 0, stream>>>(p);
   sel_locate<<<G, kSelLocThreads, 0, stream>>>(p);
-  sel_tie_counts<<<grid_blocks, kSelThreads, 0, stream>>>(p);
-  sel_plan_tiled<<<dim3(kSelMaxHeavy, (unsigned)G), kSelThreads, 0, stream>>>(p);
-  sel_classify<<<grid_blocks, kSelThreads, 0, stream>>>(p);
+  {
+    const size_t limb_bytes = sel_limb_words(num_cuts) * sizeof(int);
+    // opt in to > 48 KB of shared memory, once per device (an idempotent kernel attribute, not library state)
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      if (cudaFuncSetAttribute(sel_classify, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(sel_limb_words(kSelMaxCuts) * sizeof(int))) != cudaSuccess)
+        return check_launch("cut_select_sums smem attribute");
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    sel_classify<<<grid_blocks, kSelThreads, limb_bytes, stream>>>(p);
+  }
   sel_resolve<<<grid_cells, kSelResThreads, 0, stream>>>(p);
-  sel_finish<<<G, kSelFinThreads, 0, stream>>>(p);
+  sel_finish<<<dim3(kSelFinGroups, (unsigned)G), kSelThreads, 0, stream>>>(p);
   return check_launch("cut_select_sums");
 }
 

@@ -31,6 +31,7 @@ _Z_CACHE: Dict[str, Tensor] = {}
 
 _RATIOS = np.linspace(0, 1, 100, endpoint=False)  # ause.py:8
 _RATIOS.setflags(write=False)
+N_RATIOS = len(_RATIOS)
 
 
 def _ratios() -> np.ndarray:
@@ -153,18 +154,24 @@ def _use_select(max_len: int) -> bool:
     return os.environ.get("UB_AUSE_SORT", "0") != "1" and max_len <= _SELECT_MAX_LEN
 
 
-def _ause_sums(vec: Tensor, lens, cuts: np.ndarray, coarse: Optional[Tensor] = None) -> Tensor:
+def _ause_sums(vec: Tensor, lens, cuts: np.ndarray, coarse: Optional[Tensor] = None,
+               out: Optional[Tensor] = None) -> Tensor:
     """``[B, 4, ncuts]`` float64: payload sums under every cut for (abs err by var, sq err by var, abs err
     ascending, sq err ascending) from the prologue's ``[3, total]`` buffer (var, abs err, sq err); ``coarse``: the
-    prologue's key histograms of those three vectors, in that order."""
+    prologue's key histograms of those three vectors, in that order; ``out``: where to write them."""
     ae, se = vec[1], vec[2]
     if _use_select(max(lens) if len(lens) else 0):
-        return ops.cut_select_sums([(vec[0], ae, se), (ae, ae, None), (se, se, None)], lens, cuts, coarse=coarse)
+        return ops.cut_select_sums([(vec[0], ae, se), (ae, ae, None), (se, se, None)], lens, cuts, coarse=coarse,
+                                   out=out)
     total = vec.shape[1]
     sorted_all, perm_all = ops.segmented_sort(vec.reshape(-1), list(lens) * 3, want_perm=True, want_keys=True)
     perm_var = perm_all[:total]
-    return ops.cut_prefix_sums([ae, se, sorted_all[total:2 * total], sorted_all[2 * total:]],
+    sums = ops.cut_prefix_sums([ae, se, sorted_all[total:2 * total], sorted_all[2 * total:]],
                                [perm_var, perm_var, None, None], lens, cuts)
+    if out is not None:
+        out.copy_(sums)
+        return out
+    return sums
 
 
 def _check_err_type(err_type: str) -> None:
@@ -265,9 +272,10 @@ def auce(mean_values: ArrayLike, sigma_values: ArrayLike, target_values: ArrayLi
 
 
 def _score_rgb_device(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb_std_for_nll: float):
-    """The device half of ``score_rgb_batch``: prologue (+ AUCE histogram, NLL), AUSE slice sums, and the packing of
-    everything the host tail needs into one ``[B, 505]`` float64 tensor.  Enqueue-only (CUDA-graph capturable once
-    the segment / cut tables of the shape are cached)."""
+    """The device half of ``score_rgb_batch``: prologue (+ AUCE histogram, NLL) and AUSE slice sums, every kernel
+    writing straight into its region of ONE packed float64 buffer (``B x 400`` curve sums | ``B x 5`` scalar sums |
+    ``B x (nz + 1)`` histogram rows, int64 bit patterns) that the host tail reads back with a single copy.
+    Enqueue-only (CUDA-graph capturable once the segment / cut tables of the shape are cached)."""
     if rgb_pred.dim() == 3:
         rgb_pred, rgb_gt, rgb_std = rgb_pred[None], rgb_gt[None], rgb_std[None]
     b, h, w, c = rgb_pred.shape
@@ -275,15 +283,24 @@ def _score_rgb_device(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb
     lens = [n] * b
     z = _z_table(rgb_pred.device)
     select = _use_select(n)
+    nzp = z.numel() + 1
+    packed_dev = torch.empty(b * (4 * N_RATIOS + 5 + nzp), dtype=torch.float64, device=rgb_pred.device)
+    sums_v, psum_v, hist_v = _packed_views(packed_dev, b, nzp)
     pro = ops.score_prologue(rgb_pred.reshape(-1, c), rgb_gt.reshape(-1, c), rgb_std.reshape(-1), lens, z,
                              nll_min_std=min_rgb_std_for_nll, sigma_from_var=True, want_vectors=True,
-                             want_coarse=select)
+                             want_coarse=select, out_sums=psum_v, out_hist=hist_v.view(torch.int64))
     vec = pro["vectors"]                                   # [3, total]: var, abs err, sq err
     cuts_one = ause_cut_counts(n)
     cuts = _tiled_cuts(n, b)
-    sums = _ause_sums(vec, lens, cuts, pro.get("coarse"))                             # [B, 4, 100]
-    packed_dev = torch.cat([sums.reshape(b, -1), pro["sums"], pro["hist"].to(torch.float64)], dim=1)
+    _ause_sums(vec, lens, cuts, pro.get("coarse"), out=sums_v)                        # [B, 4, 100]
     return packed_dev, b, n, c, cuts_one
+
+
+def _packed_views(packed, b: int, nzp: int):
+    """The three regions of the packed score buffer (torch tensor or numpy array): ``[B, 4, 100]`` curve sums,
+    ``[B, 5]`` scalar sums, ``[B, nz + 1]`` histogram rows (float64 storage holding int64 bit patterns)."""
+    s0, s1 = b * 4 * N_RATIOS, b * (4 * N_RATIOS + 5)
+    return packed[:s0].reshape(b, 4, N_RATIOS), packed[s0:s1].reshape(b, 5), packed[s1:].reshape(b, nzp)
 
 
 _TILED: Dict[Tuple[int, int], np.ndarray] = {}
@@ -337,9 +354,9 @@ class PendingScores:
         packed = self.packed_host.numpy()
         b, n, c, cuts_one = self.b, self.n, self.c, self.cuts_one
         zh = z_values_host()
-        bu_ae, bu_se, or_ae, or_se = packed[:, 0:100], packed[:, 100:200], packed[:, 200:300], packed[:, 300:400]
-        psums = packed[:, 400:405]
-        hist = np.rint(packed[:, 405:405 + len(zh) + 1]).astype(np.int64)
+        sums_v, psums, hist_v = _packed_views(packed, b, len(zh) + 1)
+        bu_ae, bu_se, or_ae, or_se = sums_v[:, 0], sums_v[:, 1], sums_v[:, 2], sums_v[:, 3]
+        hist = np.ascontiguousarray(hist_v).view(np.int64)
         # all twelve curves of the batch in three numpy expressions: rows = (image, {mae, mse, rmse})
         ora = _prefix_means(np.stack([or_ae, or_se, or_se], axis=1), cuts_one, "mae")      # [B, 3, 100] float32
         byu = _prefix_means(np.stack([bu_ae, bu_se, bu_se], axis=1), cuts_one, "mae")

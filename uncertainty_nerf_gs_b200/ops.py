@@ -444,11 +444,22 @@ class Segments:
         return t
 
 
+def _own_or_new(t: Optional[Tensor], shape, dtype, device, name: str) -> Tensor:
+    if t is None:
+        return torch.empty(*shape, dtype=dtype, device=device)
+    if tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != device or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous {dtype} tensor of shape {tuple(shape)} on {device}")
+    return t
+
+
 def score_prologue(pred: Tensor, target: Tensor, std: Tensor, seg_lengths: Sequence[int], z_values: Tensor,
                    nll_min_std: float, sigma_from_var: bool = True, want_vectors: bool = True,
-                   want_coarse: bool = False) -> Dict[str, Tensor]:
+                   want_coarse: bool = False, out_sums: Optional[Tensor] = None,
+                   out_hist: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """se / ae / var vectors, float64 sums and the AUCE interval histogram for a batch of images.
     ``pred, target [N, C]``, ``std [N]``; images are consecutive segments of ``seg_lengths`` pixels.
+    ``out_sums [nseg, 5]`` float64 / ``out_hist [nseg, nz + 1]`` int64: caller-owned contiguous outputs (e.g. slices
+    of one packed result buffer) instead of fresh tensors.
     ``want_coarse``: also ``coarse [3, nseg, 4096]`` uint32 (as int32 storage), the top-12-bit key histograms of the
     three vectors that ``cut_select_sums(..., coarse=...)`` would otherwise compute with a pass of its own."""
     lib = _lib.load()
@@ -468,8 +479,8 @@ def score_prologue(pred: Tensor, target: Tensor, std: Tensor, seg_lengths: Seque
     dev = pred.device
     nseg, nz = seg.num, z_values.numel()
     out: Dict[str, Tensor] = {
-        "sums": torch.empty(nseg, _lib.UB_PROLOGUE_NSUMS, dtype=torch.float64, device=dev),
-        "hist": torch.empty(nseg, nz + 1, dtype=torch.int64, device=dev),
+        "sums": _own_or_new(out_sums, (nseg, _lib.UB_PROLOGUE_NSUMS), torch.float64, dev, "out_sums"),
+        "hist": _own_or_new(out_hist, (nseg, nz + 1), torch.int64, dev, "out_hist"),
     }
     if want_vectors:
         # one [3, N] buffer (var, abs err, sq err) so that the three AUSE sorts run as one segmented sort
@@ -492,7 +503,7 @@ def score_prologue(pred: Tensor, target: Tensor, std: Tensor, seg_lengths: Seque
     ws = _workspace(lib.ub_score_prologue_workspace_bytes(nseg, seg.max_len, nz), dev)
     with _guard(dev):
         _lib.check(lib.ub_score_prologue(C.byref(args), ws.data_ptr(), ws.numel(), _stream()))
-    _count(3)  # ratio table, prologue, finalize
+    _count(2)  # ratio table, prologue (its last block per segment folds the partial sums)
     return out
 
 
@@ -552,14 +563,15 @@ def cut_prefix_sums(values: Sequence[Tensor], perms: Union[None, Tensor, Sequenc
 
 
 def cut_select_sums(families: Sequence[Tuple[Tensor, Tensor, Optional[Tensor]]], seg_lengths: Sequence[int],
-                    cuts: np.ndarray, coarse: Optional[Tensor] = None) -> Tensor:
+                    cuts: np.ndarray, coarse: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
     """float64 sums of the payloads over the first ``cuts[s, c]`` elements of the stable ascending order of
     the keys, without sorting (``ub_cut_select_sums``): equal to ``segmented_sort`` + ``cut_prefix_sums`` up
     to float64 summation order.  ``families``: ``(keys, payload0, payload1 or None)`` triples of ``[total]``
     float32 tensors sharing the segmentation; ``payload0 is keys`` (same storage) sums the sorted keys.
     Returns ``[nseg, V, ncuts]`` with one row per payload array in family order.
     ``coarse [num_families, nseg, 4096]`` (int32 storage): the top-12-bit key histograms, when the producer of the
-    keys already has them (``score_prologue(want_coarse=True)``)."""
+    keys already has them (``score_prologue(want_coarse=True)``).  ``out``: caller-owned contiguous
+    ``[nseg, V, ncuts]`` float64 output."""
     lib = _lib.load()
     fams = []
     for i, (k, p0, p1) in enumerate(families):
@@ -576,7 +588,7 @@ def cut_select_sums(families: Sequence[Tuple[Tensor, Tensor, Optional[Tensor]]],
     cuts_dev = seg.cuts_device(cuts)
     nseg, ncuts, nf = seg.num, cuts_dev.shape[1], len(fams)
     nrows = sum(1 if p1 is None else 2 for _, _, p1 in fams)
-    out = torch.empty(nseg, nrows, ncuts, dtype=torch.float64, device=dev)
+    out = _own_or_new(out, (nseg, nrows, ncuts), torch.float64, dev, "out")
     kp = (C.c_void_p * nf)(*[k.data_ptr() for k, _, _ in fams])
     p0p = (C.c_void_p * nf)(*[p0.data_ptr() for _, p0, _ in fams])
     p1p = (C.c_void_p * nf)(*[_ptr(p1) for _, _, p1 in fams])
@@ -589,7 +601,7 @@ def cut_select_sums(families: Sequence[Tuple[Tensor, Tensor, Optional[Tensor]]],
         _lib.check(lib.ub_cut_select_sums_ex(kp, p0p, p1p, nf, nseg, seg.offsets.data_ptr(), total, seg.max_len,
                                              cuts_dev.data_ptr(), ncuts, _ptr(coarse), out.data_ptr(), ws.data_ptr(),
                                              ws.numel(), _stream()))
-    _count(9 if coarse is None else 8)
+    _count(7 if coarse is None else 6)  # [coarse], alloc, fine, locate, classify, resolve, finish
     return out
 
 
