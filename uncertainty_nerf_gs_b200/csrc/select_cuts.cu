@@ -690,33 +690,33 @@ __device__ __forceinline__ void sel_cell_bases(const SegPlan& pl, uint32_t* s_ba
 }
 
 // ---- classify: class sums of the decided elements, records of the undecided ones ---------------------------
-// Class sums without 64-bit shared-memory atomics (those are compare-and-swap loops: ATOMS.CAST.SPIN.64) and without
-// bank conflicts.  Per segment (or block) and payload array the largest finite magnitude fixes a scale
-// 2^(E - 186) (E = its biased exponent); a value whose lowest mantissa bit is a multiple of that scale -- everything
-// within 2^36 of the maximum -- is an exact integer q < 2^60, added as three 20-bit limbs with native 32-bit integer
-// atomics (exact, order-independent; zero limbs are skipped: a 24-bit mantissa touches two limbs, sometimes three).
-// Every (payload, limb, class) owns kSelCols words and a lane adds to column lane % kSelCols: lanes of one warp never
-// hit the same word unless they share class and column, and two classes collide on a bank only for the lane pair
-// (l, l + 16) -- two wavefronts per atomic instead of ~6 with one word per class -- so a tie group's thousands of
-// equal-class members need no special path.  A word sees at most 2 x 16384 / kSelCols = 2048 adds of < 2^20 (a lane
-// adds its own 8 keys of a tile or, for the general path, up to 8 queued ones of its warp: at most 16).  The few
-// values below the window, denormals, NaN and inf take the float64 compare-and-swap add.
-constexpr int kSelCols = 16;
-constexpr int kSelLimbBits = 20;
+// Class sums without 64-bit shared-memory atomics (those are compare-and-swap loops: ATOMS.CAST.SPIN.64).  Per segment
+// (or block) and payload array the largest finite magnitude fixes a scale 2^(E - 150 - kSelWindow) (E = its biased
+// exponent); a value whose lowest mantissa bit is a multiple of that scale -- everything within 2^33 of the maximum
+// -- is an exact integer q < 2^57, added as three 19-bit limbs with native 32-bit integer reductions (exact,
+// order-independent).  Every (payload, limb, class) owns kSelCols words and a lane adds to column lane % kSelCols,
+// which spreads the members of one class -- a tie group's thousands of equal-class keys included -- over kSelCols
+// words and consecutive classes over the banks.  A word sees at most 2 x 16384 / kSelCols = 4096 adds of < 2^19 (a
+// lane adds its own 8 keys of a tile or, in the general path, up to 8 queued ones of its warp: at most 16).  The few
+// values below the window, denormals, NaN and inf take the float64 compare-and-swap add.  (16 columns of 20 bits
+// halve the bank conflicts but cost a resident block per SM: 157 -> 142 us for 16 views of 800x800.)
+constexpr int kSelCols = 8;
+constexpr int kSelLimbBits = 19;
 constexpr uint32_t kSelLimbMask = (1u << kSelLimbBits) - 1u;
-constexpr int kSelWindow = 36;  // q = mantissa << (be - (emax - kSelWindow)) < 2^(24 + 36)
+constexpr int kSelWindow = 33;  // q = mantissa << (be - (emax - kSelWindow)) < 2^(24 + 33)
 static_assert(2 * (kSelMaxTilesPerBlock * kSelTile / kSelCols) <= (1 << (31 - kSelLimbBits)), "limb words cannot overflow");
 
+constexpr uint16_t kSelTiledFlag = 0x4000u;  // map code of a tie group resolved by tile: look up the tile's code
 struct ClassifyShared {
-  uint16_t map[kSelBins];           // bin -> class or kSelCellFlag | cell (undecided: a record); the bins of the tie
-                                    // groups are rewritten per tile; the coarse table is read through L1
+  uint16_t map[kSelBins];           // bin -> class, kSelCellFlag | cell (undecided: a record) or kSelTiledFlag | tiled
+                                    // index (-> tmode of the tile); the coarse table is read through L1
   uint32_t heavy[kSelMaxHeavy];
   double sum[kSelMaxCuts + 1][2];
   uint32_t base[kSelMaxCuts + 1];
   int8_t tiled[kSelMaxCuts];        // cell -> tiled index or -1
-  uint32_t slot[kSelMaxHeavy];      // first record of (tiled cell, tile) within the segment's side list
-  uint32_t cur[kSelMaxHeavy];
-  uint16_t tbin[kSelMaxHeavy];      // bin of every tie-group cell
+  uint32_t slot[kSelMaxTilesPerBlock][kSelMaxHeavy];  // first record of (tile, tiled cell) within the segment's side list
+  uint32_t cur[kSelMaxTilesPerBlock][kSelMaxHeavy];   // records of (tile, tiled cell) written so far
+  uint16_t tmode[kSelMaxTilesPerBlock][kSelMaxHeavy]; // class of the tie group's members in the tile, or kSelCellFlag | cell
   uint32_t warp_tmp[kSelWarps];
   uint32_t hot;
   uint32_t vmax[2];                 // bits of the largest finite |payload| of the block
@@ -737,33 +737,39 @@ __device__ __forceinline__ SelScale sel_scale(int emax) {
   s.sh_e = emax - kSelWindow;
   return s;
 }
-// the three limbs of a finite value inside the window (negated when the value is negative); `slow`: outside the
-// window and not zero.  SIGNED = false: the caller knows that no payload is negative (-0.0 lands outside the window
-// and adds nothing, like +0.0).
+// window test of one payload value: `fast` = it has an exact fixed-point image, `slow` = it is outside the window and
+// not zero.  SIGNED = false: the caller knows that no payload is negative (-0.0 lands outside the window and adds
+// nothing, like +0.0).
 template <bool SIGNED>
-__device__ __forceinline__ void sel_split(float v, const SelScale& sc, int (&l)[3], bool& fast, bool& slow) {
-  const uint32_t bits = __float_as_uint(v);
+__device__ __forceinline__ void sel_window(uint32_t bits, const SelScale& sc, uint32_t& sft, bool& fast, bool& slow) {
   const uint32_t be = SIGNED ? ((bits >> 23) & 0xFFu) : (bits >> 23);
   fast = (uint32_t)(be - (uint32_t)sc.lo_e) <= (uint32_t)sc.width;
-  const uint32_t mant = (bits & 0x7FFFFFu) | 0x800000u;
-  const uint32_t sft = (be - (uint32_t)sc.sh_e) & 63u;  // in [0, 36] when fast (unused otherwise)
+  sft = (be - (uint32_t)sc.sh_e) & 63u;  // in [0, kSelWindow] when fast (unused otherwise)
+  slow = !fast && (bits << 1) != 0u;
+}
+// the three limbs of q = mant << sft (negated when `neg`); mant = 0 gives three zero limbs
+__device__ __forceinline__ void sel_limbs(uint32_t mant, uint32_t sft, bool neg, int (&l)[3]) {
   const unsigned long long q = (unsigned long long)mant << sft;
   const uint32_t qlo = (uint32_t)q, qhi = (uint32_t)(q >> 32);
   l[0] = (int)(qlo & kSelLimbMask);
   l[1] = (int)(__funnelshift_r(qlo, qhi, kSelLimbBits) & kSelLimbMask);
   l[2] = (int)(qhi >> (2 * kSelLimbBits - 32));
-  if (SIGNED && (int)bits < 0) {
+  if (neg) {
     l[0] = -l[0];
     l[1] = -l[1];
     l[2] = -l[2];
   }
-  slow = !fast && (bits << 1) != 0u;
 }
-// `w`: the word of (payload, limb 0, class, this lane's column); `stride`: words between limbs
-__device__ __forceinline__ void sel_add_limbs(int* w, int stride, const int (&l)[3]) {
-  if (l[0]) atomicAdd(w, l[0]);
-  if (l[1]) atomicAdd(w + stride, l[1]);
-  if (l[2]) atomicAdd(w + 2 * stride, l[2]);
+// Three unconditional reductions (a zero limb adds zero): ptxas turns a predicated shared-memory atomic into a
+// divergence region of four instructions, which costs more issue slots than the reduction it saves.
+// `w`: shared-memory address of the word of (payload, limb 0, class, this lane's column); `stride`: bytes between limbs.
+__device__ __forceinline__ void sel_red(uint32_t w, int v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(w), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sel_add_limbs(uint32_t w, uint32_t stride, const int (&l)[3]) {
+  sel_red(w, l[0]);
+  sel_red(w + stride, l[1]);
+  sel_red(w + 2u * stride, l[2]);
 }
 
 // NONNEG: neither the keys nor the payloads of the segment hold a negative value or (the keys) a NaN -- known from
@@ -788,26 +794,32 @@ __device__ __forceinline__ void sel_classify_tiles(const SelParams& p, ClassifyS
   const uint8_t* modes = p.tilemode + (size_t)g * p.max_tiles * kSelMaxHeavy;
   const uint32_t* rows = p.tilecounts + (size_t)g * kSelMaxHeavy * p.max_tiles;
   uint16_t* rq = sh.rq[warp];
-  const int lstride = (p.num_cuts + 1) * kSelCols;  // words between the limbs of a payload
-  int* const col0 = limb + (lane & (kSelCols - 1));  // this lane's column of payload 0
-  int* const col1 = col0 + 3 * lstride;
+  const uint32_t lstride = (uint32_t)(p.num_cuts + 1) * kSelCols * 4u;  // bytes between the limbs of a payload
+  const uint32_t col0 = smem_u32(limb + (lane & (kSelCols - 1)));       // this lane's column of payload 0
+  const uint32_t col1 = col0 + 3u * lstride;
+  constexpr uint32_t kClassBytes = kSelCols * 4u;
+
+  if (nt > 0) {  // tables of the tie groups for every tile of the block (no barrier inside the tile loop)
+    for (int idx = tid; idx < kSelMaxTilesPerBlock * kSelMaxHeavy; idx += kSelThreads) {
+      const int tt = idx / kSelMaxHeavy, ti = idx % kSelMaxHeavy;
+      const int t = t0 + tt;
+      if (ti < nt && tt < p.tiles_per_block && (long long)t * kSelTile < len) {
+        const uint8_t md = modes[(size_t)t * kSelMaxHeavy + ti];
+        const int cell = pl.tcell[ti];
+        sh.slot[tt][ti] = sh.base[cell] + rows[(size_t)pl.theavy[ti] * p.max_tiles + t];
+        sh.cur[tt][ti] = 0u;
+        sh.tmode[tt][ti] = md == kSelCompact ? (uint16_t)(kSelCellFlag | cell) : (uint16_t)md;
+      }
+    }
+    if (tid < nt) sh.map[pl.cell_bin[pl.tcell[tid]]] = (uint16_t)(kSelTiledFlag | tid);
+    __syncthreads();
+  }
 
   for (int tt = 0; tt < p.tiles_per_block; ++tt) {
     const int t = t0 + tt;
     const long long tile_lo = (long long)t * kSelTile;
     if (tile_lo >= len) break;
     const int count = (int)min((long long)kSelTile, len - tile_lo);
-    if (nt > 0) {  // per-tile tables of the tie groups (uniform over the block)
-      __syncthreads();
-      if (tid < nt) {
-        const uint8_t md = modes[(size_t)t * kSelMaxHeavy + tid];
-        const int cell = pl.tcell[tid];
-        sh.slot[tid] = sh.base[cell] + rows[(size_t)pl.theavy[tid] * p.max_tiles + t];
-        sh.cur[tid] = 0u;
-        sh.map[sh.tbin[tid]] = md == kSelCompact ? (uint16_t)(kSelCellFlag | cell) : (uint16_t)md;
-      }
-      __syncthreads();
-    }
 
     // everything the fast pass does not cover -- an undecided element (a record of its cell), a payload outside the
     // fixed-point window, every element of the segment's last, partial tile -- goes through this
@@ -816,11 +828,12 @@ __device__ __forceinline__ void sel_classify_tiles(const SelParams& p, ClassifyS
       const float v0 = SELF ? kv : q0[tile_lo + pos];
       const float v1 = NPAY == 2 ? q1[tile_lo + pos] : 0.f;
       const uint32_t key = sort_key_from_float(kv);
-      const uint16_t m = sh.map[sel_bin(key, __ldg(tab + (key >> kSelLowBits)), sh.heavy, nh)];
+      uint16_t m = sh.map[sel_bin(key, __ldg(tab + (key >> kSelLowBits)), sh.heavy, nh)];
+      if (m & kSelTiledFlag) m = sh.tmode[tt][m & (kSelMaxHeavy - 1)];
       if (m & kSelCellFlag) {  // (any order: records are ranked by (key, index) later)
-        const int cell = m & 0x7FFF;
+        const int cell = m & 0x3FFF;
         const int ti = sh.tiled[cell];
-        const uint32_t d = ti >= 0 ? sh.slot[ti] + atomicAdd(&sh.cur[ti], 1u)
+        const uint32_t d = ti >= 0 ? sh.slot[tt][ti] + atomicAdd(&sh.cur[tt][ti], 1u)
                                    : sh.base[cell] + atomicAdd(cursor + cell, 1u);
         ck[d] = key;
         ci[d] = (uint32_t)(tile_lo + pos);
@@ -828,14 +841,19 @@ __device__ __forceinline__ void sel_classify_tiles(const SelParams& p, ClassifyS
         if (NPAY == 2) c1[d] = v1;
       } else {
         int l[3];
+        uint32_t sft;
         bool fast, slow;
-        sel_split<true>(v0, sc0, l, fast, slow);
-        if (fast) sel_add_limbs(col0 + (int)m * kSelCols, lstride, l);
-        else if (slow) atomicAdd(&sh.sum[m][0], (double)v0);
+        const uint32_t b0 = __float_as_uint(v0);
+        sel_window<true>(b0, sc0, sft, fast, slow);
+        sel_limbs(fast ? ((b0 & 0x7FFFFFu) | 0x800000u) : 0u, sft, (int)b0 < 0, l);
+        sel_add_limbs(col0 + (uint32_t)m * kClassBytes, lstride, l);
+        if (slow) atomicAdd(&sh.sum[m][0], (double)v0);
         if (NPAY == 2) {
-          sel_split<true>(v1, sc1, l, fast, slow);
-          if (fast) sel_add_limbs(col1 + (int)m * kSelCols, lstride, l);
-          else if (slow) atomicAdd(&sh.sum[m][1], (double)v1);
+          const uint32_t b1 = __float_as_uint(v1);
+          sel_window<true>(b1, sc1, sft, fast, slow);
+          sel_limbs(fast ? ((b1 & 0x7FFFFFu) | 0x800000u) : 0u, sft, (int)b1 < 0, l);
+          sel_add_limbs(col1 + (uint32_t)m * kClassBytes, lstride, l);
+          if (slow) atomicAdd(&sh.sum[m][1], (double)v1);
         }
       }
     };
@@ -859,17 +877,32 @@ __device__ __forceinline__ void sel_classify_tiles(const SelParams& p, ClassifyS
       uint32_t m[kSelItems];
 #pragma unroll
       for (int i = 0; i < kSelItems; ++i) m[i] = sh.map[bin[i]];
+      if (nt > 0) {  // uniform over the block
+#pragma unroll
+        for (int i = 0; i < kSelItems; ++i)
+          if (m[i] & kSelTiledFlag) m[i] = sh.tmode[tt][m[i] & (kSelMaxHeavy - 1)];
+      }
       uint32_t rare = 0u;
 #pragma unroll
       for (int i = 0; i < kSelItems; ++i) {
-        int l0[3], l1[3];
+        // an element the fast pass does not own (a record, a payload outside the window) adds nothing here: its
+        // mantissas are zeroed, hence its limbs, hence no reduction is issued
+        int l[3];
+        uint32_t sft0, sft1 = 0u;
         bool fast0, slow0, fast1 = false, slow1 = false;
-        sel_split<!NONNEG>(SELF ? kf[i] : a0[i], sc0, l0, fast0, slow0);
-        if (NPAY == 2) sel_split<!NONNEG>(a1[i], sc1, l1, fast1, slow1);
+        const uint32_t b0 = __float_as_uint(SELF ? kf[i] : a0[i]);
+        const uint32_t b1 = NPAY == 2 ? __float_as_uint(a1[i]) : 0u;
+        sel_window<!NONNEG>(b0, sc0, sft0, fast0, slow0);
+        if (NPAY == 2) sel_window<!NONNEG>(b1, sc1, sft1, fast1, slow1);
         const bool ok = !(m[i] & kSelCellFlag) && !slow0 && !slow1;
-        rare |= ok ? 0u : (1u << i);
-        if (ok && fast0) sel_add_limbs(col0 + (int)m[i] * kSelCols, lstride, l0);
-        if (NPAY == 2 && ok && fast1) sel_add_limbs(col1 + (int)m[i] * kSelCols, lstride, l1);
+        rare |= (uint32_t)(!ok) << i;
+        const uint32_t w = (m[i] & 0xFFu) * kClassBytes;
+        sel_limbs((ok && fast0) ? ((b0 & 0x7FFFFFu) | 0x800000u) : 0u, sft0, !NONNEG && (int)b0 < 0, l);
+        sel_add_limbs(col0 + w, lstride, l);
+        if (NPAY == 2) {
+          sel_limbs((ok && fast1) ? ((b1 & 0x7FFFFFu) | 0x800000u) : 0u, sft1, !NONNEG && (int)b1 < 0, l);
+          sel_add_limbs(col1 + w, lstride, l);
+        }
       }
       // queue the rare positions per warp, then run them through the general path with every lane busy
       while (rare) {
@@ -899,10 +932,7 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
     const uint16_t* map = p.binmap + (size_t)g * kSelBins;
     const int nb = pl.nbins;
     for (int i = tid; i < nb; i += kSelThreads) sh.map[i] = map[i];
-    if (tid < kSelMaxHeavy) {
-      sh.heavy[tid] = pl.heavy[tid];
-      sh.tbin[tid] = tid < pl.ntiled ? (uint16_t)pl.cell_bin[pl.tcell[tid]] : (uint16_t)0;
-    }
+    if (tid < kSelMaxHeavy) sh.heavy[tid] = pl.heavy[tid];
   }
   const int lwords = (int)sel_limb_words(nc) / (NPAY == 2 ? 1 : 2);  // one payload: only its half is used
   for (int i = tid; i < (kSelMaxCuts + 1) * 2; i += kSelThreads) (&sh.sum[0][0])[i] = 0.0;
@@ -980,7 +1010,7 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
         t1s += w[lstride + cc];
         t2s += w[2 * lstride + cc];
       }
-      // q total = t0 + t1 2^20 + t2 2^40 (|.| < 2^14 2^60 may exceed 64 bits: add as three exactly scaled doubles)
+      // q total = t0 + t1 2^19 + t2 2^38 (|.| < 2^14 2^57 may exceed 64 bits: add as three exactly scaled doubles)
       const int e = (pidx ? emax1 : emax0) - 150 - kSelWindow;
       if (t0s | t1s | t2s)
         v += ldexp((double)t0s, e) + ldexp((double)t1s, e + kSelLimbBits) + ldexp((double)t2s, e + 2 * kSelLimbBits);
@@ -989,7 +1019,7 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
   }
 }
 
-__global__ void __launch_bounds__(kSelThreads, 3) sel_classify(const SelParams p) {
+__global__ void __launch_bounds__(kSelThreads, 4) sel_classify(const SelParams p) {
   __shared__ ClassifyShared sh;
   extern __shared__ __align__(16) int sel_limb_smem[];
   const int g = blockIdx.y;
@@ -1277,7 +1307,7 @@ static SelLayout sel_layout(int F, int B, int num_cuts, int num_side_arrays, lon
   // blocks of the classifying pass: as long as possible (a block stages, zeroes and folds ~60 KB of tables) while one
   // wave of them -- three blocks per SM -- still covers the call; eight tiles each once the call is larger than that
   const int sms = sm_count();
-  const long long slots = 3LL * (sms > 0 ? sms : 148);
+  const long long slots = 4LL * (sms > 0 ? sms : 148);
   long long tpb = ((long long)l.max_tiles * l.G + slots - 1) / slots;
   l.tiles_per_block = (int)(tpb < 1 ? 1 : tpb > kSelMaxTilesPerBlock ? kSelMaxTilesPerBlock : tpb);
   l.max_blocks = (l.max_tiles + l.tiles_per_block - 1) / l.tiles_per_block;
