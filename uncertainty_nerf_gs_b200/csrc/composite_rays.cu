@@ -698,6 +698,10 @@ static int launch_tma(const CompositeParams& p, cudaStream_t stream) {
       set_error("composite_rays: cannot reserve %zu B shared memory (%s)", smem, cudaGetErrorString(e));
       return UB_ERR_LAUNCH;
     }
+    // Ask for the largest shared-memory carveout, not the smallest that holds the ring: the persistent CTA stays on
+    // its SM for the whole view, and the ~55 KB beyond its ring is what lets a block of the previous view's scoring
+    // kernels (up to 47 KB each) run beside it instead of waiting for the gap between two compositing kernels.
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const long long tiles = (p.num_rays + kRaysPerTile - 1) / kRaysPerTile;

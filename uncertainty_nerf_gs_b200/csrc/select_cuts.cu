@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kSelThreads) sel_coarse_hist(const SelParams p
 
 // ---- fine-bin allocation + heavy tie values: one block of 1024 threads per segment (a latency chain) ----------
 constexpr int kSelAllocThreads = 1024;
-__global__ void __launch_bounds__(kSelAllocThreads) sel_alloc(const SelParams p) {
+__global__ void __launch_bounds__(kSelAllocThreads, 2) sel_alloc(const SelParams p) {
   constexpr int kWarps = kSelAllocThreads / 32;
   static_assert(kSelSample == kSelAllocThreads, "one sample per thread");
   __shared__ uint32_t warp_tmp[kWarps];
@@ -485,7 +485,7 @@ __device__ __forceinline__ void sel_plan_tiled_cell(const SelParams& p, int g, i
 }
 
 // ---- locate: one block of 1024 threads per segment -----------------------------------------------------------
-__global__ void __launch_bounds__(kSelLocThreads) sel_locate(const SelParams p) {
+__global__ void __launch_bounds__(kSelLocThreads, 2) sel_locate(const SelParams p) {
   constexpr int kLocWarps = kSelLocThreads / 32;
   constexpr int kPad = (kSelBins + kLocWarps * 32 - 1) / (kLocWarps * 32) * (kLocWarps * 32);
   constexpr int span = kPad / kLocWarps, rounds = span / 32;
