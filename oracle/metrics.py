@@ -171,13 +171,25 @@ def unc_metrics_rgb(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor,
     return out
 
 
+def resize_like_reference(img: Tensor, size) -> Tensor:
+    """``F.resize(img.view(1, 1, H, W), size=size, antialias=None).squeeze(0, 1)`` (``eval_uncertainty.py:444-451``)."""
+    h, w = img.shape[-2:]
+    return torch.nn.functional.interpolate(img.reshape(1, 1, h, w), size=tuple(size), mode="bilinear",
+                                           align_corners=False, antialias=False).squeeze(0).squeeze(0)
+
+
 def unc_metrics_depth(depth: Tensor, depth_std: Tensor, depth_gt: Tensor, scale: float,
                       min_depth_std_for_nll: float = 1.0, stable: bool = True) -> Dict[str, object]:
-    """``get_unc_metrics_depth`` (``eval_uncertainty.py:415-644``) downstream of file loading and
-    without the resize branch: scale, clamp to ``[1e-3, max gt]``, NLL on the full image, mask
-    ``gt > 0``, errors, 3 x AUSE, AUCE."""
+    """``get_unc_metrics_depth`` (``eval_uncertainty.py:415-644``) downstream of file loading: the resize of
+    renders whose shape differs from the ground truth's (``:442-452``; torchvision's ``F.resize`` of a float tensor =
+    bilinear ``interpolate``, ``align_corners=False``, no antialiasing), scale, clamp to ``[1e-3, max gt]``, NLL on the
+    full image, mask ``gt > 0``, errors, 3 x AUSE, AUCE."""
     depth = depth.squeeze(-1).clone()
     depth_std = depth_std.squeeze(-1).clone()
+    if depth_gt.shape[-2:] != depth.shape[-2:]:
+        depth = resize_like_reference(depth, depth_gt.shape[-2:])
+    if depth_gt.shape[-2:] != depth_std.shape[-2:]:
+        depth_std = resize_like_reference(depth_std, depth_gt.shape[-2:])
     min_d, max_d = 1e-3, depth_gt.max().float()
     depth = scale * depth
     depth_std = scale * depth_std

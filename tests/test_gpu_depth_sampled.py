@@ -42,6 +42,33 @@ def test_score_depth_batch_vs_oracle(built_library):
         np.testing.assert_allclose(out["mse_mean"], float(ref["mse"].mean()), rtol=RTOL)
 
 
+def test_score_depth_batch_resizes_renders_like_the_reference(built_library):
+    """Renders of shape [H-1, W-1] (splatfacto's depth) against a [H, W] ground truth: eval_uncertainty.py:442-452
+    resizes them bilinearly before scoring; the oracle's resize is pinned to that code (tests/test_oracle_pinned.py).
+    The interpolation runs in torch on either side (CUDA vs CPU kernels: equal to float32 rounding), so the
+    coverage may differ for an element sitting on an interval end: compared to 2e-3 of the pixel count."""
+    from uncertainty_nerf_gs_b200.metrics import resize_like_reference, score_depth_batch
+
+    views = [_depth_view(37, 53, s) for s in range(2)]
+    small = [(d[:-1, :-1], s[:-1, :-1], g) for d, s, g in views]
+    scales = [2.5, 2.4]
+    got = resize_like_reference(torch.stack([v[0][..., 0] for v in small]).cuda(), (37, 53)).cpu()
+    want = torch.stack([om.resize_like_reference(v[0][..., 0], (37, 53)) for v in small])
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+    outs = score_depth_batch(torch.stack([v[0] for v in small]).cuda(), torch.stack([v[1] for v in small]).cuda(),
+                             torch.stack([v[2] for v in small]).cuda(), scales, min_depth_std_for_nll=1.0)
+    for (d, s, g), a, out in zip(small, scales, outs):
+        ref = om.unc_metrics_depth(d, s, g, a, min_depth_std_for_nll=1.0)
+        cov_ref = np.asarray(ref["coverage_values"], dtype=np.float64)       # fractions of the valid pixels
+        np.testing.assert_allclose(np.asarray(out["coverage_values"], dtype=np.float64), cov_ref, rtol=0,
+                                   atol=2e-3 * max(1.0, float(cov_ref.max())))
+        for k in ("err_mae", "err_mse", "err_rmse", "err_var_mae", "err_var_mse", "err_var_rmse"):
+            np.testing.assert_allclose(out[k], ref[k], rtol=1e-4, atol=1e-7)
+        for k in ("ause_mae", "ause_mse", "ause_rmse", "avg_var"):
+            np.testing.assert_allclose(out[k], ref[k], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(out["nll_depth"], ref["nll_depth"], rtol=1e-4)
+
+
 @pytest.mark.parametrize("num_samples,draws", [(48, 20), (96, 7), (5, 3)])
 def test_average_sampled_weights_with_given_noise(built_library, num_samples, draws):
     from uncertainty_nerf_gs_b200 import ops

@@ -211,3 +211,20 @@ def test_select_randomized_mixtures(built_library, seed):
     ncut = int(rng.integers(1, 129))
     cuts = np.stack([rng.integers(0, n + 1, size=ncut) for n in lens]).astype(np.int64)
     _check(var, ae, se, lens, cuts, check_sort_path=seed % 3 == 0)
+
+
+def test_select_background_of_exact_and_tiny_errors(built_library):
+    """A render over a flat background: half the pixels have an error of exactly zero, a quarter an error 2^-40 below
+    the largest one (outside the fixed-point window: the float64 path of sel_classify, whole warps of it), some are
+    negative.  Exactness must not depend on which path a value takes."""
+    n = 300000
+    g = torch.Generator().manual_seed(11)
+    var = torch.clamp(0.1 * torch.rand(n, generator=g), min=0.03) ** 2
+    ae = torch.rand(n, generator=g)
+    kind = torch.randint(0, 4, (n,), generator=g)
+    ae = torch.where(kind <= 1, torch.zeros(()), ae)                    # exact zeros (and -0.0 below)
+    ae = torch.where(kind == 2, ae * 2.0 ** -40, ae)                    # far below the window of the maximum
+    ae[::7] = -ae[::7]                                                  # signed payloads / keys, -0.0 included
+    se = ae * ae
+    lens = [n]
+    _check(var, ae, se, lens, _ause_cuts(lens))

@@ -151,11 +151,22 @@ def test_live_rgb_scoring_and_nll():
                 om.negative_gaussian_loglikelihood(p.reshape(-1, 3), g.reshape(-1, 3), s, 3e-2))   # :404-412
 
 
+def _real_torchvision() -> bool:
+    try:
+        import torchvision.transforms.functional as F
+        return hasattr(F, "resize") and callable(F.resize) and "torchvision" in (getattr(F.resize, "__module__", "") or "")
+    except Exception:
+        return False
+
+
 @needs_ref
-def test_live_depth_scoring(tmp_path):
+@pytest.mark.parametrize("render_hw", [(40, 50), (39, 49)])     # (39, 49): splatfacto's [H-1, W-1] depth -> the resize branch
+def test_live_depth_scoring(tmp_path, render_hw):
+    if render_hw != (40, 50) and not _real_torchvision():
+        pytest.skip("the resize branch calls torchvision's F.resize: needs the real package")
     gen = torch.Generator().manual_seed(1)
-    d = torch.rand(40, 50, 1, generator=gen) * 4
-    ds = torch.rand(40, 50, 1, generator=gen) * 0.3 + 0.01
+    d = torch.rand(*render_hw, 1, generator=gen) * 4
+    ds = torch.rand(*render_hw, 1, generator=gen) * 0.3 + 0.01
     gt = torch.rand(40, 50, generator=gen) * 5
     gt[gt < 0.7] = 0
     rx.write_depth_side_inputs(tmp_path / "data", [gt.numpy()], 1.7)

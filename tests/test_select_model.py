@@ -111,19 +111,35 @@ def test_exponent_of_a_coarse_bin():
 
 
 def test_fixed_point_limbs_are_exact():
-    """sel_add_payload: mantissa << (exponent + 24 - emax), three 16-bit limbs, summed as integers."""
+    """sel_window / sel_limbs: q = mantissa << (exponent + 33 - emax) for values within 2^33 of the largest magnitude,
+    three 19-bit limbs (each negated for a negative value) added as integers into one of 8 columns; a column word sees
+    at most 4096 adds (16384 keys per block, 8 columns, a lane's own keys plus queued ones), so it cannot overflow, and
+    limbs . (1, 2^19, 2^38) . 2^(emax - 150 - 33) is the exact sum."""
+    import fractions
+
+    WINDOW, LIMB, COLS = 33, 19, 8
     rng = np.random.default_rng(2)
-    v = (rng.standard_normal(16384) * np.exp2(rng.integers(-20, 1, 16384))).astype(np.float32)
+    v = (rng.standard_normal(16384) * np.exp2(rng.integers(-30, 1, 16384))).astype(np.float32)
     v = v[v != 0]
     bits = v.view(np.uint32).astype(np.int64)
     be = (bits >> 23) & 0xFF
     emax = int(be.max())
-    ok = (be != 0) & (be + 24 >= emax)
-    q = (((bits & 0x7FFFFF) | 0x800000) << (be + 24 - emax).clip(0)) * np.where(bits >> 31, -1, 1)
-    q = q[ok]
-    lo, mid, hi = q & 0xFFFF, (q >> 16) & 0xFFFF, q >> 32
-    assert abs(int(lo.sum())) < 2 ** 31 and abs(int(mid.sum())) < 2 ** 31 and abs(int(hi.sum())) < 2 ** 31
-    total = (int(hi.sum()) << 32) + (int(mid.sum()) << 16) + int(lo.sum())
-    import fractions
+    ok = (be != 0) & (be + WINDOW >= emax)
+    assert ok.mean() > 0.97
+    q = (((bits & 0x7FFFFF) | 0x800000).astype(object) << (be + WINDOW - emax).clip(0).astype(object))
+    sign = np.where(bits >> 31, -1, 1)
+    mask = (1 << LIMB) - 1
+    col = np.arange(len(v)) % COLS
+    words = np.zeros((3, COLS), dtype=object)
+    for qi, sg, c, good in zip(q, sign, col, ok):
+        if not good:
+            continue
+        qi = int(qi)
+        assert qi < 1 << (24 + WINDOW)
+        for j in range(3):
+            words[j, c] += int(sg) * ((qi >> (LIMB * j)) & mask)
+    assert all(abs(int(w)) < 2 ** 31 for w in words.reshape(-1))
+    assert 2 * (16384 // COLS) * mask < 2 ** 31                              # the kernel's static_assert
+    total = sum(int(words[j].sum()) << (LIMB * j) for j in range(3))
     exact = sum((fractions.Fraction(float(x)) for x in v[ok]), fractions.Fraction(0))
-    assert fractions.Fraction(total) * fractions.Fraction(2) ** (emax - 174) == exact
+    assert fractions.Fraction(total) * fractions.Fraction(2) ** (emax - 150 - WINDOW) == exact

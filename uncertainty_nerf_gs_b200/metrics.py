@@ -413,11 +413,20 @@ def per_image_depth_scalars(d: Dict[str, object]) -> Dict[str, float]:
     }
 
 
+def resize_like_reference(img: Tensor, size) -> Tensor:
+    """``[B, h, w] -> [B, H, W]`` the way ``F.resize(x.view(1, 1, h, w), size=size, antialias=None)`` does it per view
+    (eval_uncertainty.py:444-451): torchvision's resize of a float tensor is ``interpolate(mode="bilinear",
+    align_corners=False, antialias=False)``.  A data-format adapter in front of the hot path (plain torch)."""
+    return torch.nn.functional.interpolate(img[:, None].float(), size=tuple(size), mode="bilinear", align_corners=False,
+                                           antialias=False)[:, 0]
+
+
 def score_depth_batch(depth: Tensor, depth_std: Tensor, depth_gt: Tensor, scales: Sequence[float],
                       min_depth_std_for_nll: float = 1.0) -> List[Dict[str, object]]:
     """``get_unc_metrics_depth`` (eval_uncertainty.py:415-644) for a batch of views, downstream of file
-    loading and without the resize branch.  ``depth, depth_std, depth_gt [B, H, W]`` (or ``[B, H, W, 1]``);
-    ``scales[b]`` is the per-dataset scale ``a``.  Per view: scale, clamp to ``[1e-3, max gt]``, keep the
+    loading.  ``depth, depth_std [B, h, w]``, ``depth_gt [B, H, W]`` (or with a trailing 1); renders whose shape
+    differs from the ground truth's (splatfacto renders ``[H-1, W-1]`` depth) are resized like the reference does
+    (``:442-452``: bilinear, ``align_corners=False``, no antialiasing).  ``scales[b]`` is the per-dataset scale ``a``.  Per view: scale, clamp to ``[1e-3, max gt]``, keep the
     pixels with ``gt > 0`` (a ragged segment per view), then the same kernels as the rgb path with one
     channel and sigma = std: prologue (se / ae / var, NLL with eps = ``min_depth_std_for_nll``, interval
     histogram), one segmented sort over 3B ragged segments, cut-point prefix sums.  The per-view preparation is
@@ -426,6 +435,10 @@ def score_depth_batch(depth: Tensor, depth_std: Tensor, depth_gt: Tensor, scales
         depth, depth_std = depth[..., 0], depth_std[..., 0]
     if depth_gt.dim() == 4:
         depth_gt = depth_gt[..., 0]
+    if depth.shape[-2:] != depth_gt.shape[-2:]:
+        depth = resize_like_reference(depth, depth_gt.shape[-2:])
+    if depth_std.shape[-2:] != depth_gt.shape[-2:]:
+        depth_std = resize_like_reference(depth_std, depth_gt.shape[-2:])
     b = depth.shape[0]
     dev = depth.device
     pred, std, gt, lens = ops.depth_prepare(depth.reshape(b, -1), depth_std.reshape(b, -1), depth_gt.reshape(b, -1),
