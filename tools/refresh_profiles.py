@@ -63,4 +63,36 @@ if os.path.exists(rep):
     open(os.path.join(dst, f"{tag}_ncu_summary.txt"), "w").writelines(lines)
     if traffic:
         json.dump(traffic, open(os.path.join(dst, "composite_rays_traffic.json"), "w"), indent=1)
+# ---- every kernel of one batched scoring call (select path), full metric set ----
+rep = os.path.join(src, f"{tag}_select_full.ncu-rep")
+if os.path.exists(rep):
+    raw = run(["ncu", "-i", rep, "--page", "raw", "--csv"])
+    rows = list(csv.reader(raw.splitlines()))
+    h = rows[0]
+    want = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+            "smsp__inst_executed_op_shared_atom.sum", "launch__registers_per_thread", "launch__grid_size",
+            "launch__block_size", "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic",
+            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
+    lines = [f"# ncu --set full --clock-control none --import-source on: every kernel of one batched scoring call, 16 views of\n"
+             f"# 800x800 through the select path (tools/profile_score.py, {tag}); units as ncu reports them\n"]
+    for r in rows[2:]:
+        lines.append(f"\n== {r[h.index('Kernel Name')]}\n")
+        for w in want:
+            if w in h:
+                lines.append(f"   {w:86s} {r[h.index(w)]:>16s} {rows[1][h.index(w)]}\n")
+    for kern, unit in (("sel_classify", "select_cuts"), ("score_prologue_kernel", "score_prologue")):
+        lines.append(f"\n# warp instructions per source line, {kern} (tools/sass_lines.py)\n")
+        lines.append(run([sys.executable, "tools/sass_lines.py", rep, kern, unit, "--top", "24"]))
+    open(os.path.join(dst, f"{tag}_select_ncu_summary.txt"), "w").writelines(lines)
+open(os.path.join(dst, f"{tag}_sass_summary.txt"), "w").write(run(["bash", "tools/sass_summary.sh"]))
+for name in (f"{tag}_bench_n2.json", f"{tag}_bench_n4.json", f"{tag}_bench_n8.json", f"{tag}_diag_overlap.txt"):
+    if os.path.exists(os.path.join(src, name)):
+        shutil.copy(os.path.join(src, name), os.path.join(dst, name))
 print("profiles/ refreshed from", src)

@@ -22,5 +22,6 @@ timeout 200 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__
 # every kernel of one batched scoring call, full metric set (source page: per-instruction counts of the select / prologue kernels)
 timeout 400 ncu --profile-from-start off --set full --import-source on --clock-control none -f -o $out/${tag}_select_full \
     python tools/profile_score.py > $out/${tag}_select_full.log 2>&1
+timeout 120 python tools/diag_overlap.py 10 > $out/${tag}_diag_overlap.txt 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $out/${tag}_nvidia_smi.csv
 echo done
