@@ -549,6 +549,24 @@ def time_scoring(ctx, members, gt, h, w, steps):
     one = (rgb, gt, std)
     score_ms = timed(lambda: metrics.score_rgb_batch(*one), score_steps)
     score_stream_ms = streamed(one, score_steps)
+
+    def graph_streamed(args_, n):
+        """one view per call, the call being a CUDA-graph replay; two graph slots alternate so that the host tail of
+        view i (read-back wait + numpy curves) runs while view i + 1 is on the device"""
+        slots = [pipeline.GraphedScore(*args_), pipeline.GraphedScore(*args_)]
+        state = {"pend": None, "i": 0}
+
+        def one_():
+            nxt = slots[state["i"] & 1].launch()
+            state["i"] += 1
+            if state["pend"] is not None:
+                state["pend"].finish()
+            state["pend"] = nxt
+        ms = timed(one_, n)
+        state["pend"].finish()
+        return ms
+
+    score_graph_stream_ms = graph_streamed(one, 4 * score_steps)
     b8 = 8
     eight = tuple(t[None].expand(b8, *t.shape).contiguous() for t in one)
     n8 = max(3, score_steps // 4)
@@ -577,7 +595,12 @@ def time_scoring(ctx, members, gt, h, w, steps):
             "eight_views_per_call_ms_per_image_sort_path": sort_b8_ms,
             "streamed_one_view_per_call_ms": score_stream_ms,
             "synchronous_one_view_per_call_ms": score_ms,
+            "graph_replay_one_view_per_call_ms": score_graph_stream_ms,
             "images_per_s_one_view_per_call_streamed": world / (score_stream_ms * 1e-3),
+            "images_per_s_one_view_per_call_graph_replay": world / (score_graph_stream_ms * 1e-3),
+            "one_view_note": "streamed = eager kernel-by-kernel enqueue (host-bound: ~0.14 ms of Python / ctypes + the "
+                             "numpy tail per call); graph replay = the same device work as one cudaGraphLaunch, two slots "
+                             "alternating (pipeline.GraphedScore)",
             "roofline_select": {"bound": "hbm", "bytes_per_pixel": 92, "model": "prologue 40 B + 3 key reads 36 B + payload reads 16 B",
                                 "achieved": 92 * n / (score_b8_ms * 1e-3) / 1e9, "peak": ctx.peak, "unit": "GB/s",
                                 "frac": 92 * n / (score_b8_ms * 1e-3) / 1e9 / ctx.peak},

@@ -52,3 +52,16 @@ def sw():
     with torch.cuda.stream(side):
         pass
 print(json.dumps({"stream switch us": round(bench(sw), 1)}))
+
+# ---- where the host time of one scoring call goes (800x800) ----
+import cProfile, pstats, io
+p8, s8, g8 = synthetic.scoring_image(800, 800, seed=0, device=dev)
+for _ in range(5):
+    metrics.score_rgb_batch_async(p8, g8, s8).finish()
+pr = cProfile.Profile()
+torch.cuda.synchronize()
+pr.enable()
+pend = [metrics.score_rgb_batch_async(p8, g8, s8) for _ in range(50)]
+pr.disable()
+[x.finish() for x in pend]
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(18); print(s.getvalue()[:4500])
