@@ -15,6 +15,13 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 
 
+def _norm(sig: str) -> str:
+    """kernel signature without the differences between ncu and c++filt: "(int)48" vs "48", "(bool)1" vs "true", spaces"""
+    sig = re.sub(r"\((int|bool|unsigned int|long)\)", "", sig)
+    sig = sig.replace("true", "1").replace("false", "0").replace("ub::", "")
+    return re.sub(r"\s+", "", sig.split("(")[0] if "<" not in sig else sig[:sig.rindex(">") + 1])
+
+
 def main():
     rep, kernel, unit = sys.argv[1], sys.argv[2], sys.argv[3]
     top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 40
@@ -45,7 +52,7 @@ def main():
         if m:
             cur_fn = m.group(1)
             dem = subprocess.run(["c++filt", cur_fn.split(",")[0]], capture_output=True, text=True).stdout.strip()
-            want = dem.split("(")[0].strip() == name.split("(")[0].strip() or dem.startswith(name.split("(")[0])
+            want = _norm(dem) == _norm(name)
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', l)
         if m:

@@ -49,6 +49,7 @@ struct CompositeParams {
   int beta_mode;
   long long rays_per_chunk;
   int tiles_per_chunk;  // rays_per_chunk / 8 on the fast path (0: one chunk)
+  int chunk_shift;      // log2(tiles_per_chunk) when it is a power of two (the usual 32768-ray chunk), else -1
   int eval_mode;
   float* o_rgb;
   float* o_acc;
@@ -121,14 +122,16 @@ struct ChunkBounds {
   }
 };
 
-// exclusive prefix over the 4 lanes of a ray of the lanes' float64 totals, in lane order
+// exclusive prefix over the 4 lanes of a ray of the lanes' float64 totals: an inclusive scan in two shuffle-up steps
+// minus the lane's own total (float64 sums of float32 terms: exact, so the association does not matter)
 __device__ __forceinline__ double ray_exclusive_offset(double total, int q, int group_base) {
-  const double t0 = shfl_double(FULL_MASK, total, group_base | 0);
-  const double t1 = shfl_double(FULL_MASK, total, group_base | 1);
-  const double t2 = shfl_double(FULL_MASK, total, group_base | 2);
-  const double s01 = t0 + t1;
-  const double s012 = s01 + t2;
-  return q == 0 ? 0.0 : (q == 1 ? t0 : (q == 2 ? s01 : s012));
+  (void)group_base;
+  double v = total;
+  double u = shfl_up_double(FULL_MASK, v, 1);
+  if (q >= 1) v += u;
+  u = shfl_up_double(FULL_MASK, v, 2);
+  if (q >= 2) v += u;
+  return v - total;
 }
 
 template <int S, int NCW, int NST>
@@ -205,8 +208,8 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
     const uint32_t ph = (uint32_t)((j / NST) & 1);
     const int tile = j * (int)gridDim.x + (int)blockIdx.x;
     const int ray0 = tile * kRaysPerTile;
-    const bool active = (long long)ray0 + r < p.num_rays;
     const int ray = ray0 + r;
+    const bool active = ray < (int)p.num_rays;  // the fast path takes num_rays < 2^30
 
     mbar_wait(&full_bar[st], ph, j);
     const float* sb = stages + (size_t)st * kStageFloats;
@@ -276,7 +279,8 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
         step[4 * v + 3] = __fadd_rn(x.w, y.w) * 0.5f;
       }
     }
-    bounds.enter(p.tiles_per_chunk > 0 ? tile / p.tiles_per_chunk : 0, p.chunk_ws);
+    bounds.enter(p.chunk_shift >= 0 ? (tile >> p.chunk_shift) : (p.tiles_per_chunk > 0 ? tile / p.tiles_per_chunk : 0),
+                 p.chunk_ws);
     float rmin = step[0], rmax = step[0];  // step range of the ray (fminf / fmaxf skip NaN, like the chunk bounds)
 #pragma unroll
     for (int i = 1; i < P; ++i) {
@@ -301,17 +305,16 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
     }
     off = ray_exclusive_offset(run, q, group_base);
     int first = S;
+    const double half_here = kHalf - off;  // off + pre[i] >= kHalf, with the lane's offset moved to the other side
 #pragma unroll
     for (int i = P - 1; i >= 0; --i)
-      if (off + pre[i] >= kHalf) first = q * P + i;
+      if (pre[i] >= half_here) first = q * P + i;
     first = min(first, __shfl_xor_sync(FULL_MASK, first, 1));
     first = min(first, __shfl_xor_sync(FULL_MASK, first, 2));
     first = min(first, S - 1);  // clamp(idx, 0, S-1)
-    const int floc = first - q * P;
-    float depth = step[0];
-#pragma unroll
-    for (int i = 1; i < P; ++i) depth = (i == floc) ? step[i] : depth;
-    depth = __shfl_sync(FULL_MASK, depth, group_base | (first / P));
+    // the midpoint of sample `first`, recomputed from the stage (the 4 lanes of a ray read the same two words) instead of
+    // a select chain over the lane's 12 midpoints plus a shuffle
+    const float depth = __fadd_rn(sb[2 * kTileFloats + r * S + first], sb[3 * kTileFloats + r * S + first]) * 0.5f;
 
     // ---- expected depth numerator, depth variance ----
     float e_num = 0.f, dvar = 0.f;
@@ -416,25 +419,21 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
       if (lane == 0) p.cand_flags[tile] = ((unsigned long long)var_m << 32) | clip_m;   // bit 4 r <-> ray r of the tile
     }
 
-    // ---- outputs: the 4 lanes of a ray split the stores ----
+    // ---- outputs: the 4 lanes of a ray split the stores.  Branch-free: a four-way branch on q runs its four bodies one
+    // after the other with a quarter of the lanes each (two of them a square root); here every lane fills up to three
+    // store slots selected by q, and one square root serves rgb_std (q == 2) and depth_std (q == 3) ----
     if (active) {
-      if (q == 0) {
-        if (p.o_rgb) {
-          p.o_rgb[(size_t)ray * 3 + 0] = cr;
-          p.o_rgb[(size_t)ray * 3 + 1] = cg;
-          p.o_rgb[(size_t)ray * 3 + 2] = cb;
-        }
-      } else if (q == 1) {
-        if (p.o_acc) p.o_acc[ray] = acc;
-        if (p.o_depth) p.o_depth[ray] = depth;
-        if (p.o_exp) p.o_exp[ray] = e_exp;
-      } else if (q == 2) {
-        if (p.o_rgb_var) p.o_rgb_var[ray] = var;
-        if (p.o_rgb_std) p.o_rgb_std[ray] = sqrtf(var);
-      } else {
-        if (p.o_dvar) p.o_dvar[ray] = dvar;
-        if (p.o_dstd) p.o_dstd[ray] = sqrtf(dvar);
-      }
+      const float sq = sqrtf(q == 2 ? var : dvar);
+      const float v0 = q == 0 ? cr : (q == 1 ? acc : (q == 2 ? var : dvar));
+      const float v1 = q == 0 ? cg : (q == 1 ? depth : sq);
+      const float v2 = q == 0 ? cb : e_exp;
+      float* const b0 = q == 0 ? p.o_rgb : (q == 1 ? p.o_acc : (q == 2 ? p.o_rgb_var : p.o_dvar));
+      float* const b1 = q == 0 ? p.o_rgb : (q == 1 ? p.o_depth : (q == 2 ? p.o_rgb_std : p.o_dstd));
+      float* const b2 = q == 0 ? p.o_rgb : (q == 1 ? p.o_exp : nullptr);
+      const size_t at = q == 0 ? (size_t)ray * 3 : (size_t)ray;
+      if (b0) b0[at] = v0;
+      if (b1) b1[at + (q == 0 ? 1 : 0)] = v1;
+      if (b2) b2[at + (q == 0 ? 2 : 0)] = v2;
       if (p.o_w) {
         float4* ow = reinterpret_cast<float4*>(p.o_w + (size_t)ray * S + q * P);
 #pragma unroll
@@ -799,6 +798,11 @@ static int composite_prepare(const ub_composite_rays_args* a, void* workspace, s
   p.o_w = a->out_weights;
   p.chunk_ws = static_cast<unsigned*>(workspace);
   p.tiles_per_chunk = a->rays_per_chunk > 0 ? (int)(a->rays_per_chunk / kRaysPerTile) : 0;
+  p.chunk_shift = -1;
+  if (p.tiles_per_chunk > 0 && (p.tiles_per_chunk & (p.tiles_per_chunk - 1)) == 0) {
+    p.chunk_shift = 0;
+    while ((1 << p.chunk_shift) < p.tiles_per_chunk) ++p.chunk_shift;
+  }
   if (cand_list != nullptr && composite_fast_path(a))  // the generic kernel keeps the visit-every-ray finalize
     p.cand_flags = static_cast<unsigned long long*>(cand_list);
   return UB_OK;
