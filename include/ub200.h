@@ -292,12 +292,32 @@ int ub_cut_prefix_sums(const float* const* values_host, const int32_t* const* pe
                        int64_t max_segment_len, const int64_t* cuts, int32_t num_cuts, double* out_sums,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Host tail of the batched scorer (HOST function, HOST pointers, no stream): from the packed results of a batch --
+ * packed = [num_views][4][num_cuts] AUSE slice sums (abs err by var, sq err by var, abs err ascending, sq err
+ * ascending) | [num_views][5] prologue sums (se, ae, var, nll, sigma) | [num_views][num_z + 1] interval histogram
+ * (int64 bit patterns), as ub_cut_select_sums / ub_score_prologue wrote them and one device->host copy brought them
+ * over -- to what get_unc_metrics_rgb returns per image (eval_uncertainty.py:323-402): for the error types (mae, mse,
+ * rmse) the normalised curves of metrics/ause.py:15-44 -- out_by_unc [V][3][num_cuts] float64, the oracle curve as
+ * float64 (out_oracle64) and as float32 (out_oracle32) with out_oracle_is64 [V][3] saying which of the two the
+ * reference's dtype rules produce -- and out_ause [V][3]; out_scalars [V][3] = nll, avg_var, mse mean (float32);
+ * out_auce_curves [V][5][num_z] = coverage, interval length, coverage error, abs, neg (metrics/auce.py:24-45);
+ * out_auc [V][3] = areas of abs error, length, neg error (:47-54).  cuts [num_cuts]: the slice lengths int((1-r) n);
+ * ratio_steps [num_cuts - 1] = diff of the removal ratios; one_minus_alpha [num_z], alpha_steps [num_z - 1].
+ * Every operation runs in the dtype and order numpy uses for the reference's expressions (pairwise row sums of
+ * np.trapz included): the results equal the numpy evaluation bit for bit. */
+int ub_score_tail_host(const double* packed, int32_t num_views, int64_t n, int32_t channels, const int64_t* cuts,
+                       int32_t num_cuts, const double* ratio_steps, const double* z_values, int32_t num_z,
+                       const double* one_minus_alpha, const double* alpha_steps, double* out_by_unc,
+                       double* out_oracle64, float* out_oracle32, int32_t* out_oracle_is64, double* out_ause,
+                       float* out_scalars, double* out_auce_curves, double* out_auc);
+
 /* AUSE cut-point sums without a full sort (multi-cut radix select).  Same result as ub_segmented_sort
  * followed by ub_cut_prefix_sums -- the sums over the first cuts[s, c] elements of the stable ascending
  * order of the keys (metrics/ause.py:10-20 with the error as its own key, :25-34 with the uncertainty as
  * key and the errors as payload) -- when the permutation itself is not needed: keys are classified against
- * the cut positions (adaptive 4096-bin histogram, tie groups resolved by element index, the few undecided
- * keys around every cut sorted by the segmented radix sort), payloads summed per class in float64.
+ * the cut positions (count-proportional fine bins over a 4096-bin coarse histogram, tie groups resolved by element
+ * index, the few undecided keys around every cut ranked per cell), payloads summed per class exactly (fixed point)
+ * and returned as float64.
  * Family f (<= 4) has keys keys_host[f] [total] and one or two payload arrays pay0_host[f], pay1_host[f]
  * (HOST arrays of DEVICE pointers; pay1_host or its entries may be NULL; pay0 == keys is recognised).
  * All families share seg_offsets (DEVICE int64 [num_views + 1], off[0] == 0) and cuts (DEVICE

@@ -248,3 +248,25 @@ def test_auce_counts_exact_at_interval_boundaries(built_library):
     out = auce(m, s, t)
     n = float(m.size)
     assert np.array_equal(np.rint(np.asarray(out["coverage_values"]) * n), np.rint(np.asarray(ref["coverage_values"]) * n))
+
+
+def test_auce_counts_with_zero_sigma_pixels(built_library):
+    """Empty rays render with variance 0: sigma == 0 makes every interval the point m (count 0 unless t == m).  The
+    prologue answers that from the ratio table (an infinite ratio) instead of the exact float64 search, which a warp
+    would otherwise enter for every such pixel; counts must still equal numpy's, also where t == m."""
+    from uncertainty_nerf_gs_b200.metrics import auce
+
+    rng = np.random.default_rng(11)
+    n = 200_000
+    m = rng.random((n, 1)).astype(np.float32)
+    s = (0.05 + 0.1 * rng.random((n, 1))).astype(np.float32)
+    t = np.clip(m + s * rng.standard_normal((n, 1)).astype(np.float32), 0, 1).astype(np.float32)
+    zero = rng.random(n) < 0.05
+    s[zero] = 0.0
+    same = zero & (rng.random(n) < 0.3)
+    t[same] = m[same]                                   # sigma == 0 and t == m: inside every interval
+    s[rng.random(n) < 0.001] = -0.1                      # a few negative sigmas: never inside
+    with np.errstate(invalid="ignore", over="ignore"):
+        ref = om.auce(m, s, t)
+    out = auce(m, s, t)
+    assert np.array_equal(np.rint(np.asarray(out["coverage_values"]) * n), np.rint(np.asarray(ref["coverage_values"]) * n))

@@ -171,3 +171,52 @@ def test_ause_path_switch_and_select_refuses_cpu_tensors(monkeypatch):
     x = torch.rand(100)
     with pytest.raises(RuntimeError, match="no CPU implementation"):
         ops.cut_select_sums([(x, x, None)], [100], metrics.ause_cut_counts(100)[None, :])
+
+
+def _random_packed(rng, b, n, c, nzp, kind):
+    """A packed score buffer as the device would fill it: slice sums (non-increasing in the cut index, like prefix sums
+    of non-negative errors at decreasing cut counts), prologue sums, an interval histogram that sums to n * c."""
+    from uncertainty_nerf_gs_b200 import metrics as M
+
+    packed = np.zeros(b * (400 + 5 + nzp))
+    sums_v, psums, hist_v = M._packed_views(packed, b, nzp)
+    cuts = M.ause_cut_counts(n)
+    per_el = rng.random((b, 4, 1)) * 10.0 ** rng.integers(-6, 3, (b, 4, 1))
+    sums_v[:] = cuts[None, None, :] * per_el * (1.0 + 0.3 * rng.random((b, 4, 100)))
+    if kind == "oracle_wins":
+        sums_v[:, 2:] *= 50.0                      # the float32 oracle maximum beats the by-uncertainty one
+    if kind == "nan":
+        sums_v[0, 0, 3] = np.nan                   # a NaN inside a curve: Python's max() semantics
+        sums_v[-1, 2, 0] = np.nan                  # a leading NaN sticks
+    if kind == "zero":
+        sums_v[0] = 0.0                            # 0 / 0 curves
+    psums[:] = rng.random((b, 5)) * n
+    h = rng.multinomial(n * c, np.full(nzp, 1.0 / nzp), size=b).astype(np.int64)
+    hist_v[:] = h.view(np.float64)
+    return packed, cuts
+
+
+@pytest.mark.parametrize("kind", ["plain", "oracle_wins", "nan", "zero"])
+@pytest.mark.parametrize("b,n", [(1, 640000), (5, 1089480), (3, 37), (2, 100)])
+def test_native_score_tail_equals_numpy_tail(kind, b, n):
+    """ub_score_tail_host (csrc/score_tail.cu, a HOST function of the C ABI) against the numpy statement of the same
+    tail, bit for bit: dtypes of the curves included (the oracle curve is float32 unless the by-uncertainty maximum
+    wins), np.trapz's pairwise row sums included, NaN placement included."""
+    from uncertainty_nerf_gs_b200 import metrics as M
+
+    rng = np.random.default_rng(hash((kind, b, n)) % (1 << 32))
+    c = 3
+    nzp = len(M.z_values_host()) + 1
+    packed, cuts = _random_packed(rng, b, n, c, nzp, kind)
+    with np.errstate(all="ignore"):
+        want = M._numpy_tail(packed, b, n, c, cuts)
+    got = M._native_tail(packed, b, n, c, cuts)
+    assert len(got) == len(want) == b
+    for dg, dw in zip(got, want):
+        assert list(dg.keys()) == list(dw.keys())
+        for k in dw:
+            g, w = np.asarray(dg[k]), np.asarray(dw[k])
+            assert g.dtype == w.dtype, (k, g.dtype, w.dtype)
+            assert g.shape == w.shape, k
+            assert np.array_equal(np.atleast_1d(g).view(np.uint8), np.atleast_1d(w).view(np.uint8)) or \
+                np.array_equal(g, w, equal_nan=True), k       # same bits (NaN payloads aside)

@@ -228,7 +228,10 @@ __global__ void __launch_bounds__(kPrologueThreads, 3) score_prologue_kernel(con
 #pragma unroll
       for (int c = 1; c < C; ++c) m_max = fmaxf(m_max, fabsf(pr[px * C + c]));
       const bool guard_ok = sigma > 1e-30f && sigma < 1e30f && sigma * kSigmaGuard >= m_max;
-      const float r_mul = guard_ok ? inv_sigma : __int_as_float(0x7FC00000);
+      // sigma == 0 exactly (an empty ray: all weights zero) is common enough to keep out of tier 3: every interval is
+      // the point m, so the count is 0 unless t == m -- an infinite multiplier makes the ratio inf (table entry "no
+      // threshold holds") for d != 0 and NaN (-> the exact path) for d == 0
+      const float r_mul = guard_ok ? inv_sigma : (sigma == 0.f ? __int_as_float(0x7F800000) : __int_as_float(0x7FC00000));
       float se_px = 0.f, ae_px = 0.f, nll_px = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {

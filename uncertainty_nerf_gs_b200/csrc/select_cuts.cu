@@ -71,8 +71,7 @@ struct SegPlan {
   int flags;  // bit 0: the segment holds negative keys, bit 1: it holds NaN keys (from the coarse histogram)
   int pad2;
   uint32_t heavy[kSelMaxHeavy];      // heavy tie values (any order)
-  uint32_t tkey[kSelMaxHeavy];       // tiled cells: tie groups that hold a cut and are resolved by tile
-  int tcell[kSelMaxHeavy];
+  int tcell[kSelMaxHeavy];           // tiled cells: tie groups that hold a cut and are resolved by tile
   int theavy[kSelMaxHeavy];          // tiled cell -> index of its key among the heavy tie values (row of tilecounts)
   int cut_k[kSelMaxCuts];            // original index of the j-th smallest cut
   int cut_T[kSelMaxCuts];            // bins < T are under the cut
@@ -84,7 +83,7 @@ struct SegPlan {
   uint32_t cell_count[kSelMaxCuts];
   uint32_t cell_comp[kSelMaxCuts];   // records in the cell's slot
   int cell_j0[kSelMaxCuts], cell_j1[kSelMaxCuts];  // cuts [j0, j1) lie inside the cell
-  int cell_tiled[kSelMaxCuts];       // index into tkey / tcell, -1: the whole cell goes to the side list
+  int cell_tiled[kSelMaxCuts];       // index into tcell / theavy, -1: the whole cell goes to the side list
 };
 
 struct SelParams {
@@ -110,7 +109,7 @@ struct SelParams {
   uint32_t* table;        // [G][kSelCoarse]: (first fine bin << 5) | shift of the low 20 key bits
   SegPlan* plan;          // [G]
   uint16_t* binmap;       // [G][kSelBins]: class, or kSelCellFlag | cell
-  uint32_t* tilecounts;   // [G][kSelMaxHeavy][max_tiles] per heavy tie value; after sel_plan_tiled, rows of tiled cells:
+  uint32_t* tilecounts;   // [G][kSelMaxHeavy][max_tiles] per heavy tie value; after sel_locate, rows of tiled cells:
                           // first record of (tiled cell, tile)
   uint8_t* tilemode;      // [G][max_tiles][kSelMaxHeavy]: class of the tie group's members in the tile, or kSelCompact
   double* spart;          // [G][max_blocks][num_cuts + 1][2]
@@ -308,7 +307,7 @@ __device__ __forceinline__ uint32_t sel_key(float f) {
 // value by value over all eight keys (one shared-memory load per heavy value instead of eight)
 // `tcnt` (fine histogram only): per heavy value, the number of its occurrences among these eight keys per thread --
 // one 2048-key tile per block-wide call -- is added to tcnt[h] (stable order inside a tie group is the element order,
-// so a tie group that turns out to hold a cut is resolved from these per-tile counts, see sel_plan_tiled)
+// so a tie group that turns out to hold a cut is resolved from these per-tile counts, see sel_plan_tiled_cell)
 template <bool NONNEG, bool COUNT = false>
 __device__ __forceinline__ void sel_bins8(const float (&v)[8], const uint32_t* __restrict__ tab,
                                           const uint32_t* heavy, int nh, uint32_t (&u)[8], int (&bin)[8],
@@ -618,7 +617,6 @@ __global__ void __launch_bounds__(kSelLocThreads, 2) sel_locate(const SelParams 
     if (s_celltiled[cell] >= 0) {
       ti = s_tmp[cell];
       for (int w = 0; w < warp; ++w) ti += s_wc2[w];
-      pl.tkey[ti] = pl.heavy[s_celltiled[cell]];
       pl.tcell[ti] = cell;
       pl.theavy[ti] = s_celltiled[cell];
     }
@@ -676,16 +674,13 @@ __global__ void __launch_bounds__(kSelLocThreads, 2) sel_locate(const SelParams 
   for (int h = 0; h < ntiled; ++h) sel_plan_tiled_cell<kLocWarps>(p, g, h);
 }
 
-// first record of every cell's slot within the segment's side list (s_base[ncells] = all records) and the
-// biggest tie-group cell; every thread of the block must call it
-__device__ __forceinline__ void sel_cell_bases(const SegPlan& pl, uint32_t* s_base, uint32_t* warp_tmp,
-                                               uint32_t* s_hot) {
+// first record of every cell's slot within the segment's side list (s_base[ncells] = all records); every thread of
+// the block must call it
+__device__ __forceinline__ void sel_cell_bases(const SegPlan& pl, uint32_t* s_base, uint32_t* warp_tmp) {
   const int tid = threadIdx.x, ncells = pl.ncells;
-  if (tid == 0) *s_hot = 0u;
   const uint32_t v = tid < ncells ? pl.cell_comp[tid] : 0u;
   const uint32_t ex = sel_block_excl_scan(v, warp_tmp, nullptr);  // syncs
   if (tid <= ncells && tid <= kSelMaxCuts) s_base[tid] = ex;
-  if (tid < ncells && pl.cell_tiled[tid] >= 0) atomicMax(s_hot, (pl.cell_count[tid] << 7) | (uint32_t)tid);
   __syncthreads();
 }
 
@@ -718,7 +713,6 @@ struct ClassifyShared {
   uint32_t cur[kSelMaxTilesPerBlock][kSelMaxHeavy];   // records of (tile, tiled cell) written so far
   uint16_t tmode[kSelMaxTilesPerBlock][kSelMaxHeavy]; // class of the tie group's members in the tile, or kSelCellFlag | cell
   uint32_t warp_tmp[kSelWarps];
-  uint32_t hot;
   uint32_t vmax[2];                 // bits of the largest finite |payload| of the block
   uint32_t vneg;                    // a payload of the block is negative
   uint32_t rqn[kSelWarps];          // per warp: positions queued for the general path
@@ -941,7 +935,7 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
   if (tid == 2) sh.vneg = 0u;
   if (tid < kSelWarps) sh.rqn[tid] = 0u;
   if (tid < kSelMaxCuts) sh.tiled[tid] = tid < ncells ? (int8_t)pl.cell_tiled[tid] : (int8_t)-1;
-  sel_cell_bases(pl, sh.base, sh.warp_tmp, &sh.hot);
+  sel_cell_bases(pl, sh.base, sh.warp_tmp);
   if (blockIdx.x == 0 && tid < nc) {  // the resolve blocks find their slot without redoing the scan
     const int cell = pl.cut_cell[tid];
     if (cell >= 0) pl.run[tid].base = sh.base[cell];

@@ -206,15 +206,19 @@ _ONE_MINUS_ALPHA: Optional[np.ndarray] = None
 _ALPHA_STEPS: Optional[np.ndarray] = None
 
 
-def _auce_from_hist_batch(hist: np.ndarray, sigma_sum: np.ndarray, n: np.ndarray, z: np.ndarray) -> List[Dict[str, object]]:
-    """auce.py:24-54 from the interval histograms ``hist [B, nz+1]``: coverage_k = #{elements satisfying > k
-    thresholds} / n; mean interval length = 2 z_k mean(sigma) (equal to the reference's float64
-    ``mean(upper - lower)`` to ~2e-16 relative).  ``sigma_sum, n``: per-image float64."""
+def _alpha_tables() -> None:
     global _ALPHA_ARR, _ONE_MINUS_ALPHA, _ALPHA_STEPS
     if _ALPHA_ARR is None:
         _ALPHA_ARR = np.array(_alphas())
         _ONE_MINUS_ALPHA = 1.0 - _ALPHA_ARR
         _ALPHA_STEPS = np.diff(_ALPHA_ARR)
+
+
+def _auce_from_hist_batch(hist: np.ndarray, sigma_sum: np.ndarray, n: np.ndarray, z: np.ndarray) -> List[Dict[str, object]]:
+    """auce.py:24-54 from the interval histograms ``hist [B, nz+1]``: coverage_k = #{elements satisfying > k
+    thresholds} / n; mean interval length = 2 z_k mean(sigma) (equal to the reference's float64
+    ``mean(upper - lower)`` to ~2e-16 relative).  ``sigma_sum, n``: per-image float64."""
+    _alpha_tables()
     inside = np.cumsum(hist[:, ::-1], axis=1)[:, ::-1][:, 1:]  # count with c > k, k = 0..nz-1
     with np.errstate(divide="ignore", invalid="ignore"):
         coverage = inside.astype(np.float64) / n[:, None]
@@ -352,35 +356,81 @@ class PendingScores:
     def _finish(self) -> List[Dict[str, object]]:
         self.done.synchronize()
         packed = self.packed_host.numpy()
-        b, n, c, cuts_one = self.b, self.n, self.c, self.cuts_one
-        zh = z_values_host()
-        sums_v, psums, hist_v = _packed_views(packed, b, len(zh) + 1)
-        bu_ae, bu_se, or_ae, or_se = sums_v[:, 0], sums_v[:, 1], sums_v[:, 2], sums_v[:, 3]
-        hist = np.ascontiguousarray(hist_v).view(np.int64)
-        # all twelve curves of the batch in three numpy expressions: rows = (image, {mae, mse, rmse})
-        ora = _prefix_means(np.stack([or_ae, or_se, or_se], axis=1), cuts_one, "mae")      # [B, 3, 100] float32
-        byu = _prefix_means(np.stack([bu_ae, bu_se, bu_se], axis=1), cuts_one, "mae")
-        with np.errstate(invalid="ignore"):
-            ora[:, 2] = np.sqrt(ora[:, 2])                                                   # rmse: torch.sqrt of the mean
-            byu[:, 2] = np.sqrt(byu[:, 2])
-        o_all, v_all, a_all = _ause_tail_batch(ora.reshape(b * 3, 100), byu.reshape(b * 3, 100))
-        tails = {et: (o_all[k::3], v_all[k::3], a_all[k::3]) for k, et in enumerate(("mae", "mse", "rmse"))}
-        nll = (psums[:, 3] / (n * c)).astype(np.float32)
-        avg_var = (psums[:, 2] / n).astype(np.float32)
-        mse_mean = (psums[:, 0] / n).astype(np.float32)
-        auce_rows = _auce_from_hist_batch(hist, psums[:, 4] * c, np.full(b, float(n * c)), zh)
-        results = []
-        for i in range(b):
-            d: Dict[str, object] = {}
-            for et in ("mae", "mse", "rmse"):
-                o, v, a = tails[et]
-                d[f"err_{et}"], d[f"err_var_{et}"], d[f"ause_{et}"] = o[i], v[i], a[i]
-            d["nll_rgb"] = float(nll[i])
-            d["avg_var"] = float(avg_var[i])
-            d["mse_mean"] = float(mse_mean[i])
-            d.update(auce_rows[i])
-            results.append(d)
-        return results
+        if os.environ.get("UB_NUMPY_TAIL", "0") != "1":
+            return _native_tail(packed, self.b, self.n, self.c, self.cuts_one)
+        return _numpy_tail(packed, self.b, self.n, self.c, self.cuts_one)
+
+
+def _native_tail(packed: np.ndarray, b: int, n: int, c: int, cuts_one: np.ndarray) -> List[Dict[str, object]]:
+    """The host tail of ``score_rgb_batch`` in one native call (``ub_score_tail_host``, csrc/score_tail.cu): the
+    reference's numpy / torch expressions downstream of the device results, operation by operation in the reference's
+    dtypes -- bit-identical to ``_numpy_tail`` (tests/test_host_logic.py), ~2 us per image instead of 0.2 ms + 17 us."""
+    from . import _lib
+
+    lib = _lib.load()
+    zh = z_values_host()
+    _alpha_tables()
+    nz, nc = len(zh), len(cuts_one)
+    packed = np.ascontiguousarray(packed, dtype=np.float64)
+    cuts = np.ascontiguousarray(cuts_one, dtype=np.int64)
+    by_unc, o64 = np.empty((b, 3, nc)), np.empty((b, 3, nc))
+    o32, is64 = np.empty((b, 3, nc), dtype=np.float32), np.empty((b, 3), dtype=np.int32)
+    ause_v, scal = np.empty((b, 3)), np.empty((b, 3), dtype=np.float32)
+    curves, auc = np.empty((b, 5, nz)), np.empty((b, 3))
+    _lib.check(lib.ub_score_tail_host(packed.ctypes.data, b, n, c, cuts.ctypes.data, nc, _RATIO_STEPS.ctypes.data,
+                                      zh.ctypes.data, nz, _ONE_MINUS_ALPHA.ctypes.data, _ALPHA_STEPS.ctypes.data,
+                                      by_unc.ctypes.data, o64.ctypes.data, o32.ctypes.data, is64.ctypes.data,
+                                      ause_v.ctypes.data, scal.ctypes.data, curves.ctypes.data, auc.ctypes.data))
+    # rows as lists of array views / scalars (one C call each) instead of b x 20 numpy index expressions
+    o64r, o32r, bur = list(o64.reshape(b * 3, nc)), list(o32.reshape(b * 3, nc)), list(by_unc.reshape(b * 3, nc))
+    w64, au, sc = is64.ravel().tolist(), list(ause_v.ravel()), scal.ravel().tolist()
+    cv, ac = list(curves.reshape(b * 5, nz)), list(auc.ravel())
+    results = []
+    for i in range(b):
+        j, q = 3 * i, 5 * i
+        results.append({
+            "err_mae": o64r[j] if w64[j] else o32r[j], "err_var_mae": bur[j], "ause_mae": au[j],
+            "err_mse": o64r[j + 1] if w64[j + 1] else o32r[j + 1], "err_var_mse": bur[j + 1], "ause_mse": au[j + 1],
+            "err_rmse": o64r[j + 2] if w64[j + 2] else o32r[j + 2], "err_var_rmse": bur[j + 2], "ause_rmse": au[j + 2],
+            "nll_rgb": sc[j], "avg_var": sc[j + 1], "mse_mean": sc[j + 2],
+            "coverage_values": cv[q], "avg_length_values": cv[q + 1], "coverage_error_values": cv[q + 2],
+            "abs_coverage_error_values": cv[q + 3], "neg_coverage_error_values": cv[q + 4],
+            "auc_abs_error_values": ac[j], "auc_length_values": ac[j + 1], "auc_neg_error_values": ac[j + 2],
+        })
+    return results
+
+
+def _numpy_tail(packed: np.ndarray, b: int, n: int, c: int, cuts_one: np.ndarray) -> List[Dict[str, object]]:
+    """The same tail as numpy expressions (the statement the native tail is checked against; ``UB_NUMPY_TAIL=1``
+    routes ``finish()`` through it)."""
+    zh = z_values_host()
+    sums_v, psums, hist_v = _packed_views(packed, b, len(zh) + 1)
+    bu_ae, bu_se, or_ae, or_se = sums_v[:, 0], sums_v[:, 1], sums_v[:, 2], sums_v[:, 3]
+    hist = np.ascontiguousarray(hist_v).view(np.int64)
+    # all twelve curves of the batch in three numpy expressions: rows = (image, {mae, mse, rmse})
+    ora = _prefix_means(np.stack([or_ae, or_se, or_se], axis=1), cuts_one, "mae")      # [B, 3, 100] float32
+    byu = _prefix_means(np.stack([bu_ae, bu_se, bu_se], axis=1), cuts_one, "mae")
+    with np.errstate(invalid="ignore"):
+        ora[:, 2] = np.sqrt(ora[:, 2])                                                   # rmse: torch.sqrt of the mean
+        byu[:, 2] = np.sqrt(byu[:, 2])
+    o_all, v_all, a_all = _ause_tail_batch(ora.reshape(b * 3, 100), byu.reshape(b * 3, 100))
+    tails = {et: (o_all[k::3], v_all[k::3], a_all[k::3]) for k, et in enumerate(("mae", "mse", "rmse"))}
+    nll = (psums[:, 3] / (n * c)).astype(np.float32)
+    avg_var = (psums[:, 2] / n).astype(np.float32)
+    mse_mean = (psums[:, 0] / n).astype(np.float32)
+    auce_rows = _auce_from_hist_batch(hist, psums[:, 4] * c, np.full(b, float(n * c)), zh)
+    results = []
+    for i in range(b):
+        d: Dict[str, object] = {}
+        for et in ("mae", "mse", "rmse"):
+            o, v, a = tails[et]
+            d[f"err_{et}"], d[f"err_var_{et}"], d[f"ause_{et}"] = o[i], v[i], a[i]
+        d["nll_rgb"] = float(nll[i])
+        d["avg_var"] = float(avg_var[i])
+        d["mse_mean"] = float(mse_mean[i])
+        d.update(auce_rows[i])
+        results.append(d)
+    return results
 
 
 def score_rgb_batch(rgb_pred: Tensor, rgb_gt: Tensor, rgb_std: Tensor, min_rgb_std_for_nll: float = 3e-2
