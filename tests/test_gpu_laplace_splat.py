@@ -279,3 +279,31 @@ def test_splat_producers_edge_cases(built_library):
     assert float(a.detach().abs().max()) == 0.0 and torch.equal(img.detach()[0, 0].cpu(), torch.tensor([0.25, 0.5, 0.75]))
     (img.sum() + a.sum()).backward()
     assert float(rgbs.grad.abs().max()) == 0.0 and float(x.grad.abs().max()) == 0.0
+
+
+def test_laplace_density_head_on_tensor_cores_opt_in(built_library):
+    """UB_LAPLACE_TC_DENSITY=1 (read once per process, so a child process): the density head as a [P,64] x [64,100]
+    tcgen05 GEMM.  Faster, but exp amplifies the tensor core's truncating accumulation: 5e-5 relative, not 1e-5 --
+    the reason it is not the default."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import torch, sys
+sys.path.insert(0, ".")
+from oracle import laplace as ol
+from uncertainty_nerf_gs_b200 import ops, synthetic
+lap = synthetic.laplace_head(1500, 64, 1, 100, seed=1)
+lap["mu_q"] = lap["mu_q"] * 0.2
+theta = ol.posterior_samples(lap["mu_q"], lap["ggn"], lap["eps_draws"])
+mu, mu2, s2 = ol.sample_laplace(lap["x"], theta, 1, torch.exp)
+out = ops.laplace_ll_moments(lap["x"].cuda(), theta.cuda(), 1, "exp", want_mean2=True)
+torch.testing.assert_close(out["mean"].cpu(), mu, rtol=5e-5, atol=1e-6)
+torch.testing.assert_close(out["mean2"].cpu(), mu2, rtol=1e-4, atol=1e-6)
+print("ok")
+'''
+    env = dict(os.environ, UB_LAPLACE_TC_DENSITY="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr

@@ -17,7 +17,7 @@
 namespace ub {
 
 // tensor-core path (laplace_moments_tc.cu); UB_ERR_UNSUPPORTED when the shape does not fit it
-int launch_laplace_tc(const float* x, long long num_points, const float* params, int n_samples, int act,
+int launch_laplace_tc(const float* x, long long num_points, const float* params, int n_samples, int out_dim, int act,
                       float* o_mean, float* o_mean2, float* o_sigma2, cudaStream_t stream);
 
 constexpr int kLapThreads = 128;
@@ -174,17 +174,22 @@ extern "C" int ub_laplace_ll_moments(const float* x, int64_t num_points, int32_t
   UB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0, UB_ERR_UNSUPPORTED,
              "laplace_ll_moments: x must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (out_dim == 3) {
-    // rgb head: tcgen05 3xTF32 path unless UB_LAPLACE_FMA=1 forces the fp32-FMA kernel
-    static const bool force_fma = [] { const char* e = getenv("UB_LAPLACE_FMA"); return e && atoi(e) != 0; }();
-    if (!force_fma && !no_tc) {
-      const int rc = launch_laplace_tc(x, num_points, sampled_params, n_samples, activation, out_mean, out_mean2,
-                                       out_sigma2, stream);
-      if (rc != UB_ERR_UNSUPPORTED) return rc;
-    }
-    return launch_laplace<3, 2>(x, num_points, sampled_params, n_samples, activation, out_mean, out_mean2,
-                                out_sigma2, stream);
+  // tcgen05 3xTF32 path unless UB_LAPLACE_FMA=1 or the caller's flag forces the fp32-FMA kernel, which also takes the
+  // shapes the tensor-core kernel does not (> 304 columns).  rgb head: always.  Density head: the same GEMM with the
+  // draws as its N dimension runs 2.4x faster there (0.20 vs 0.49 ms per 1.05 M points), but the tensor core adds
+  // into its float32 accumulator with truncation -- 24 accumulations x ulp(v) -- and exp turns that absolute error of
+  // the pre-activation into a relative error of the output: 1.1e-5 at v ~ 7, outside the 1e-5 contract (sigmoid
+  // damps it by >= 4).  Hence opt-in: UB_LAPLACE_TC_DENSITY=1.
+  static const bool force_fma = [] { const char* e = getenv("UB_LAPLACE_FMA"); return e && atoi(e) != 0; }();
+  static const bool tc_density = [] { const char* e = getenv("UB_LAPLACE_TC_DENSITY"); return e && atoi(e) != 0; }();
+  if (!force_fma && !no_tc && (out_dim == 3 || tc_density)) {
+    const int rc = launch_laplace_tc(x, num_points, sampled_params, n_samples, out_dim, activation, out_mean, out_mean2,
+                                     out_sigma2, stream);
+    if (rc != UB_ERR_UNSUPPORTED) return rc;
   }
-  return launch_laplace<1, 2>(x, num_points, sampled_params, n_samples, activation, out_mean, out_mean2,
-                              out_sigma2, stream);
+  if (out_dim == 3)
+    return launch_laplace<3, 2>(x, num_points, sampled_params, n_samples, activation, out_mean, out_mean2, out_sigma2,
+                                stream);
+  return launch_laplace<1, 2>(x, num_points, sampled_params, n_samples, activation, out_mean, out_mean2, out_sigma2,
+                              stream);
 }

@@ -2,7 +2,9 @@
 //
 // Reference arithmetic: models/laplace/laplace_field.py:545-565 (see laplace_moments.cu).  For the rgb head
 // this is a [P,64] x [64,300] GEMM followed by sigmoid and a reduction over the 100 parameter draws --
-// the one GEMM-shaped, compute-bound step of the path (38.4 kflop per point against 256 B).
+// the one GEMM-shaped, compute-bound step of the path (38.4 kflop per point against 256 B).  The density head
+// (one output, exp) is the same GEMM with the draws alone as its N dimension ([P,64] x [64,100]): template O = 1,
+// only the first accumulator half is computed.
 //
 // One CTA per SM, 512 threads, a tile = 128 points:
 //   * A (features) and B (all sampled weight rows, 3 per draw) are split x = hi + lo with hi = x truncated
@@ -32,7 +34,6 @@ constexpr int kTcN = kTcN0 + kTcN1;
 constexpr int kTcRowGroupBytes = (kTcH / 4) * 128;  // 2048: 16 K-chunks x (8 rows x 16 B)
 constexpr uint32_t kTcTmemCols = 512;
 constexpr uint32_t kTcTmemCol1 = 256;    // column offset of the second accumulator half
-constexpr int kTcO = 3;
 
 struct TcSmem {
   float a_hi[kTcM * kTcH];
@@ -105,8 +106,8 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
-// one 16-column chunk of this thread's point: activation and per-channel partial sums (by i % 3)
-template <int ACT, bool FULL>
+// one 16-column chunk of this thread's point: activation and per-channel partial sums (by i % O)
+template <int ACT, int O, bool FULL>
 __device__ __forceinline__ void epilogue_chunk(const float* v, const float* bias, int valid, float* t, float* t2) {
   const float4* b4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll
@@ -126,13 +127,13 @@ __device__ __forceinline__ void epilogue_chunk(const float* v, const float* bias
         y = v[i] + bb[e];
       }
       if (!FULL && i >= valid) y = 0.f;
-      t[i % kTcO] += y;
-      t2[i % kTcO] = fmaf(y, y, t2[i % kTcO]);
+      t[i % O] += y;
+      t2[i % O] = fmaf(y, y, t2[i % O]);
     }
   }
 }
 
-template <int ACT>
+template <int ACT, int O>
 __global__ void __launch_bounds__(kTcThreads, 1)
 laplace_moments_tc_kernel(const float* __restrict__ x, long long num_points,
                           const float* __restrict__ params, int n_samples,
@@ -140,10 +141,11 @@ laplace_moments_tc_kernel(const float* __restrict__ x, long long num_points,
                           float* __restrict__ o_sigma2) {
   extern __shared__ __align__(128) unsigned char tc_smem_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(tc_smem_raw);
-  constexpr int O = kTcO;
+  static_assert(O == 1 || O == 3, "density or rgb head");
   constexpr int NP = O * kTcH + O;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int ncols = n_samples * O;  // <= 300 valid accumulator columns
+  const int ncols = n_samples * O;  // <= 304 valid accumulator columns
+  const bool two_halves = ncols > kTcN0;  // the density head's 100 columns fit the first accumulator half
   unsigned char* a_hi_b = reinterpret_cast<unsigned char*>(sm.a_hi);
   unsigned char* a_lo_b = reinterpret_cast<unsigned char*>(sm.a_lo);
 
@@ -213,7 +215,7 @@ laplace_moments_tc_kernel(const float* __restrict__ x, long long num_points,
         const uint32_t idesc = half ? umma_idesc_tf32(kTcM, kTcN1) : umma_idesc_tf32(kTcM, kTcN0);
         const uint32_t brow = half ? (uint32_t)(kTcN0 / 8) * kTcRowGroupBytes : 0u;
 #pragma unroll
-        for (int ks = 0; ks < kTcH / 8; ++ks) {
+        for (int ks = 0; ks < kTcH / 8 && (half == 0 || two_halves); ++ks) {
           const uint32_t ko = (uint32_t)ks * 256u;  // two 128-byte K chunks per instruction
           const uint64_t dah = umma_desc(a_hi + ko), dal = umma_desc(a_lo + ko);
           const uint64_t dbh = umma_desc(b_hi + brow + ko), dbl = umma_desc(b_lo + brow + ko);
@@ -227,7 +229,7 @@ laplace_moments_tc_kernel(const float* __restrict__ x, long long num_points,
     prefetch(tile + gridDim.x);  // global loads of the next tile fly while this one is in the tensor core
 
     // ---- epilogue: this thread's point, 16-column chunks c = group, group + 4, ... ----
-    float mu[O] = {0.f, 0.f, 0.f}, mu2[O] = {0.f, 0.f, 0.f};
+    float mu[3] = {0.f, 0.f, 0.f}, mu2[3] = {0.f, 0.f, 0.f};
     bool waited1 = false;
     mbar_wait(&sm.mma_bar[0], phase);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -242,10 +244,10 @@ laplace_moments_tc_kernel(const float* __restrict__ x, long long num_points,
       const uint32_t col = c0 < kTcN0 ? (uint32_t)c0 : kTcTmemCol1 + (uint32_t)(c0 - kTcN0);
       float v[16];
       tmem_ld16(tmem + lane_base + col, v);
-      float t[O] = {0.f, 0.f, 0.f}, t2[O] = {0.f, 0.f, 0.f};  // by (i % 3), relative to the chunk start
-      if (c0 + 16 <= ncols) epilogue_chunk<ACT, true>(v, sm.bias + c0, 16, t, t2);
-      else epilogue_chunk<ACT, false>(v, sm.bias + c0, ncols - c0, t, t2);
-      const int ph = c % O;  // channel of the chunk's first column: (16 c) % 3 == c % 3
+      float t[3] = {0.f, 0.f, 0.f}, t2[3] = {0.f, 0.f, 0.f};  // by (i % O), relative to the chunk start
+      if (c0 + 16 <= ncols) epilogue_chunk<ACT, O, true>(v, sm.bias + c0, 16, t, t2);
+      else epilogue_chunk<ACT, O, false>(v, sm.bias + c0, ncols - c0, t, t2);
+      const int ph = c % O;  // channel of the chunk's first column: (16 c) % 3 == c % 3 (0 for one output)
       if (ph == 0) {
         mu[0] += t[0]; mu[1] += t[1]; mu[2] += t[2]; mu2[0] += t2[0]; mu2[1] += t2[1]; mu2[2] += t2[2];
       } else if (ph == 1) {
@@ -265,7 +267,7 @@ laplace_moments_tc_kernel(const float* __restrict__ x, long long num_points,
     }
     __syncthreads();
     if (group == 0 && ok) {
-      float sm1[O] = {0.f, 0.f, 0.f}, sm2[O] = {0.f, 0.f, 0.f};
+      float sm1[3] = {0.f, 0.f, 0.f}, sm2[3] = {0.f, 0.f, 0.f};
 #pragma unroll
       for (int g = 0; g < kTcGroups; ++g) {
         const float4 a = *reinterpret_cast<const float4*>(red + ((size_t)g * kTcM + row) * 8);
@@ -292,11 +294,11 @@ laplace_moments_tc_kernel(const float* __restrict__ x, long long num_points,
   }
 }
 
-template <int ACT>
+template <int ACT, int O>
 static int launch_tc(const float* x, long long num_points, const float* params, int n_samples, float* o_mean,
                      float* o_mean2, float* o_sigma2, cudaStream_t stream) {
   const size_t smem = sizeof(TcSmem) + 128;
-  auto kern = laplace_moments_tc_kernel<ACT>;
+  auto kern = laplace_moments_tc_kernel<ACT, O>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -310,14 +312,16 @@ static int launch_tc(const float* x, long long num_points, const float* params, 
 }
 
 // returns UB_ERR_UNSUPPORTED when the shape does not fit this path (caller falls back to the FMA kernel)
-int launch_laplace_tc(const float* x, long long num_points, const float* params, int n_samples, int act,
-                      float* o_mean, float* o_mean2, float* o_sigma2, cudaStream_t stream) {
-  if (n_samples * kTcO > kTcN) return UB_ERR_UNSUPPORTED;
-  if (act == UB_ACT_SIGMOID)
-    return launch_tc<UB_ACT_SIGMOID>(x, num_points, params, n_samples, o_mean, o_mean2, o_sigma2, stream);
-  if (act == UB_ACT_EXP)
-    return launch_tc<UB_ACT_EXP>(x, num_points, params, n_samples, o_mean, o_mean2, o_sigma2, stream);
-  return launch_tc<UB_ACT_IDENTITY>(x, num_points, params, n_samples, o_mean, o_mean2, o_sigma2, stream);
+int launch_laplace_tc(const float* x, long long num_points, const float* params, int n_samples, int out_dim,
+                      int act, float* o_mean, float* o_mean2, float* o_sigma2, cudaStream_t stream) {
+  if ((out_dim != 1 && out_dim != 3) || n_samples * out_dim > kTcN) return UB_ERR_UNSUPPORTED;
+#define UB_TC(A)                                                                                              \
+  return out_dim == 3 ? launch_tc<A, 3>(x, num_points, params, n_samples, o_mean, o_mean2, o_sigma2, stream) \
+                      : launch_tc<A, 1>(x, num_points, params, n_samples, o_mean, o_mean2, o_sigma2, stream)
+  if (act == UB_ACT_SIGMOID) UB_TC(UB_ACT_SIGMOID);
+  if (act == UB_ACT_EXP) UB_TC(UB_ACT_EXP);
+  UB_TC(UB_ACT_IDENTITY);
+#undef UB_TC
 }
 
 }  // namespace ub
