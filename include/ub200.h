@@ -301,12 +301,14 @@ int ub_cut_prefix_sums(const float* const* values_host, const int32_t* const* pe
  * float64 (out_oracle64) and as float32 (out_oracle32) with out_oracle_is64 [V][3] saying which of the two the
  * reference's dtype rules produce -- and out_ause [V][3]; out_scalars [V][3] = nll, avg_var, mse mean (float32);
  * out_auce_curves [V][5][num_z] = coverage, interval length, coverage error, abs, neg (metrics/auce.py:24-45);
- * out_auc [V][3] = areas of abs error, length, neg error (:47-54).  cuts [num_cuts]: the slice lengths int((1-r) n);
+ * out_auc [V][3] = areas of abs error, length, neg error (:47-54).  num_pixels [V]: pixels per view (ragged for the
+ * masked depth modality, get_unc_metrics_depth :415-644 with channels = 1); cuts [V][num_cuts]: its slice lengths
+ * int((1-r) n);
  * ratio_steps [num_cuts - 1] = diff of the removal ratios; one_minus_alpha [num_z], alpha_steps [num_z - 1].
  * Every operation runs in the dtype and order numpy uses for the reference's expressions (pairwise row sums of
  * np.trapz included): the results equal the numpy evaluation bit for bit. */
-int ub_score_tail_host(const double* packed, int32_t num_views, int64_t n, int32_t channels, const int64_t* cuts,
-                       int32_t num_cuts, const double* ratio_steps, const double* z_values, int32_t num_z,
+int ub_score_tail_host(const double* packed, int32_t num_views, const int64_t* num_pixels, int32_t channels,
+                       const int64_t* cuts, int32_t num_cuts, const double* ratio_steps, const double* z_values, int32_t num_z,
                        const double* one_minus_alpha, const double* alpha_steps, double* out_by_unc,
                        double* out_oracle64, float* out_oracle32, int32_t* out_oracle_is64, double* out_ause,
                        float* out_scalars, double* out_auce_curves, double* out_auc);

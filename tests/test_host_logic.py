@@ -220,3 +220,31 @@ def test_native_score_tail_equals_numpy_tail(kind, b, n):
             assert g.shape == w.shape, k
             assert np.array_equal(np.atleast_1d(g).view(np.uint8), np.atleast_1d(w).view(np.uint8)) or \
                 np.array_equal(g, w, equal_nan=True), k       # same bits (NaN payloads aside)
+
+
+def test_native_score_tail_ragged_depth_views():
+    """The depth modality: one channel, a different pixel count (hence different slice lengths) per view, a view with
+    no valid pixel at all.  Native tail == the per-view numpy statement, bit for bit."""
+    from uncertainty_nerf_gs_b200 import metrics as M
+
+    rng = np.random.default_rng(5)
+    lens = [40000, 0, 1237, 99, 7]
+    b = len(lens)
+    nzp = len(M.z_values_host()) + 1
+    packed = np.zeros(b * (400 + 5 + nzp))
+    sums_v, psums, hist_v = M._packed_views(packed, b, nzp)
+    cuts = np.stack([M.ause_cut_counts(n) for n in lens])
+    sums_v[:] = cuts[:, None, :] * (rng.random((b, 4, 1)) + 0.1) * (1.0 + 0.3 * rng.random((b, 4, 100)))
+    psums[:] = rng.random((b, 5)) * np.asarray(lens)[:, None]
+    h = np.stack([rng.multinomial(n, np.full(nzp, 1.0 / nzp)) for n in lens]).astype(np.int64)
+    hist_v[:] = h.view(np.float64)
+    with np.errstate(all="ignore"):
+        want = M._numpy_depth_tail(packed, b, lens, cuts)
+    got = M._native_tail(packed, b, np.asarray(lens, dtype=np.int64), 1, cuts, nll_key="nll_depth")
+    for dg, dw in zip(got, want):
+        assert list(dg.keys()) == list(dw.keys())
+        for k in dw:
+            g, w = np.asarray(dg[k]), np.asarray(dw[k])
+            assert g.dtype == w.dtype and g.shape == w.shape, k
+            assert np.array_equal(np.atleast_1d(g).view(np.uint8), np.atleast_1d(w).view(np.uint8)) or \
+                np.array_equal(g, w, equal_nan=True), k

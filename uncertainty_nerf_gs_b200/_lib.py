@@ -106,7 +106,7 @@ SIGNATURES = {
                                      C.c_int64, C.c_int64, fp, C.c_int32, fp, fp, C.c_size_t, fp]),
     "ub_cut_select_sums_ex": (C.c_int, [C.POINTER(fp), C.POINTER(fp), C.POINTER(fp), C.c_int32, C.c_int32, fp,
                                         C.c_int64, C.c_int64, fp, C.c_int32, fp, fp, fp, C.c_size_t, fp]),
-    "ub_score_tail_host": (C.c_int, [fp, C.c_int32, C.c_int64, C.c_int32, fp, C.c_int32, fp, fp, C.c_int32, fp, fp,
+    "ub_score_tail_host": (C.c_int, [fp, C.c_int32, fp, C.c_int32, fp, C.c_int32, fp, fp, C.c_int32, fp, fp,
                                      fp, fp, fp, fp, fp, fp, fp, fp]),
     "ub_laplace_ll_moments": (C.c_int, [fp, C.c_int64, C.c_int32, C.c_int32, fp, C.c_int32, C.c_int32,
                                         fp, fp, fp, fp]),

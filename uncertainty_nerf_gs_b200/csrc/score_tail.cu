@@ -58,18 +58,18 @@ static T py_max(const T* a, int n) {
 
 extern "C" {
 
-int ub_score_tail_host(const double* packed, int32_t num_views, int64_t n, int32_t channels, const int64_t* cuts,
-                       int32_t num_cuts, const double* ratio_steps, const double* z_values, int32_t num_z,
+int ub_score_tail_host(const double* packed, int32_t num_views, const int64_t* num_pixels, int32_t channels,
+                       const int64_t* cuts, int32_t num_cuts, const double* ratio_steps, const double* z_values, int32_t num_z,
                        const double* one_minus_alpha, const double* alpha_steps, double* out_by_unc,
                        double* out_oracle64, float* out_oracle32, int32_t* out_oracle_is64, double* out_ause,
                        float* out_scalars, double* out_auce_curves, double* out_auc) {
   using namespace ub;
-  UB_REQUIRE(packed && cuts && ratio_steps && z_values && one_minus_alpha && alpha_steps, UB_ERR_BAD_ARG,
+  UB_REQUIRE(packed && num_pixels && cuts && ratio_steps && z_values && one_minus_alpha && alpha_steps, UB_ERR_BAD_ARG,
              "score_tail: NULL input");
   UB_REQUIRE(out_by_unc && out_oracle64 && out_oracle32 && out_oracle_is64 && out_ause && out_scalars &&
                  out_auce_curves && out_auc,
              UB_ERR_BAD_ARG, "score_tail: NULL output");
-  UB_REQUIRE(num_views >= 1 && num_cuts >= 2 && num_cuts <= 128 && num_z >= 2 && num_z <= 127 && n >= 0 && channels >= 1,
+  UB_REQUIRE(num_views >= 1 && num_cuts >= 2 && num_cuts <= 128 && num_z >= 2 && num_z <= 127 && channels >= 1,
              UB_ERR_BAD_ARG, "score_tail: bad sizes");
   const int B = num_views, NC = num_cuts, NZ = num_z;
   const double* sums = packed;                              // [B][4][NC]: ae by var, se by var, ae ascending, se ascending
@@ -77,13 +77,15 @@ int ub_score_tail_host(const double* packed, int32_t num_views, int64_t n, int32
   const double* hist_bits = psums + (size_t)B * 5;          // [B][NZ + 1] int64 bit patterns
   double tmp[128];
   for (int b = 0; b < B; ++b) {
+    const int64_t n = num_pixels[b];                  // pixels of this view (ragged for the masked depth modality)
+    const int64_t* vcuts = cuts + (size_t)b * NC;     // its slice lengths int((1 - r) n)
     const double* s4 = sums + (size_t)b * 4 * NC;
     // rows (mae, mse, rmse): oracle = (ae, se, se) ascending, by-uncertainty = (ae, se, se) by var
     const int by_row[3] = {0, 1, 1}, or_row[3] = {2, 3, 3};
     for (int e = 0; e < 3; ++e) {
       float ora[128], byu32[128];
       for (int k = 0; k < NC; ++k) {
-        const int64_t c = cuts[k];
+        const int64_t c = vcuts[k];
         // float32 value of err_sorted[:c].mean(); an empty slice gives NaN like torch
         float o = c > 0 ? (float)(s4[or_row[e] * NC + k] / (double)c) : NAN;
         float u = c > 0 ? (float)(s4[by_row[e] * NC + k] / (double)c) : NAN;

@@ -361,7 +361,8 @@ class PendingScores:
         return _numpy_tail(packed, self.b, self.n, self.c, self.cuts_one)
 
 
-def _native_tail(packed: np.ndarray, b: int, n: int, c: int, cuts_one: np.ndarray) -> List[Dict[str, object]]:
+def _native_tail(packed: np.ndarray, b: int, n, c: int, cuts_one: np.ndarray, nll_key: str = "nll_rgb"
+                 ) -> List[Dict[str, object]]:
     """The host tail of ``score_rgb_batch`` in one native call (``ub_score_tail_host``, csrc/score_tail.cu): the
     reference's numpy / torch expressions downstream of the device results, operation by operation in the reference's
     dtypes -- bit-identical to ``_numpy_tail`` (tests/test_host_logic.py), ~2 us per image instead of 0.2 ms + 17 us."""
@@ -370,14 +371,18 @@ def _native_tail(packed: np.ndarray, b: int, n: int, c: int, cuts_one: np.ndarra
     lib = _lib.load()
     zh = z_values_host()
     _alpha_tables()
-    nz, nc = len(zh), len(cuts_one)
+    nz = len(zh)
     packed = np.ascontiguousarray(packed, dtype=np.float64)
     cuts = np.ascontiguousarray(cuts_one, dtype=np.int64)
+    if cuts.ndim == 1:                                   # one image size for the whole batch (rgb)
+        cuts = np.ascontiguousarray(np.broadcast_to(cuts, (b, cuts.shape[0])))
+    nc = cuts.shape[1]
+    npix = np.ascontiguousarray(np.broadcast_to(np.asarray(n, dtype=np.int64), (b,)))
     by_unc, o64 = np.empty((b, 3, nc)), np.empty((b, 3, nc))
     o32, is64 = np.empty((b, 3, nc), dtype=np.float32), np.empty((b, 3), dtype=np.int32)
     ause_v, scal = np.empty((b, 3)), np.empty((b, 3), dtype=np.float32)
     curves, auc = np.empty((b, 5, nz)), np.empty((b, 3))
-    _lib.check(lib.ub_score_tail_host(packed.ctypes.data, b, n, c, cuts.ctypes.data, nc, _RATIO_STEPS.ctypes.data,
+    _lib.check(lib.ub_score_tail_host(packed.ctypes.data, b, npix.ctypes.data, c, cuts.ctypes.data, nc, _RATIO_STEPS.ctypes.data,
                                       zh.ctypes.data, nz, _ONE_MINUS_ALPHA.ctypes.data, _ALPHA_STEPS.ctypes.data,
                                       by_unc.ctypes.data, o64.ctypes.data, o32.ctypes.data, is64.ctypes.data,
                                       ause_v.ctypes.data, scal.ctypes.data, curves.ctypes.data, auc.ctypes.data))
@@ -392,7 +397,7 @@ def _native_tail(packed: np.ndarray, b: int, n: int, c: int, cuts_one: np.ndarra
             "err_mae": o64r[j] if w64[j] else o32r[j], "err_var_mae": bur[j], "ause_mae": au[j],
             "err_mse": o64r[j + 1] if w64[j + 1] else o32r[j + 1], "err_var_mse": bur[j + 1], "ause_mse": au[j + 1],
             "err_rmse": o64r[j + 2] if w64[j + 2] else o32r[j + 2], "err_var_rmse": bur[j + 2], "ause_rmse": au[j + 2],
-            "nll_rgb": sc[j], "avg_var": sc[j + 1], "mse_mean": sc[j + 2],
+            nll_key: sc[j], "avg_var": sc[j + 1], "mse_mean": sc[j + 2],
             "coverage_values": cv[q], "avg_length_values": cv[q + 1], "coverage_error_values": cv[q + 2],
             "abs_coverage_error_values": cv[q + 3], "neg_coverage_error_values": cv[q + 4],
             "auc_abs_error_values": ac[j], "auc_length_values": ac[j + 1], "auc_neg_error_values": ac[j + 2],
@@ -497,24 +502,36 @@ def score_depth_batch(depth: Tensor, depth_std: Tensor, depth_gt: Tensor, scales
     total = pred.shape[0]
     z = _z_table(dev)
     select = _use_select(max(lens) if len(lens) else 0)
+    nzp = z.numel() + 1
+    packed_dev = torch.empty(b * (4 * N_RATIOS + 5 + nzp), dtype=torch.float64, device=dev)
+    sums_v, psum_v, hist_v = _packed_views(packed_dev, b, nzp)
     pro = ops.score_prologue(pred, gt, std, lens, z, nll_min_std=min_depth_std_for_nll, sigma_from_var=False,
-                             want_vectors=True, want_coarse=select)
+                             want_vectors=True, want_coarse=select, out_sums=psum_v, out_hist=hist_v.view(torch.int64))
     vec = pro["vectors"]
     cuts = np.stack([ause_cut_counts(n) for n in lens])
-    sums = _ause_sums(vec, lens, cuts, pro.get("coarse"))
-    packed = torch.cat([sums.reshape(b, -1), pro["sums"], pro["hist"].to(torch.float64)], dim=1).cpu().numpy()
+    _ause_sums(vec, lens, cuts, pro.get("coarse"), out=sums_v)
+    packed = packed_dev.cpu().numpy()                      # one device->host copy of the three regions
+    if os.environ.get("UB_NUMPY_TAIL", "0") != "1":
+        return _native_tail(packed, b, np.asarray(lens, dtype=np.int64), 1, cuts, nll_key="nll_depth")
+    return _numpy_depth_tail(packed, b, lens, cuts)
+
+
+def _numpy_depth_tail(packed: np.ndarray, b: int, lens: Sequence[int], cuts: np.ndarray) -> List[Dict[str, object]]:
+    """The depth tail as numpy expressions, one view at a time (ragged lengths); the statement the native tail is
+    checked against."""
     zh = z_values_host()
+    sums_a, psums_a, hist_a = _packed_views(packed, b, len(zh) + 1)
+    hist_i = np.ascontiguousarray(hist_a).view(np.int64)
     results = []
     for i in range(b):
-        row, n, ci = packed[i], lens[i], cuts[i]
-        bu_ae, bu_se, or_ae, or_se = row[0:100], row[100:200], row[200:300], row[300:400]
-        psums = row[400:405]
-        hist = np.rint(row[405:405 + len(zh) + 1]).astype(np.int64)
+        n, ci = lens[i], cuts[i]
+        bu_ae, bu_se, or_ae, or_se = sums_a[i, 0], sums_a[i, 1], sums_a[i, 2], sums_a[i, 3]
+        psums, hist = psums_a[i], hist_i[i]
         d: Dict[str, object] = {}
-        _, d["err_mse"], d["err_var_mse"], d["ause_mse"] = _ause_tail(
-            _prefix_means(or_se, ci, "mse"), _prefix_means(bu_se, ci, "mse"))
         _, d["err_mae"], d["err_var_mae"], d["ause_mae"] = _ause_tail(
             _prefix_means(or_ae, ci, "mae"), _prefix_means(bu_ae, ci, "mae"))
+        _, d["err_mse"], d["err_var_mse"], d["ause_mse"] = _ause_tail(
+            _prefix_means(or_se, ci, "mse"), _prefix_means(bu_se, ci, "mse"))
         _, d["err_rmse"], d["err_var_rmse"], d["ause_rmse"] = _ause_tail(
             _prefix_means(or_se, ci, "rmse"), _prefix_means(bu_se, ci, "rmse"))
         with np.errstate(divide="ignore", invalid="ignore"):
