@@ -202,6 +202,13 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
   const int group_base = lane & ~3;
   const int lane_off = r * S + q * P;
   ChunkBounds bounds;
+  // the (up to) three outputs this lane stores per ray, by its quarter q -- loop-invariant, selected once:
+  //   q == 0: rgb[3 ray + 0, 1, 2]    q == 1: accumulation, depth, expected depth    q == 2: rgb_var, rgb_std    q == 3: depth_var, depth_std
+  float* const out0 = q == 0 ? p.o_rgb : (q == 1 ? p.o_acc : (q == 2 ? p.o_rgb_var : p.o_dvar));
+  float* const out1 = q == 0 ? (p.o_rgb ? p.o_rgb + 1 : nullptr)
+                             : (q == 1 ? p.o_depth : (q == 2 ? p.o_rgb_std : p.o_dstd));
+  float* const out2 = q == 0 ? (p.o_rgb ? p.o_rgb + 2 : nullptr) : (q == 1 ? p.o_exp : nullptr);
+  const int out_mult = q == 0 ? 3 : 1;
 
   for (int j = w; j < my_tiles; j += NCW) {
     const int st = j % NST;
@@ -427,13 +434,10 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
       const float v0 = q == 0 ? cr : (q == 1 ? acc : (q == 2 ? var : dvar));
       const float v1 = q == 0 ? cg : (q == 1 ? depth : sq);
       const float v2 = q == 0 ? cb : e_exp;
-      float* const b0 = q == 0 ? p.o_rgb : (q == 1 ? p.o_acc : (q == 2 ? p.o_rgb_var : p.o_dvar));
-      float* const b1 = q == 0 ? p.o_rgb : (q == 1 ? p.o_depth : (q == 2 ? p.o_rgb_std : p.o_dstd));
-      float* const b2 = q == 0 ? p.o_rgb : (q == 1 ? p.o_exp : nullptr);
-      const size_t at = q == 0 ? (size_t)ray * 3 : (size_t)ray;
-      if (b0) b0[at] = v0;
-      if (b1) b1[at + (q == 0 ? 1 : 0)] = v1;
-      if (b2) b2[at + (q == 0 ? 2 : 0)] = v2;
+      const size_t at = (size_t)ray * out_mult;
+      if (out0) out0[at] = v0;
+      if (out1) out1[at] = v1;
+      if (out2) out2[at] = v2;
       if (p.o_w) {
         float4* ow = reinterpret_cast<float4*>(p.o_w + (size_t)ray * S + q * P);
 #pragma unroll
