@@ -718,7 +718,8 @@ struct ClassifyShared {
   uint32_t rqn[kSelWarps];          // per warp: positions queued for the general path
   uint16_t rq[kSelWarps][kSelTile / kSelWarps];
 };
-// dynamic shared memory: int limb[2 payloads][3 limbs][num_cuts + 1 classes][kSelCols]
+// dynamic shared memory: int limb[2 payloads][3 limbs][num_cuts + 1 classes][kSelCols]; a family with one payload
+// array uses the same words as [3 limbs][num_cuts + 1 classes][2 kSelCols]
 __host__ __device__ inline size_t sel_limb_words(int num_cuts) { return (size_t)2 * 3 * (num_cuts + 1) * kSelCols; }
 
 struct SelScale {
@@ -788,10 +789,12 @@ __device__ __forceinline__ void sel_classify_tiles(const SelParams& p, ClassifyS
   const uint8_t* modes = p.tilemode + (size_t)g * p.max_tiles * kSelMaxHeavy;
   const uint32_t* rows = p.tilecounts + (size_t)g * kSelMaxHeavy * p.max_tiles;
   uint16_t* rq = sh.rq[warp];
-  const uint32_t lstride = (uint32_t)(p.num_cuts + 1) * kSelCols * 4u;  // bytes between the limbs of a payload
-  const uint32_t col0 = smem_u32(limb + (lane & (kSelCols - 1)));       // this lane's column of payload 0
+  // one payload array: its limbs take the whole table, 16 columns instead of 8 (half the bank conflicts)
+  constexpr int kCols = NPAY == 2 ? kSelCols : 2 * kSelCols;
+  const uint32_t lstride = (uint32_t)(p.num_cuts + 1) * kCols * 4u;     // bytes between the limbs of a payload
+  const uint32_t col0 = smem_u32(limb + (lane & (kCols - 1)));          // this lane's column of payload 0
   const uint32_t col1 = col0 + 3u * lstride;
-  constexpr uint32_t kClassBytes = kSelCols * 4u;
+  constexpr uint32_t kClassBytes = kCols * 4u;
 
   if (nt > 0) {  // tables of the tie groups for every tile of the block (no barrier inside the tile loop)
     for (int idx = tid; idx < kSelMaxTilesPerBlock * kSelMaxHeavy; idx += kSelThreads) {
@@ -928,7 +931,7 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
     for (int i = tid; i < nb; i += kSelThreads) sh.map[i] = map[i];
     if (tid < kSelMaxHeavy) sh.heavy[tid] = pl.heavy[tid];
   }
-  const int lwords = (int)sel_limb_words(nc) / (NPAY == 2 ? 1 : 2);  // one payload: only its half is used
+  const int lwords = (int)sel_limb_words(nc);  // two payloads x 8 columns or one payload x 16 columns
   for (int i = tid; i < (kSelMaxCuts + 1) * 2; i += kSelThreads) (&sh.sum[0][0])[i] = 0.0;
   for (int i = tid; i < lwords / 4; i += kSelThreads) reinterpret_cast<int4*>(limb)[i] = make_int4(0, 0, 0, 0);
   if (tid < 2) sh.vmax[tid] = 0u;
@@ -990,16 +993,17 @@ __device__ __forceinline__ void sel_classify_body(const SelParams& p, ClassifySh
 
   __syncthreads();  // all adds of the block done: fold the limb columns into the float64 sums
   double* sp = p.spart + ((size_t)g * p.max_blocks + blockIdx.x) * (size_t)(nc + 1) * 2;
-  const int lstride = (nc + 1) * kSelCols;
+  constexpr int kCols = NPAY == 2 ? kSelCols : 2 * kSelCols;
+  const int lstride = (nc + 1) * kCols;
   for (int i = tid; i < (nc + 1) * 2; i += kSelThreads) {
     const int cls = i >> 1, pidx = i & 1;
     double v = (&sh.sum[0][0])[i];
     if (pidx < NPAY) {
-      const int* w = limb + pidx * 3 * lstride + cls * kSelCols;
+      const int* w = limb + pidx * 3 * lstride + cls * kCols;
       long long t0s = 0, t1s = 0, t2s = 0;
 #pragma unroll
-      for (int c = 0; c < kSelCols; ++c) {
-        const int cc = (c + tid) & (kSelCols - 1);  // threads start at different columns: no bank conflict
+      for (int c = 0; c < kCols; ++c) {
+        const int cc = (c + tid) & (kCols - 1);  // threads start at different columns: no bank conflict
         t0s += w[cc];
         t1s += w[lstride + cc];
         t2s += w[2 * lstride + cc];
