@@ -228,3 +228,32 @@ def test_select_background_of_exact_and_tiny_errors(built_library):
     se = ae * ae
     lens = [n]
     _check(var, ae, se, lens, _ause_cuts(lens))
+
+
+@pytest.mark.parametrize("signed", [False, True])
+def test_select_payloads_that_are_no_family_keys(built_library, signed):
+    """A single family whose payloads are not the key array of any family: the fixed-point scale of the class sums then
+    comes from a scan of each block's own payloads (different scales in different blocks) and so does the knowledge
+    that a payload is negative.  Payload magnitudes vary by 10 orders across the segment, so the blocks do get
+    different scales."""
+    from uncertainty_nerf_gs_b200 import ops
+
+    g = torch.Generator().manual_seed(21 + int(signed))
+    lens = [150000, 70001]
+    n = sum(lens)
+    keys = torch.rand(n, generator=g)
+    ramp = torch.exp(torch.linspace(-12.0, 11.0, n))                   # block to block: very different magnitudes
+    p0 = torch.rand(n, generator=g) * ramp
+    p1 = torch.rand(n, generator=g) / ramp
+    if signed:
+        p0 = p0 * torch.where(torch.rand(n, generator=g) < 0.5, -1.0, 1.0)
+        p1[::3] = -p1[::3]
+    cuts = _ause_cuts(lens)
+    got = ops.cut_select_sums([(keys.cuda(), p0.cuda(), p1.cuda())], lens, cuts).cpu().numpy()
+    want = _reference(keys, [p0, p1], lens, cuts)
+    scale = _scale([p0, p1], lens)
+    assert got.shape == want.shape
+    err = np.abs(got - want) / scale
+    assert err.max() <= TOL, f"max scaled deviation {err.max():.3e}"
+    one = ops.cut_select_sums([(keys.cuda(), p0.cuda(), None)], lens, cuts).cpu().numpy()      # one payload array
+    assert np.abs(one[:, 0] - want[:, 0]).max() / scale[:, 0].max() <= TOL
