@@ -177,9 +177,10 @@ extern "C" int ub_laplace_ll_moments(const float* x, int64_t num_points, int32_t
   // tcgen05 3xTF32 path unless UB_LAPLACE_FMA=1 or the caller's flag forces the fp32-FMA kernel, which also takes the
   // shapes the tensor-core kernel does not (> 304 columns).  rgb head: always.  Density head: the same GEMM with the
   // draws as its N dimension runs 2.4x faster there (0.20 vs 0.49 ms per 1.05 M points), but the tensor core adds
-  // into its float32 accumulator with truncation -- 24 accumulations x ulp(v) -- and exp turns that absolute error of
-  // the pre-activation into a relative error of the output: 1.1e-5 at v ~ 7, outside the 1e-5 contract (sigmoid
-  // damps it by >= 4).  Hence opt-in: UB_LAPLACE_TC_DENSITY=1.
+  // into its float32 accumulator with truncation and exp turns that absolute error of the pre-activation into a
+  // relative error of the output: with one accumulator 1.1e-5 on E[y] at v ~ 7, with the products spread over three
+  // accumulators (what the kernel does) 6.5e-6 on E[y] but 1.5e-5 on E[y^2] -- outside the 1e-5 contract, which the
+  // FMA kernel keeps (7e-6 worst; sigmoid damps the error by >= 4).  Hence opt-in: UB_LAPLACE_TC_DENSITY=1.
   static const bool force_fma = [] { const char* e = getenv("UB_LAPLACE_FMA"); return e && atoi(e) != 0; }();
   static const bool tc_density = [] { const char* e = getenv("UB_LAPLACE_TC_DENSITY"); return e && atoi(e) != 0; }();
   if (!force_fma && !no_tc && (out_dim == 3 || tc_density)) {

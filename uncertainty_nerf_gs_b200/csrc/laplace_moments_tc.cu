@@ -209,6 +209,25 @@ laplace_moments_tc_kernel(const float* __restrict__ x, long long num_points,
     // ---- MMA: one thread issues 2 halves x 8 K-steps x 3 split products, one commit per half ----
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (O == 1) {
+        // One output: the 100 draws fit one accumulator width, so three accumulators (TMEM columns 0 / 160 / 320) take
+        // the products apart -- hi*hi of K-steps 0-3, hi*hi of K-steps 4-7, all cross terms -- and the epilogue adds them
+        // in float32.  The tensor core adds into its accumulator with truncation; after exp an absolute error of the
+        // pre-activation is a relative error of the output, and 24 accumulations into one accumulator cost 1.1e-5 at
+        // v ~ 7.  Four per accumulator (the cross terms are 2^-11 smaller) stay inside the 1e-5 contract.
+        const uint32_t idesc = umma_idesc_tf32(kTcM, kTcN0);
+#pragma unroll
+        for (int ks = 0; ks < kTcH / 8; ++ks) {
+          const uint32_t ko = (uint32_t)ks * 256u;
+          const uint64_t dah = umma_desc(a_hi + ko), dal = umma_desc(a_lo + ko);
+          const uint64_t dbh = umma_desc(b_hi + ko), dbl = umma_desc(b_lo + ko);
+          umma_tf32(tmem + (ks < 4 ? 0u : (uint32_t)kTcN0), dah, dbh, idesc, (ks & 3) ? 1u : 0u);
+          umma_tf32(tmem + 2u * kTcN0, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+          umma_tf32(tmem + 2u * kTcN0, dah, dbl, idesc, 1u);
+        }
+        umma_commit(&sm.mma_bar[0]);
+        umma_commit(&sm.mma_bar[1]);
+      } else {
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const uint32_t d = tmem + (half ? kTcTmemCol1 : 0u);
@@ -224,6 +243,7 @@ laplace_moments_tc_kernel(const float* __restrict__ x, long long num_points,
           umma_tf32(d, dah, dbl, idesc, 1u);
         }
         umma_commit(&sm.mma_bar[half]);
+      }
       }
     }
     prefetch(tile + gridDim.x);  // global loads of the next tile fly while this one is in the tensor core
@@ -244,6 +264,13 @@ laplace_moments_tc_kernel(const float* __restrict__ x, long long num_points,
       const uint32_t col = c0 < kTcN0 ? (uint32_t)c0 : kTcTmemCol1 + (uint32_t)(c0 - kTcN0);
       float v[16];
       tmem_ld16(tmem + lane_base + col, v);
+      if (O == 1) {  // hi*hi of the second half of K, then the cross terms
+        float v1[16], v2[16];
+        tmem_ld16(tmem + lane_base + (uint32_t)kTcN0 + col, v1);
+        tmem_ld16(tmem + lane_base + 2u * kTcN0 + col, v2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(__fadd_rn(v[i], v1[i]), v2[i]);
+      }
       float t[3] = {0.f, 0.f, 0.f}, t2[3] = {0.f, 0.f, 0.f};  // by (i % O), relative to the chunk start
       if (c0 + 16 <= ncols) epilogue_chunk<ACT, O, true>(v, sm.bias + c0, 16, t, t2);
       else epilogue_chunk<ACT, O, false>(v, sm.bias + c0, ncols - c0, t, t2);
@@ -314,7 +341,7 @@ static int launch_tc(const float* x, long long num_points, const float* params, 
 // returns UB_ERR_UNSUPPORTED when the shape does not fit this path (caller falls back to the FMA kernel)
 int launch_laplace_tc(const float* x, long long num_points, const float* params, int n_samples, int out_dim,
                       int act, float* o_mean, float* o_mean2, float* o_sigma2, cudaStream_t stream) {
-  if ((out_dim != 1 && out_dim != 3) || n_samples * out_dim > kTcN) return UB_ERR_UNSUPPORTED;
+  if (out_dim == 3 ? n_samples * 3 > kTcN : (out_dim != 1 || n_samples > kTcN0)) return UB_ERR_UNSUPPORTED;
 #define UB_TC(A)                                                                                              \
   return out_dim == 3 ? launch_tc<A, 3>(x, num_points, params, n_samples, o_mean, o_mean2, o_sigma2, stream) \
                       : launch_tc<A, 1>(x, num_points, params, n_samples, o_mean, o_mean2, o_sigma2, stream)
