@@ -146,7 +146,8 @@ static int launch_laplace(const float* x, long long num_points, const float* par
   const long long groups = (num_points + PTS - 1) / PTS;
   long long blocks = (groups + kLapThreads - 1) / kLapThreads;
   // the parameter table is re-staged per grid-stride iteration: keep the grid persistent-sized
-  const long long cap = (long long)(sm_count() > 0 ? sm_count() : 148) * (smem > 100 * 1024 ? 1 : 2);
+  // (three blocks per SM where the table is small: the density head's 27 KB; 162 registers x 128 threads allow no more)
+  const long long cap = (long long)(sm_count() > 0 ? sm_count() : 148) * (smem > 100 * 1024 ? 1 : (smem > 60 * 1024 ? 2 : 3));
   if (blocks > cap) blocks = cap;
   kern<<<(unsigned)blocks, kLapThreads, smem, stream>>>(x, num_points, params, n_samples, per_fill, act,
                                                         o_mean, o_mean2, o_sigma2);
