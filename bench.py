@@ -846,7 +846,7 @@ def extra_configs2(ctx):
             "laplace_density_head_fma": {"ms": den_ms, "points_per_s": P / (den_ms * 1e-3),
                                          "roofline": {"bound": "tensor", "achieved": flop_den / (den_ms * 1e-3) / 1e12, "peak": 74.0,
                                                       "unit": "TFLOP/s", "frac": flop_den / (den_ms * 1e-3) / 1e12 / 74.0,
-                                                      "peak_source": "fp32-FMA roof (CUDA cores; O=1 is not a GEMM shape)"}},
+                                                      "peak_source": "fp32-FMA roof (CUDA cores; the tcgen05 variant of the density head, 2.4x faster, is opt-in: after exp its E[y^2] leaves the 1e-5 contract)"}},
             "score_200_views": {"ms_per_image": sc_ms / B, "images_per_s": B / (sc_ms * 1e-3), "views_per_call": B,
                                 "roofline": {"bound": "hbm", "bytes_per_pixel": 92, "achieved": 92 * n * B / (sc_ms * 1e-3) / 1e9,
                                              "peak": peak, "unit": "GB/s", "frac": 92 * n * B / (sc_ms * 1e-3) / 1e9 / peak}},
