@@ -437,6 +437,15 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     solo_ms = [a.elapsed_time(b) / cnt for a, b, cnt in solo_timers[1:]]
     comp_solo_ms = sum(solo_ms) / len(solo_ms)
+    # the same calls without the deltas stream (ub_composite_rays_args.deltas == NULL: deltas = ends - starts)
+    lean_members = [{k: v for k, v in mm.items() if k != "deltas"} for mm in members]
+    lean_timers = []
+    for _ in range(3):
+        pipeline.render_members(lean_members, h, w, CHUNK, lean_timers)
+    torch.cuda.synchronize()
+    lean_ms = [a.elapsed_time(b) / cnt for a, b, cnt in lean_timers[1:]]
+    comp_lean_ms = sum(lean_ms) / len(lean_ms)
+    del lean_members
 
     scoring = time_scoring(ctx, members, gt, h, w, steps)
 
@@ -490,7 +499,16 @@ def run_ours(args, rank, world, local_rank):
                              "(second stream); `standalone` = the same call with the device otherwise idle",
                      "standalone": {"ms_per_launch": comp_solo_ms,
                                     "achieved": BYTES_PER_RAY * R / (comp_solo_ms * 1e-3) / 1e9,
-                                    "frac": BYTES_PER_RAY * R / (comp_solo_ms * 1e-3) / 1e9 / peak}},
+                                    "frac": BYTES_PER_RAY * R / (comp_solo_ms * 1e-3) / 1e9 / peak},
+                     "derived_deltas": {"ms_per_launch": comp_lean_ms, "bytes_per_ray": BYTES_PER_RAY - 4 * S,
+                                        "rays_per_s": R / (comp_lean_ms * 1e-3),
+                                        "achieved": (BYTES_PER_RAY - 4 * S) * R / (comp_lean_ms * 1e-3) / 1e9,
+                                        "frac": (BYTES_PER_RAY - 4 * S) * R / (comp_lean_ms * 1e-3) / 1e9 / peak,
+                                        "note": "standalone, deltas == NULL in ub_composite_rays_args: the kernel takes "
+                                                "ends - starts (what RayBundle.get_ray_samples stores as deltas) and reads "
+                                                "one stream less -- SURVEY 8(d)'s 1384 B/ray variant; bit-identical "
+                                                "outputs for such ray samples.  Not the headline: the reference "
+                                                "interface hands deltas over, and so does every other number of this line"}},
         "gpu_launches": run["launches"],
         "host_ms_per_step": run["host_ms_per_step"],
         "clocks": clock_summary,
@@ -655,6 +673,25 @@ def time_e2e(ctx, members, gt, h, w, m, view_id, steps):
            "note": "PCIe / host-memory bound: the pipeline's H2D rate equals the bare pinned->device copy rate measured "
                    "with all ranks copying at once; the per-rank rate falls with N because the ranks share the host's "
                    "memory system (one NUMA node exposed on this box)"}
+    # the same call without the deltas stream (HostViewEvaluator(derive_deltas=True)): 12 % fewer bytes over PCIe
+    del ev, slot
+    torch.cuda.empty_cache()
+    ev = pipeline.HostViewEvaluator(m, R, S, h, w, dev, derive_deltas=True)
+    for _ in range(2):
+        ev(host_members, host_gt, CHUNK)
+    ctx.barrier()
+    t0.record()
+    for _ in range(e_steps):
+        d = ev(host_members, host_gt, CHUNK)
+        rec = pipeline.pack_record(view_id, d)[None, :]
+        if world > 1:
+            pipeline.gather_records(rec, dev, rows_per_rank=1)
+    t1.record()
+    ctx.barrier()
+    l_ms = ctx.max_over_ranks(t0.elapsed_time(t1))
+    out["derived_deltas"] = {"value": m * R * world / (l_ms / e_steps * 1e-3), "unit": UNIT, "ms_per_step": l_ms / e_steps,
+                             "h2d_bytes_per_step": ev.h2d_bytes,
+                             "note": "deltas neither copied nor read (ends - starts in the kernel); not the headline"}
     del host_members, host_gt, ev
     return out
 

@@ -69,7 +69,8 @@ enum {
 
 typedef struct ub_composite_rays_args {
   const float* density;      /* [R,S]                                                        */
-  const float* deltas;       /* [R,S]                                                        */
+  const float* deltas;       /* [R,S]; NULL: ends - starts in float32 (what RaySamples.deltas  */
+                             /* holds after RayBundle.get_ray_samples) -- one stream less     */
   const float* starts;       /* [R,S]                                                        */
   const float* ends;         /* [R,S]                                                        */
   const float* rgb;          /* [R,S,3]                                                      */

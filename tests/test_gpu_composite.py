@@ -254,3 +254,39 @@ def test_batched_members_equal_individual_calls(built_library, num_samples, chun
     assert img[1]["rgb"].shape == (9, 37, 3) and img[0]["depth_std"].shape == (9, 37, 1)
     nine = ops.composite_rays_many([[members[i % 5][k] for k in keys] for i in range(9)])   # more than one C batch
     assert len(nine) == 9 and torch.equal(nine[8]["rgb"], nine[3]["rgb"])
+
+
+@pytest.mark.parametrize("num_rays,num_samples,chunk", [(4096, 48, None), (1001, 48, 512), (7, 48, None), (70000, 48, 1 << 15),
+                                                        (333, 32, None), (500, 64, None), (129, 96, None),
+                                                        (257, 5, None), (300, 50, 64), (64, 256, None)])
+def test_derived_deltas_equal_given_deltas(built_library, num_rays, num_samples, chunk):
+    """``deltas=None`` (ub_composite_rays_args.deltas == NULL): the bin widths are ``ends - starts`` in float32, which is
+    what nerfstudio's ``RayBundle.get_ray_samples`` stores in ``RaySamples.deltas`` -- every output bit for bit the one
+    of the call that is handed that difference, on the TMA path, the generic path and through the NaN-guard redo of the
+    finalize pass; and the oracle on the same inputs within the usual tolerances."""
+    from uncertainty_nerf_gs_b200 import ops
+    from uncertainty_nerf_gs_b200.models.outputs import active_nerfacto_outputs, active_nerfacto_outputs_many
+
+    inp = synthetic.ray_samples(num_rays, num_samples, seed=7 * num_rays + num_samples)
+    inp["deltas"] = inp["ends"] - inp["starts"]
+    if chunk is not None:
+        inp["beta"][::5, 0] = float("inf")      # inf betas in chunks that also hold NaNs: the finalize pass recomputes them
+    dev = _cuda(inp)
+    given = active_nerfacto_outputs(**dev, return_weights=True, rays_per_chunk=chunk)
+    none = dict(dev, deltas=None)
+    derived = active_nerfacto_outputs(**none, return_weights=True, rays_per_chunk=chunk)
+    for k in KEYS + ["weights"]:
+        assert torch.equal(given[k].view(torch.int32), derived[k].view(torch.int32)), k
+    many = active_nerfacto_outputs_many([{k: v for k, v in dev.items() if k != "deltas"}, dev], rays_per_chunk=chunk)
+    for k in KEYS:
+        assert torch.equal(many[0][k].view(torch.int32), given[k].view(torch.int32)), k
+        assert torch.equal(many[1][k].view(torch.int32), given[k].view(torch.int32)), k
+    raw = ops.composite_rays(dev["density"], None, dev["starts"], dev["ends"], dev["rgb"], dev["beta"], beta_mode="raw",
+                             background=(0.25, 0.5, 0.75), eval_mode=False)
+    raw_given = ops.composite_rays(dev["density"], dev["deltas"], dev["starts"], dev["ends"], dev["rgb"], dev["beta"],
+                                   beta_mode="raw", background=(0.25, 0.5, 0.75), eval_mode=False)
+    for k in KEYS:
+        assert torch.equal(raw[k].view(torch.int32), raw_given[k].view(torch.int32)), k
+    if chunk is None:
+        ref = oc.active_nerfacto_outputs(**inp)
+        _check(derived, ref, inp, KEYS, ATOL)

@@ -56,3 +56,25 @@ def test_graphed_score_equals_eager(built_library):
     second = gs.launch().finish()[0]
     _same(second, metrics.score_rgb_batch(p, g, s)[0])
     _same(first, want)
+
+
+def test_host_view_evaluator_with_and_without_the_deltas_stream(built_library):
+    """The end-to-end entry (pinned host ray samples in, metric dict out) equals the device-resident evaluation of the
+    same view; with ``derive_deltas`` the deltas are neither copied nor read and -- for ray samples whose deltas are
+    ``ends - starts``, nerfstudio's invariant -- nothing changes, bit for bit."""
+    from uncertainty_nerf_gs_b200 import pipeline
+
+    h, w, S, M = 24, 40, 48, 3
+    members = [synthetic.ray_samples(h * w, S, seed=11 + i) for i in range(M)]
+    for m in members:
+        m["deltas"] = m["ends"] - m["starts"]
+    gt = synthetic.scoring_image(h, w, seed=3)[2]
+    want = pipeline.evaluate_view([{k: v.cuda() for k, v in m.items()} for m in members], gt.cuda(), h, w, rays_per_chunk=256)
+    host = [{k: v.pin_memory() for k, v in m.items()} for m in members]
+    full = pipeline.HostViewEvaluator(M, h * w, S, h, w, "cuda:0")
+    lean = pipeline.HostViewEvaluator(M, h * w, S, h, w, "cuda:0", derive_deltas=True)
+    assert full.h2d_bytes - lean.h2d_bytes == M * h * w * S * 4
+    for ev in (full, lean, lean):
+        got = ev(host, gt.pin_memory(), 256)
+        for k in want:
+            assert np.array_equal(np.asarray(got[k]), np.asarray(want[k]), equal_nan=True), k

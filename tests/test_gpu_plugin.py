@@ -92,6 +92,24 @@ def test_active_nerfacto_get_outputs_eval_and_backgrounds(stubs):
         assert torch.equal(out["density"], inp["density"])                   # passed through, as in the reference
 
 
+def test_active_nerfacto_get_outputs_with_derived_deltas(stubs, monkeypatch):
+    """``UB_DERIVE_DELTAS=1``: the patched ``get_outputs`` hands the compositor no deltas; for ray samples built the way
+    ``RayBundle.get_ray_samples`` builds them (deltas = ends - starts) every output is bit for bit the default path's."""
+    R, S = 777, 48
+    inp = _cuda(synthetic.ray_samples(R, S, seed=5))
+    inp["deltas"] = inp["ends"] - inp["starts"]
+    lv = [tuple(t.cuda() for t in l) for l in stubs.proposal_levels(R, 5)]
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("UB_DERIVE_DELTAS", flag)
+        model = _active_nerfacto_standin(stubs, inp, lv, chunk=256)
+        with torch.no_grad():
+            outs.append(model.get_outputs(stubs.flat_ray_bundle(R, device="cuda")))
+    assert list(outs[0].keys()) == list(outs[1].keys())
+    for k in outs[0]:
+        assert torch.equal(outs[0][k].view(torch.int32), outs[1][k].view(torch.int32)), k
+
+
 def test_active_nerfacto_camera_chunk_loop(stubs):
     """The inherited ``get_outputs_for_camera_ray_bundle`` calls the replacement once per eval chunk."""
     g = z("ref_composite.npz")

@@ -122,6 +122,11 @@ struct ChunkBounds {
   }
 };
 
+// deltas == NULL: the bin widths are ends - starts in float32, which is what nerfstudio's RayBundle.get_ray_samples stores
+__device__ __forceinline__ float delta_at(const CompositeParams& p, size_t i) {
+  return p.deltas ? p.deltas[i] : __fsub_rn(p.ends[i], p.starts[i]);
+}
+
 // exclusive prefix over the 4 lanes of a ray of the lanes' float64 totals: an inclusive scan in two shuffle-up steps
 // minus the lane's own total (float64 sums of float32 terms: exact, so the association does not matter)
 __device__ __forceinline__ double ray_exclusive_offset(double total, int q, int group_base) {
@@ -160,6 +165,7 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
   const int num_tiles = (int)((p.num_rays + kRaysPerTile - 1) / kRaysPerTile);
   const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool has_beta = p.beta != nullptr;
+  const bool derive = p.deltas == nullptr;  // deltas = ends - starts (what RayBundle.get_ray_samples stores): one stream less
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) {
@@ -183,9 +189,9 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
         const uint32_t sb = (uint32_t)n * S * 4u;  // bytes of one scalar stream
         float* dst = stages + (size_t)st * kStageFloats;
         const size_t off = (size_t)ray0 * S;
-        mbar_arrive_expect_tx(&full_bar[st], sb * (has_beta ? 8u : 7u));
+        mbar_arrive_expect_tx(&full_bar[st], sb * ((has_beta ? 8u : 7u) - (derive ? 1u : 0u)));
         bulk_g2s(dst + 0 * kTileFloats, p.density + off, sb, &full_bar[st]);
-        bulk_g2s(dst + 1 * kTileFloats, p.deltas + off, sb, &full_bar[st]);
+        if (!derive) bulk_g2s(dst + 1 * kTileFloats, p.deltas + off, sb, &full_bar[st]);
         bulk_g2s(dst + 2 * kTileFloats, p.starts + off, sb, &full_bar[st]);
         bulk_g2s(dst + 3 * kTileFloats, p.ends + off, sb, &full_bar[st]);
         if (has_beta) bulk_g2s(dst + 4 * kTileFloats, p.beta + off, sb, &full_bar[st]);
@@ -233,9 +239,18 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
     {
       const float4* a = reinterpret_cast<const float4*>(sb + 0 * kTileFloats + lane_off);
       const float4* b = reinterpret_cast<const float4*>(sb + 1 * kTileFloats + lane_off);
+      const float4* c = reinterpret_cast<const float4*>(sb + 2 * kTileFloats + lane_off);
+      const float4* d = reinterpret_cast<const float4*>(sb + 3 * kTileFloats + lane_off);
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        const float4 x = a[v], y = b[v];
+        const float4 x = a[v];
+        float4 y;
+        if (derive) {
+          const float4 s0 = c[v], s1 = d[v];
+          y = make_float4(__fsub_rn(s1.x, s0.x), __fsub_rn(s1.y, s0.y), __fsub_rn(s1.z, s0.z), __fsub_rn(s1.w, s0.w));
+        } else {
+          y = b[v];
+        }
         dd[4 * v + 0] = __fmul_rn(y.x, x.x);
         dd[4 * v + 1] = __fmul_rn(y.y, x.y);
         dd[4 * v + 2] = __fmul_rn(y.z, x.z);
@@ -498,7 +513,7 @@ __global__ void __launch_bounds__(256) composite_rays_generic(const CompositePar
       if (FROM_WEIGHTS) {
         if (ok) wi = p.weights_in[row + i];
       } else {
-        float ddi = ok ? p.deltas[row + i] * p.density[row + i] : 0.f;
+        float ddi = ok ? delta_at(p, row + i) * p.density[row + i] : 0.f;
         double incl = warp_inclusive_scan((double)ddi, lane);
         // exclusive prefix = carry + inclusive prefix of the previous lane
         double prev = shfl_up_double(FULL_MASK, incl, 1);
@@ -560,7 +575,7 @@ __global__ void __launch_bounds__(256) composite_rays_generic(const CompositePar
         if (FROM_WEIGHTS) {
           if (ok) wi = p.weights_in[row + i];
         } else {
-          float ddi = ok ? p.deltas[row + i] * p.density[row + i] : 0.f;
+          float ddi = ok ? delta_at(p, row + i) * p.density[row + i] : 0.f;
           double incl = warp_inclusive_scan((double)ddi, lane);
           double prev = shfl_up_double(FULL_MASK, incl, 1);
           double excl = lane == 0 ? carry_dd : carry_dd + prev;
@@ -645,7 +660,7 @@ __device__ __forceinline__ void finalize_ray(const CompositeParams& p, long long
       double carry = 0.0;
       float var = 0.f;
       for (int i = 0; i < S; ++i) {
-        const float ddi = p.deltas[row + i] * p.density[row + i];
+        const float ddi = delta_at(p, row + i) * p.density[row + i];
         const float wi = nan_to_num((1.0f - expf(-ddi)) * expf(-(float)carry));
         carry += (double)ddi;
         var += (wi * wi) * nan_to_num(p.beta[row + i]);
@@ -763,8 +778,8 @@ static int composite_prepare(const ub_composite_rays_args* a, void* workspace, s
   UB_REQUIRE(a->num_rays >= 0 && a->num_samples >= 1, UB_ERR_BAD_ARG,
              "composite_rays: bad shape R=%lld S=%d", (long long)a->num_rays, a->num_samples);
   if (a->num_rays == 0) return UB_OK;
-  UB_REQUIRE(a->density && a->deltas && a->starts && a->ends && a->rgb, UB_ERR_BAD_ARG,
-             "composite_rays: density/deltas/starts/ends/rgb must be non-NULL");
+  UB_REQUIRE(a->density && a->starts && a->ends && a->rgb, UB_ERR_BAD_ARG,
+             "composite_rays: density/starts/ends/rgb must be non-NULL");  // deltas == NULL: ends - starts
   UB_REQUIRE(a->background_mode >= UB_BG_LAST_SAMPLE && a->background_mode <= UB_BG_FIXED,
              UB_ERR_BAD_ARG, "composite_rays: bad background_mode %d", a->background_mode);
   UB_REQUIRE(a->beta_mode == UB_BETA_RAW || a->beta_mode == UB_BETA_NAN_GUARD, UB_ERR_BAD_ARG,

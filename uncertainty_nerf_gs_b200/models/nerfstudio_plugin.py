@@ -112,6 +112,12 @@ def active_nerfacto_get_outputs(self, ray_bundle):
             for i, (w, s, e) in enumerate(levels):
                 out[f"prop_depth_{i}"] = ops.render_weights(w.detach(), s, e, want=("depth",))["depth"]
         return out
+    if os.environ.get("UB_DERIVE_DELTAS", "0") == "1":
+        # opt-in: RayBundle.get_ray_samples stores deltas = bin_ends - bin_starts and the same two tensors as the
+        # frustum's starts / ends, so the compositor can take the difference itself and read one stream less
+        # (bit-identical outputs, tests/test_gpu_composite.py).  Off by default: a sampler that fills
+        # RaySamples.deltas any other way would be silently ignored.
+        args = (args[0], None) + args[2:]
     out = mo.active_nerfacto_outputs(*args, background=_background_of(self), eval_mode=True, proposal_levels=levels)
     out["density"] = density
     return out

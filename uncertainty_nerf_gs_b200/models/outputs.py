@@ -19,14 +19,15 @@ Level = Tuple[Tensor, Tensor, Tensor]  # (weights, starts, ends) of one proposal
 STD_KEYS = ("rgb", "depth", "expected_depth")
 
 
-def active_nerfacto_outputs(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor, rgb: Tensor,
+def active_nerfacto_outputs(density: Tensor, deltas: Optional[Tensor], starts: Tensor, ends: Tensor, rgb: Tensor,
                             beta: Tensor, *, background="last_sample", rays_per_chunk: Optional[int] = None,
                             eval_mode: bool = True, proposal_levels: Sequence[Level] = (),
                             return_weights: bool = False, image_hw: Optional[Tuple[int, int]] = None
                             ) -> Dict[str, Tensor]:
     """``ActiveNerfactoModel.get_outputs`` downstream of ``field.forward``
     (reference activenerfacto_model.py:94-127, 150-151).  Inputs ``[R, S, C]``; outputs ``[R, C]``, or
-    ``[H, W, C]`` with ``image_hw`` (the per-camera view the chunk loop of ``get_outputs_for_camera`` builds)."""
+    ``[H, W, C]`` with ``image_hw`` (the per-camera view the chunk loop of ``get_outputs_for_camera`` builds).
+    ``deltas=None``: ``ends - starts``, see ``ops.composite_rays``."""
     o = ops.composite_rays(density, deltas, starts, ends, rgb, beta, background=background,
                            beta_mode="nan_guard", rays_per_chunk=rays_per_chunk, eval_mode=eval_mode,
                            return_weights=return_weights, image_hw=image_hw)
@@ -52,9 +53,9 @@ def active_nerfacto_outputs_many(members: Sequence[Dict[str, Tensor]], *, backgr
                                  rays_per_chunk: Optional[int] = None, image_hw: Optional[Tuple[int, int]] = None
                                  ) -> List[Dict[str, Tensor]]:
     """``active_nerfacto_outputs`` (eval mode) for the M members of one view in one batched call
-    (``ub_composite_rays_batch``).  ``members[i]`` holds ``density, deltas, starts, ends, rgb, beta``; every
-    returned dict has the reference's keys in the reference's order."""
-    res = ops.composite_rays_many([(m["density"], m["deltas"], m["starts"], m["ends"], m["rgb"], m["beta"])
+    (``ub_composite_rays_batch``).  ``members[i]`` holds ``density, deltas, starts, ends, rgb, beta`` (``deltas``
+    absent or None: ``ends - starts``); every returned dict has the reference's keys in the reference's order."""
+    res = ops.composite_rays_many([(m["density"], m.get("deltas"), m["starts"], m["ends"], m["rgb"], m["beta"])
                                    for m in members], background=background, beta_mode="nan_guard",
                                   rays_per_chunk=rays_per_chunk, eval_mode=True, image_hw=image_hw)
     return [{"rgb": o["rgb"], "accumulation": o["accumulation"], "depth": o["depth"],

@@ -94,7 +94,7 @@ def _ray_stream(t: Tensor, name: str, R: int, S: int, C_: int = 1) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
-def composite_rays(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor, rgb: Tensor,
+def composite_rays(density: Tensor, deltas: Optional[Tensor], starts: Tensor, ends: Tensor, rgb: Tensor,
                    beta: Optional[Tensor] = None, *, background: Union[str, Sequence[float], Tensor] = "last_sample",
                    beta_mode: str = "nan_guard", rays_per_chunk: Optional[int] = None,
                    eval_mode: bool = True, return_weights: bool = False,
@@ -102,13 +102,17 @@ def composite_rays(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor
     """One fused pass over ``[R, S]`` ray samples -> rgb, accumulation, median depth, expected depth,
     ``rgb_var = sum w^2 beta``, depth variance (+ std of both).  Outputs are ``[R, C]`` like the
     reference's per-chunk ``get_outputs`` (activenerfacto_model.py:94-127), or ``[H, W, C]`` when
-    ``image_hw = (H, W)`` with ``H * W == R`` (what ``get_outputs_for_camera`` makes of them)."""
+    ``image_hw = (H, W)`` with ``H * W == R`` (what ``get_outputs_for_camera`` makes of them).
+    ``deltas=None``: the bin widths are ``ends - starts`` (float32) -- bit for bit what nerfstudio's
+    ``RayBundle.get_ray_samples`` stores in ``RaySamples.deltas`` -- and the kernel reads one stream less (1384 instead
+    of 1576 B per 48-sample ray)."""
     lib = _lib.load()
     if not isinstance(density, torch.Tensor) or density.dim() not in (2, 3):
         raise ValueError("density: expected [R, S] or [R, S, 1]")
     R, S = int(density.shape[0]), int(density.shape[1])
     density = _ray_stream(density, "density", R, S)
-    deltas = _ray_stream(deltas, "deltas", R, S)
+    if deltas is not None:
+        deltas = _ray_stream(deltas, "deltas", R, S)
     starts = _ray_stream(starts, "starts", R, S)
     ends = _ray_stream(ends, "ends", R, S)
     rgb = _ray_stream(rgb, "rgb", R, S, 3)
@@ -116,7 +120,7 @@ def composite_rays(density: Tensor, deltas: Tensor, starts: Tensor, ends: Tensor
         beta = _ray_stream(beta, "beta", R, S)
     dev = density.device
     args = _lib.CompositeRaysArgs()
-    args.density, args.deltas = density.data_ptr(), deltas.data_ptr()
+    args.density, args.deltas = density.data_ptr(), _ptr(deltas)
     args.starts, args.ends = starts.data_ptr(), ends.data_ptr()
     args.rgb, args.beta = rgb.data_ptr(), _ptr(beta)
     args.num_rays, args.num_samples = R, S
@@ -210,13 +214,14 @@ def composite_rays_many(batches: Sequence[Sequence[Tensor]], *, background: Unio
     for a, batch in zip(arr, batches):
         density, deltas, starts, ends, rgb, beta = batch
         density = _ray_stream(density, "density", R, S)
-        deltas = _ray_stream(deltas, "deltas", R, S)
+        if deltas is not None:
+            deltas = _ray_stream(deltas, "deltas", R, S)
         starts = _ray_stream(starts, "starts", R, S)
         ends = _ray_stream(ends, "ends", R, S)
         rgb = _ray_stream(rgb, "rgb", R, S, 3)
         beta = _ray_stream(beta, "beta", R, S)
         keep.append((density, deltas, starts, ends, rgb, beta))
-        a.density, a.deltas, a.starts, a.ends = density.data_ptr(), deltas.data_ptr(), starts.data_ptr(), ends.data_ptr()
+        a.density, a.deltas, a.starts, a.ends = density.data_ptr(), _ptr(deltas), starts.data_ptr(), ends.data_ptr()
         a.rgb, a.beta = rgb.data_ptr(), beta.data_ptr()
         a.num_rays, a.num_samples = R, S
         a.background_mode = bg_mode

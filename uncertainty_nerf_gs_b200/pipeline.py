@@ -291,7 +291,7 @@ class GraphedViews:
 
     @staticmethod
     def _key(members) -> tuple:
-        return tuple(m[k].data_ptr() for m in members for k in RAY_KEYS)
+        return tuple(0 if m.get(k) is None else m[k].data_ptr() for m in members for k in RAY_KEYS)
 
     def launch(self, members: Sequence[Dict[str, Tensor]], rgb_gt: Tensor, timers: Optional[list] = None) -> PendingView:
         from . import ops
@@ -343,15 +343,21 @@ class GraphedViews:
 class HostViewEvaluator:
     """End-to-end entry: the caller holds one view's member ray samples and ground truth in *pinned host*
     memory; every call copies them to the device on a copy stream (member m+1 uploads while member m
-    composites), runs the pipeline and reads the metric record back."""
+    composites), runs the pipeline and reads the metric record back.  ``derive_deltas``: the members' ``deltas`` are
+    neither copied nor read -- the compositor takes ``ends - starts``, which is what ``RayBundle.get_ray_samples``
+    stores there (12 % fewer bytes over PCIe)."""
 
-    def __init__(self, num_members: int, num_rays: int, num_samples: int, height: int, width: int, device):
+    def __init__(self, num_members: int, num_rays: int, num_samples: int, height: int, width: int, device,
+                 derive_deltas: bool = False):
         self.m, self.r, self.s, self.h, self.w = num_members, num_rays, num_samples, height, width
         self.device = torch.device(device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         shapes = {"density": (num_rays, num_samples, 1), "deltas": (num_rays, num_samples, 1),
                   "starts": (num_rays, num_samples, 1), "ends": (num_rays, num_samples, 1),
                   "rgb": (num_rays, num_samples, 3), "beta": (num_rays, num_samples, 1)}
+        if derive_deltas:
+            del shapes["deltas"]
+        self.keys = tuple(k for k in RAY_KEYS if k in shapes)
         self.slots = [{k: torch.empty(s, device=self.device) for k, s in shapes.items()}
                       for _ in range(num_members)]
         self.gt_dev = torch.empty(height, width, 3, device=self.device)
@@ -365,7 +371,7 @@ class HostViewEvaluator:
         events = []
         with torch.cuda.stream(self.copy_stream):
             for mh, slot in zip(members_host, self.slots):
-                for k in RAY_KEYS:
+                for k in self.keys:
                     slot[k].copy_(mh[k], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
@@ -374,7 +380,7 @@ class HostViewEvaluator:
         outs = []
         for slot, ev in zip(self.slots, events):
             main.wait_event(ev)
-            o = mo.active_nerfacto_outputs(slot["density"], slot["deltas"], slot["starts"], slot["ends"], slot["rgb"],
+            o = mo.active_nerfacto_outputs(slot["density"], slot.get("deltas"), slot["starts"], slot["ends"], slot["rgb"],
                                            slot["beta"], rays_per_chunk=rays_per_chunk, image_hw=(self.h, self.w))
             for k in PER_SAMPLE_KEYS:
                 o.pop(k, None)
