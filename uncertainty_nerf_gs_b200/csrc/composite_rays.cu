@@ -129,8 +129,7 @@ __device__ __forceinline__ float delta_at(const CompositeParams& p, size_t i) {
 
 // exclusive prefix over the 4 lanes of a ray of the lanes' float64 totals: an inclusive scan in two shuffle-up steps
 // minus the lane's own total (float64 sums of float32 terms: exact, so the association does not matter)
-__device__ __forceinline__ double ray_exclusive_offset(double total, int q, int group_base) {
-  (void)group_base;
+__device__ __forceinline__ double ray_exclusive_offset(double total, int q) {
   double v = total;
   double u = shfl_up_double(FULL_MASK, v, 1);
   if (q >= 1) v += u;
@@ -205,7 +204,6 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
   const int w = warp;
   const int r = lane >> 2;  // ray within the tile
   const int q = lane & 3;   // quarter of the ray this lane owns
-  const int group_base = lane & ~3;
   const int lane_off = r * S + q * P;
   ChunkBounds bounds;
   // the (up to) three outputs this lane stores per ray, by its quarter q -- loop-invariant, selected once:
@@ -264,7 +262,7 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
       pre[i] = run;
       run += (double)dd[i];
     }
-    double off = ray_exclusive_offset(run, q, group_base);
+    double off = ray_exclusive_offset(run, q);
 
     // ---- weights ----
     float wgt[P];
@@ -325,7 +323,7 @@ __global__ void __launch_bounds__(32 * (1 + NCW), 1) composite_rays_tma(const Co
       run += (double)wgt[i];
       pre[i] = run;
     }
-    off = ray_exclusive_offset(run, q, group_base);
+    off = ray_exclusive_offset(run, q);
     int first = S;
     const double half_here = kHalf - off;  // off + pre[i] >= kHalf, with the lane's offset moved to the other side
 #pragma unroll
