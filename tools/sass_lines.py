@@ -42,8 +42,9 @@ def main():
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", unit, str(ROOT / "uncertainty_nerf_gs_b200" / "libub200.so")], cwd=td,
                        capture_output=True)
-        cubin = next(Path(td).glob("*.cubin"))
-        dis = subprocess.run(["nvdisasm", "-g", "-c", str(cubin)], capture_output=True, text=True).stdout
+        # `unit` is a substring match (composite_tiles also extracts composite_tiles_bwd): disassemble every hit
+        dis = "\n".join(subprocess.run(["nvdisasm", "-g", "-c", str(cubin)], capture_output=True, text=True).stdout
+                        for cubin in sorted(Path(td).glob("*.cubin")))
     # locate the function by its mangled name containing the kernel string
     line_of = {}
     cur_fn, cur_line, want = None, None, False

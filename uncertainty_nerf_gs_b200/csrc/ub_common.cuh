@@ -169,7 +169,14 @@ __device__ __forceinline__ float splat_sigma(float ca, float cb, float cc, float
   const float c = __fmaf_rn(__fmul_rn(cc, dy), dy, a);
   return __fmaf_rn(__fmul_rn(cb, dx), dy, __fmul_rn(0.5f, c));
 }
-__device__ __forceinline__ float splat_falloff(float sigma) { return __expf(-sigma); }
+// __expf(-sigma) the way gsplat's kernel gets it (built with --use_fast_math): ex2.approx.ftz of the float32 product with
+// log2(e).  Without that flag nvcc wraps the same two instructions in a rescaling path for results below 2^-126
+// (five instructions), which alpha >= 1/255 can never need; in the normal range both give the same bits.
+__device__ __forceinline__ float splat_falloff(float sigma) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(-sigma, 1.4426950408889634f)));
+  return r;
+}
 __device__ __forceinline__ float splat_alpha(float opac, float sigma) {
   return fminf(0.999f, __fmul_rn(opac, splat_falloff(sigma)));
 }
