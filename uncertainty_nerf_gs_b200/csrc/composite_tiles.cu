@@ -54,8 +54,9 @@ struct TileParams {
 template <int CH>
 __global__ void __launch_bounds__(kTileThreads) composite_tiles_kernel(const TileParams p) {
   constexpr int NCOLV = (CH + 2 + 3) / 4;  // float4 records after the first: {cb, cc, c0, c1}, {c2..c5}, ...
-  __shared__ float4 s_geo[kTileThreads];
-  __shared__ float4 s_rec[NCOLV][kTileThreads];
+  // one record per staged splat, {x, y, opacity, conic.a} {conic.b, conic.c, c0, c1} {c2..c5} ...: the per-pixel loop
+  // forms one address per splat and reads its float4s at constant offsets
+  __shared__ float4 s_gr[kTileThreads][1 + NCOLV];
   __shared__ float4 s_box[kTileThreads];
   __shared__ unsigned char s_list[kTileThreads / 32][kTileThreads];  // per warp: staged splats that can touch its block
   __shared__ float s_max[kTileThreads / 32][CH];
@@ -100,11 +101,11 @@ __global__ void __launch_bounds__(kTileThreads) composite_tiles_kernel(const Til
         }
       }
       const float opac = p.opacities[g];
-      s_geo[threadIdx.x] = make_float4(xy.x, xy.y, opac, ca);
-      s_rec[0][threadIdx.x] = make_float4(cb, cc, col[0], col[1]);
+      s_gr[threadIdx.x][0] = make_float4(xy.x, xy.y, opac, ca);
+      s_gr[threadIdx.x][1] = make_float4(cb, cc, col[0], col[1]);
 #pragma unroll
       for (int v = 1; v < NCOLV; ++v)
-        s_rec[v][threadIdx.x] = make_float4(col[4 * v - 2], col[4 * v - 1], col[4 * v], col[4 * v + 1]);
+        s_gr[threadIdx.x][1 + v] = make_float4(col[4 * v - 2], col[4 * v - 1], col[4 * v], col[4 * v + 1]);
       s_box[threadIdx.x] = p.no_cull ? make_float4(-INFINITY, INFINITY, -INFINITY, INFINITY)
                                      : splat_reach_box(xy.x, xy.y, opac, ca, cb, cc);
     }
@@ -128,10 +129,12 @@ __global__ void __launch_bounds__(kTileThreads) composite_tiles_kernel(const Til
       cnt += __popc(m);
     }
     __syncwarp();
-    for (int q = 0; q < cnt && !done; ++q) {
-      const int t = s_list[warp][q];
-      const float4 ga = s_geo[t];
-      const float4 gb = s_rec[0][t];
+    // (the list is walked by its shared-memory address: one induction variable instead of a counter and a pointer)
+    for (uint32_t lp = smem_u32(s_list[warp]), le = lp + (uint32_t)cnt; lp < le && !done; ++lp) {
+      uint32_t t;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t) : "r"(lp));
+      const float4 ga = s_gr[t][0];
+      const float4 gb = s_gr[t][1];
       const float dx = ga.x - px, dy = ga.y - py;
       const float sigma = splat_sigma(ga.w, gb.x, gb.y, dx, dy);
       const float alpha = splat_alpha(ga.z, sigma);
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(kTileThreads) composite_tiles_kernel(const Til
       if (CH > 1) acc[1] += gb.w * vis;
 #pragma unroll
       for (int v = 1; v < NCOLV; ++v) {
-        const float4 r = s_rec[v][t];
+        const float4 r = s_gr[t][1 + v];
         if (4 * v - 2 < CH) acc[4 * v - 2] += r.x * vis;
         if (4 * v - 1 < CH) acc[4 * v - 1] += r.y * vis;
         if (4 * v + 0 < CH) acc[4 * v + 0] += r.z * vis;
